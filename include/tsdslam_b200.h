@@ -1,0 +1,240 @@
+/*
+ * tsdslam_b200 -- C ABI of the B200-native (sm_100a) mapping/localisation hot path of ohm_tsd_slam.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its extension points are the public
+ * classes of namespace obvious, used in-process by ThreadMapping / ThreadLocalize.  Each entry point
+ * below names the reference interface it replaces (file:line relative to the reference tree); the
+ * header-compatible C++ adapter over this ABI lives in ohm_tsd_slam_b200/obvious/ (INTEGRATION.md).
+ *
+ * Conventions
+ *   - every call returns 0 on success, a negative TSD_E_* code otherwise; tsd_last_error() gives text;
+ *   - plain pointers and sizes only; the caller owns all host buffers, the library owns device memory;
+ *   - all floating point is IEEE double, as in the reference (obfloat == double, obcore/base/types.h:28-31);
+ *   - matrices are row-major; a pose is the 3x3 homogeneous matrix of Sensor::getTransformation();
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with TSD_E_NO_DEVICE.
+ *   - one handle = one CUDA stream; calls on one handle are ordered, calls on different handles may
+ *     overlap (the reference itself shares the grid between threads without a lock, ThreadMapping.cpp:46-61).
+ */
+#ifndef TSDSLAM_B200_H
+#define TSDSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSD_OK 0
+#define TSD_E_INVALID (-1)   /* bad argument */
+#define TSD_E_NO_DEVICE (-2) /* no CUDA device / driver: the product has no CPU path */
+#define TSD_E_CUDA (-3)      /* a CUDA runtime call failed */
+#define TSD_E_NOMEM (-4)
+#define TSD_E_RANGE (-5)     /* coordinates outside the grid (freeFootprint) */
+
+/* EnumTsdGridInterpolate, reconstruct/grid/TsdGrid.h:28-31 */
+#define TSD_INTERPOLATE_SUCCESS 0
+#define TSD_INTERPOLATE_INVALIDINDEX 1
+#define TSD_INTERPOLATE_EMPTYPARTITION 2
+#define TSD_INTERPOLATE_ISNAN 3
+
+/* EnumTsdGridPartitionIdentifier, reconstruct/grid/TsdGrid.h:32-34 */
+#define TSD_PARTITION_UNINITIALIZED 0
+#define TSD_PARTITION_EMPTY 1
+#define TSD_PARTITION_CONTENT 2
+
+/* EnumIcpState, registration/icp/Icp.h:25-32 */
+#define TSD_ICP_IDLE 0
+#define TSD_ICP_PROCESSING 1
+#define TSD_ICP_NOTMATCHABLE 2
+#define TSD_ICP_MAXITERATIONS 3
+#define TSD_ICP_TIMEELAPSED 4
+#define TSD_ICP_SUCCESS 5
+#define TSD_ICP_CONVERGED 6
+#define TSD_ICP_ERROR 7
+
+const char* tsd_last_error(void);
+/* number of CUDA devices visible, 0 when there is none */
+int tsd_device_count(void);
+/* total kernel launches issued by this library in this process (bench.py's gpu_launches) */
+uint64_t tsd_kernel_launches(void);
+
+/* Inverse of a 3x3 pose: LU with partial pivoting and column-wise solves, the routine behind
+ * obvious::Matrix::invert (obcore/math/linalg/gsl/Matrix.cpp:168-179) as SensorPolar2D::backProject
+ * (SensorPolar2D.cpp:120-121) and RayCastPolar2D (RayCastPolar2D.cpp:120-121) use it.  Host code. */
+int tsd_invert3x3(const double in[9], double out[9]);
+
+/* What the kernels read out of an obvious::SensorPolar2D (reconstruct/grid/SensorPolar2D.h,
+ * reconstruct/Sensor.h): measurement data + mask, pose and the scalar sensor model. */
+typedef struct tsd_scan
+{
+  int32_t n;             /* Sensor::getRealMeasurementSize() */
+  int32_t _pad;
+  const double* ranges;  /* Sensor::getRealMeasurementData(), host, n */
+  const uint8_t* mask;   /* Sensor::getRealMeasurementMask(), host, n (bool) */
+  double pose[9];        /* Sensor::getTransformation() */
+  double pose_inv[9];    /* its inverse (tsd_invert3x3) */
+  double phi_min;        /* SensorPolar2D::getPhiMin() */
+  double angular_res;    /* SensorPolar2D::getAngularResolution() */
+  double phi_lower;      /* SensorPolar2D::getPhiLowerBound() */
+  double phi_upper;      /* SensorPolar2D::getPhiUpperBound() */
+  double max_range;      /* Sensor::getMaximumRange() */
+  double min_range;      /* Sensor::getMinimumRange() */
+  double low_reflectivity_range; /* Sensor::getLowReflectivityRange() */
+} tsd_scan_t;
+
+/* ------------------------------------------------------------------------------------------------
+ * TsdGrid  (reconstruct/grid/TsdGrid.h, TsdGrid.cpp; partitions: TsdGridPartition.h/.cpp,
+ * classification: TsdGridComponent.cpp:43-124)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tsd_grid tsd_grid_t;
+
+/* TsdGrid::TsdGrid(cellSize, layoutPartition, layoutGrid)  (TsdGrid.cpp:20-23,112-169; SlamNode.cpp:77).
+ * layoutPartition must be 5 (32x32 cells, the only layout the node uses); layoutGrid 5..16.
+ * device: CUDA ordinal.  Cell state of the whole grid is allocated densely in HBM up front. */
+int tsdg_create(double cell_size, int layout_partition, int layout_grid, int device, tsd_grid_t** out);
+
+/* Same grid geometry, but this handle owns only the partition rows [row_begin, row_end) (a band of a
+ * grid sharded over several GPUs, one process per GPU).  Cells outside the band are never touched;
+ * one halo partition row above the band is kept for the replicated borders. */
+int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, int device, int part_row_begin,
+                     int part_row_end, tsd_grid_t** out);
+int tsdg_destroy(tsd_grid_t* grid);
+
+/* TsdGrid::setMaxTruncation (TsdGrid.cpp:206-215; SlamNode.cpp:78).  Must precede the first push. */
+int tsdg_set_max_truncation(tsd_grid_t* grid, double val);
+/* getters of TsdGrid.h:79-150 */
+int tsdg_get_geometry(const tsd_grid_t* grid, int32_t* cells_x, int32_t* cells_y, int32_t* partition_size,
+                      double* cell_size, double* min_x, double* max_x, double* min_y, double* max_y,
+                      double* max_truncation);
+
+/* TsdGrid::freeFootprint (TsdGrid.cpp:609-638; ThreadLocalize.cpp:504).  TSD_E_RANGE when out of bounds. */
+int tsdg_free_footprint(tsd_grid_t* grid, double cx, double cy, double width, double height);
+
+/* TsdGrid::push(SensorPolar2D*) (TsdGrid.cpp:217-284; ThreadMapping.cpp:38,55): classify partitions,
+ * integrate the scan, refresh the replicated borders.  Blocking. */
+int tsdg_push(tsd_grid_t* grid, const tsd_scan_t* scan);
+/* Enqueue only (host buffers are copied before return); tsdg_sync() waits. */
+int tsdg_push_async(tsd_grid_t* grid, const tsd_scan_t* scan);
+int tsdg_sync(tsd_grid_t* grid);
+
+/* Counters of the most recent completed push. */
+typedef struct tsd_push_stats
+{
+  uint64_t cell_updates;     /* cells whose {tsd,weight} were rewritten (addTsd or increaseEmptiness) */
+  uint64_t cell_visits;      /* cells of active partitions */
+  uint32_t active_tiles;     /* partitions that passed isInRange */
+  uint32_t emptied_tiles;    /* partitions on which increaseEmptiness ran (allocated or not) */
+  uint32_t newly_initialized;/* partitions allocated by this push */
+  uint32_t fallback_cells;   /* beam index resolved by the exact slow path */
+} tsd_push_stats_t;
+int tsdg_last_push_stats(tsd_grid_t* grid, tsd_push_stats_t* out);
+
+/* TsdGrid::interpolateBilinear (TsdGrid.h:284-304; TSD_PDFMatching.cpp:241), batched: xy is n x 2. */
+int tsdg_interpolate_bilinear(tsd_grid_t* grid, int32_t n, const double* xy, double* tsd, int32_t* status);
+/* TsdGrid::interpolateNormal (TsdGrid.cpp:517-546), batched; ok[i] = 1 on success. */
+int tsdg_interpolate_normal(tsd_grid_t* grid, int32_t n, const double* xy, double* normals, int32_t* ok);
+
+/* Partition accessors (TsdGrid::getPartitions, TsdGridPartition::isInitialized/isEmpty and the state that
+ * TsdGrid::storeGrid writes, TsdGrid.cpp:548-607).  state[p] is a TSD_PARTITION_* value. */
+int tsdg_num_partitions(const tsd_grid_t* grid, int32_t* n);
+int tsdg_partition_states(tsd_grid_t* grid, int32_t* state, double* init_weight);
+/* (dim+1) x (dim+1) row-major arrays, border row/column included, like TsdGridPartition::_grid.
+ * Returns TSD_E_INVALID for an uninitialised partition. */
+int tsdg_download_partition(tsd_grid_t* grid, int32_t p, double* tsd, double* weight);
+int tsdg_upload_partition(tsd_grid_t* grid, int32_t p, const double* tsd, const double* weight);
+/* Mark every partition initialised with the given cell value (bench: the dense, bandwidth-bound regime). */
+int tsdg_fill(tsd_grid_t* grid, double tsd, double weight);
+
+/* ------------------------------------------------------------------------------------------------
+ * RayCastPolar2D  (reconstruct/grid/RayCastPolar2D.h/.cpp)
+ * rays_world: 2 x n row-major = *Sensor::getNormalizedRayMap(cellSize) (Sensor.cpp:36-48), i.e. world-frame
+ * beam directions of length cellSize.  Outputs are in the SENSOR frame (RayCastPolar2D.cpp:172-177).
+ * ---------------------------------------------------------------------------------------------- */
+/* calcCoordsFromCurrentViewMask (RayCastPolar2D.cpp:113-192; ThreadLocalize.cpp:353): coords/normals are
+ * n x 2, written only where mask[i] != 0; *count = number of hits. */
+int tsdg_raycast_mask(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_world, double* coords,
+                      double* normals, uint8_t* mask, uint32_t* count);
+/* calcCoordsFromCurrentView (RayCastPolar2D.cpp:27-111): compacted, in beam order; *count = doubles written. */
+int tsdg_raycast(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_world, double* coords,
+                 double* normals, uint32_t* count);
+
+/* Sharded grid: per-beam first event of this band.  key[i] = 2*step + (abort ? 1 : 0) (lower wins;
+ * UINT64_MAX = no event); payload[i] = {cx, cy, nx, ny} in the sensor frame (valid for a hit).  The caller
+ * min-reduces the keys over all bands (NCCL) and takes the payload of the winner. */
+int tsdg_raycast_band_keys(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_world,
+                           uint64_t** dev_keys, double** dev_payload);
+/* step counters of the most recent raycast on this handle */
+int tsdg_last_raycast_steps(tsd_grid_t* grid, uint64_t* fine_steps, uint64_t* coarse_steps);
+
+/* ------------------------------------------------------------------------------------------------
+ * Icp + FlannPairAssignment + OutOfBoundsFilter2D + DistanceFilter + ReciprocalFilter +
+ * ClosedFormEstimator2D, wired as ThreadLocalize.cpp:210-225 and run as ThreadLocalize.cpp:571-581.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tsd_icp tsd_icp_t;
+
+/* bounds = {xMin, xMax, yMin, yMax} of OutOfBoundsFilter2D (OutOfBoundsFilter2D.cpp:8-15);
+ * dist_iterations is DistanceFilter's third ctor argument (DistanceFilter.cpp:11-20), the node passes
+ * icp_iterations - 10. */
+int icp_create(uint32_t max_iterations, double dist_max, double dist_min, uint32_t dist_iterations,
+               const double bounds[4], int device, tsd_icp_t** out);
+int icp_destroy(tsd_icp_t* icp);
+/* Icp::reset + OutOfBoundsFilter2D::setPose + setModel + setScene + iterate + getFinalTransformation.
+ * model/normals: n_model x 2, scene: n_scene x 2 (already compacted to valid points); t_init: 4x4 or NULL.
+ * t_out 3x3; *mse is what the reference calls rms (mean squared pair distance, ClosedFormEstimator2D.cpp:59-62). */
+int icp_run(tsd_icp_t* icp, const double* model, const double* normals, int32_t n_model, const double* scene,
+            int32_t n_scene, const double pose[9], const double* t_init, double t_out[9], double* mse,
+            uint32_t* pairs, uint32_t* iterations, int32_t* state);
+/* Parity aid: pair list, mse and accumulated 4x4 of every iteration of the last icp_run.
+ * pair_model/pair_scene: max_it x cap; returns iterations stored through *n_it. */
+int icp_get_trace(tsd_icp_t* icp, int32_t max_it, int32_t cap, uint32_t* pair_model, uint32_t* pair_scene,
+                  int32_t* pair_count, double* mse, double* t_final16, int32_t* n_it);
+
+/* ------------------------------------------------------------------------------------------------
+ * Hypothesis scoring of the RANSAC matchers (registration/ransacMatching/).  A hypothesis is the pair
+ * (model index idx, scene index i) of the reference's trial loops; the kernels rebuild phi and T from
+ * it exactly as TSD_PDFMatching.cpp:206-220 / RandomNormalMatching.cpp:251-263 / PDFMatching.cpp:235-250 do,
+ * skip it when fabs(phi) >= phi_max, and score it.  m/s: n x 2 ray-model matrices, phi_m/phi_s: n.
+ * control: 3 x n_control (homogeneous columns).  The winner is the first best in list order (the
+ * reference's single-thread order: trial ascending, i ascending).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tsd_hypothesis
+{
+  int32_t idx_model;
+  int32_t idx_scene;
+} tsd_hypothesis_t;
+
+typedef struct tsd_matcher tsd_matcher_t;
+int match_create(int device, tsd_matcher_t** out);
+int match_destroy(tsd_matcher_t* m);
+
+/* TSD_PDFMatching.cpp:213-260.  score[h] = product of likelihoods, or -1 when the hypothesis is skipped.
+ * best = index of the first maximum (> 0), -1 when none; t_best 3x3 (identity when none). */
+int match_score_tsd(tsd_matcher_t* m, tsd_grid_t* grid, int32_t n_hyp, const tsd_hypothesis_t* hyps, int32_t n,
+                    const double* model, const double* scene, const double* phi_m, const double* phi_s,
+                    double phi_max, int32_t n_control, const double* control, const double t_sensor[9],
+                    double zrand, double* score, int32_t* best, double t_best[9]);
+
+/* RandomNormalMatching.cpp:255-359.  model_valid: n_valid x 2 points of idxMValid with their orientations
+ * phi_valid (phiM[idxMValid[k]]); phi_control: n_control.  Per hypothesis: cnt_match, max_cnt_match, err_sum
+ * (cnt_match = -1 when skipped).  best follows the reference's ordered predicate (:344-359). */
+int match_score_rnm(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyps, int32_t n, const double* model,
+                    const double* scene, const double* phi_m, const double* phi_s, double phi_max,
+                    int32_t n_control, const double* control, const double* phi_control, int32_t n_valid,
+                    const double* model_valid, const double* phi_valid, double theta_min, double theta_max,
+                    double scale_distance, double scale_orientation, uint32_t cnt_match_thresh, int32_t* cnt_match,
+                    int32_t* max_cnt_match, double* err_sum, int32_t* best, double t_best[9]);
+
+/* PDFMatching.cpp:242-376 + probabilityOfTwoSingleScans (:435-487).  params: zhit zphi zshort zmax zrand
+ * percentagePointsInC rangemax sigphi sighit lamshort maxAngleDiff maxAnglePenalty.  model_angles/model_dists:
+ * n_valid (PDFMatching.cpp:200-204). */
+int match_score_pdf(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyps, int32_t n, const double* model,
+                    const double* scene, const double* phi_m, const double* phi_s, double phi_max,
+                    int32_t n_control, const double* control, int32_t n_valid, const double* model_angles,
+                    const double* model_dists, const double params[12], double* prob, int32_t* fov_count,
+                    int32_t* best, double t_best[9]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSDSLAM_B200_H */
