@@ -117,6 +117,12 @@ int tsdg_push(tsd_grid_t* grid, const tsd_scan_t* scan);
 /* Enqueue only (host buffers are copied before return); tsdg_sync() waits. */
 int tsdg_push_async(tsd_grid_t* grid, const tsd_scan_t* scan);
 int tsdg_sync(tsd_grid_t* grid);
+/* The two halves of tsdg_push_async: copy a scan to the device once, integrate it (again) without any
+ * host-to-device traffic.  Lets a caller keep the measurement resident (bench.py's device-resident leg). */
+int tsdg_stage_scan(tsd_grid_t* grid, const tsd_scan_t* scan);
+int tsdg_push_staged(tsd_grid_t* grid);
+/* The handle's cudaStream_t, for callers that time or order work with CUDA events. */
+void* tsdg_stream(tsd_grid_t* grid);
 
 /* Counters of the most recent completed push. */
 typedef struct tsd_push_stats

@@ -1,0 +1,358 @@
+"""ctypes binding of libtsdslam_b200.so (include/tsdslam_b200.h): the reference-facing call path.
+
+This module is plumbing only.  It fails loudly when the CUDA library is missing or when there is no
+CUDA device: there is no CPU path behind it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+from .scan import Hypothesis, PushStats, Scan, ScanStruct
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_up = C.POINTER(C.c_uint32)
+_bp = C.POINTER(C.c_ubyte)
+_sp = C.POINTER(ScanStruct)
+_hp = C.POINTER(Hypothesis)
+_vpp = C.POINTER(C.c_void_p)
+
+EXPORTS = [
+    "tsd_last_error", "tsd_device_count", "tsd_kernel_launches", "tsd_invert3x3",
+    "tsdg_create", "tsdg_create_band", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
+    "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged",
+    "tsdg_stream", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
+    "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
+    "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
+    "icp_create", "icp_destroy", "icp_run", "icp_get_trace",
+    "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
+]
+
+
+class TsdError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (building if the sources are newer) the CUDA library.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.needs_build():
+        path = _build.build()
+    L = C.CDLL(path)
+    L.tsd_last_error.restype = C.c_char_p
+    L.tsd_kernel_launches.restype = C.c_uint64
+    L.tsd_invert3x3.argtypes = [_dp, _dp]
+    L.tsdg_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, _vpp]
+    L.tsdg_create_band.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vpp]
+    L.tsdg_destroy.argtypes = [C.c_void_p]
+    L.tsdg_set_max_truncation.argtypes = [C.c_void_p, C.c_double]
+    L.tsdg_get_geometry.argtypes = [C.c_void_p, _ip, _ip, _ip] + [_dp] * 6
+    L.tsdg_free_footprint.argtypes = [C.c_void_p] + [C.c_double] * 4
+    L.tsdg_push.argtypes = [C.c_void_p, _sp]
+    L.tsdg_push_async.argtypes = [C.c_void_p, _sp]
+    L.tsdg_stage_scan.argtypes = [C.c_void_p, _sp]
+    L.tsdg_push_staged.argtypes = [C.c_void_p]
+    L.tsdg_sync.argtypes = [C.c_void_p]
+    L.tsdg_stream.restype = C.c_void_p
+    L.tsdg_stream.argtypes = [C.c_void_p]
+    L.tsdg_last_push_stats.argtypes = [C.c_void_p, C.POINTER(PushStats)]
+    L.tsdg_interpolate_bilinear.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
+    L.tsdg_interpolate_normal.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
+    L.tsdg_num_partitions.argtypes = [C.c_void_p, _ip]
+    L.tsdg_partition_states.argtypes = [C.c_void_p, _ip, _dp]
+    L.tsdg_download_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
+    L.tsdg_upload_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
+    L.tsdg_fill.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.tsdg_raycast_mask.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _bp, _up]
+    L.tsdg_raycast.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _up]
+    L.tsdg_last_raycast_steps.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.icp_create.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_uint32, _dp, C.c_int, _vpp]
+    L.icp_destroy.argtypes = [C.c_void_p]
+    L.icp_run.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _up, _up, _ip]
+    L.icp_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _up, _up, _ip, _dp, _dp, _ip]
+    L.match_create.argtypes = [C.c_int, _vpp]
+    L.match_destroy.argtypes = [C.c_void_p]
+    L.match_score_tsd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, _hp, C.c_int32, _dp, _dp, _dp, _dp, C.c_double,
+                                  C.c_int32, _dp, _dp, C.c_double, _dp, _ip, _dp]
+    L.match_score_rnm.argtypes = [C.c_void_p, C.c_int32, _hp, C.c_int32, _dp, _dp, _dp, _dp, C.c_double, C.c_int32, _dp,
+                                  _dp, C.c_int32, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32, _ip,
+                                  _ip, _dp, _ip, _dp]
+    L.match_score_pdf.argtypes = [C.c_void_p, C.c_int32, _hp, C.c_int32, _dp, _dp, _dp, _dp, C.c_double, C.c_int32, _dp,
+                                  C.c_int32, _dp, _dp, _dp, _dp, _ip, _ip, _dp]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise TsdError(f"libtsdslam_b200 error {rc}: {lib().tsd_last_error().decode()}")
+
+
+def device_count() -> int:
+    return int(lib().tsd_device_count())
+
+
+def kernel_launches() -> int:
+    return int(lib().tsd_kernel_launches())
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def invert3x3(m) -> np.ndarray:
+    m = _f64(m)
+    out = np.empty((3, 3))
+    check(lib().tsd_invert3x3(_d(m), _d(out)))
+    return out
+
+
+class Grid:
+    """obvious::TsdGrid on the device."""
+
+    def __init__(self, cell_size: float, layout_partition: int, layout_grid: int, device: int = 0, band=None):
+        h = C.c_void_p()
+        if band is None:
+            check(lib().tsdg_create(cell_size, layout_partition, layout_grid, device, C.byref(h)))
+        else:
+            check(lib().tsdg_create_band(cell_size, layout_partition, layout_grid, device, band[0], band[1], C.byref(h)))
+        self.h = h
+        self.cell_size = cell_size
+        self.dim = 1 << layout_partition
+        self.cells = 1 << layout_grid
+        self.parts_per_side = self.cells // self.dim
+        self.n_partitions = self.parts_per_side ** 2
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tsdg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_max_truncation(self, v):
+        check(lib().tsdg_set_max_truncation(self.h, v))
+
+    @property
+    def bounds(self):
+        v = [C.c_double() for _ in range(4)]
+        check(lib().tsdg_get_geometry(self.h, None, None, None, None, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]),
+                                      C.byref(v[3]), None))
+        return tuple(x.value for x in v)
+
+    def free_footprint(self, cx, cy, w, h) -> bool:
+        rc = lib().tsdg_free_footprint(self.h, cx, cy, w, h)
+        if rc == -5:
+            return False
+        check(rc)
+        return True
+
+    def push(self, scan: Scan):
+        check(lib().tsdg_push(self.h, scan.byref()))
+
+    def push_async(self, scan: Scan):
+        check(lib().tsdg_push_async(self.h, scan.byref()))
+
+    def stage_scan(self, scan: Scan):
+        check(lib().tsdg_stage_scan(self.h, scan.byref()))
+
+    def push_staged(self):
+        check(lib().tsdg_push_staged(self.h))
+
+    def sync(self):
+        check(lib().tsdg_sync(self.h))
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(lib().tsdg_stream(self.h) or 0)
+
+    def last_push_stats(self):
+        st = PushStats()
+        check(lib().tsdg_last_push_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def partition_states(self):
+        st = np.empty(self.n_partitions, dtype=np.int32)
+        iw = np.empty(self.n_partitions)
+        check(lib().tsdg_partition_states(self.h, st.ctypes.data_as(_ip), _d(iw)))
+        return st, iw
+
+    def download_partition(self, p: int):
+        n = (self.dim + 1) ** 2
+        tsd = np.empty(n)
+        w = np.empty(n)
+        if lib().tsdg_download_partition(self.h, p, _d(tsd), _d(w)) != 0:
+            return None
+        return tsd.reshape(self.dim + 1, -1), w.reshape(self.dim + 1, -1)
+
+    def upload_partition(self, p: int, tsd, w):
+        tsd, w = _f64(tsd), _f64(w)
+        check(lib().tsdg_upload_partition(self.h, p, _d(tsd), _d(w)))
+
+    def fill(self, tsd, weight):
+        check(lib().tsdg_fill(self.h, tsd, weight))
+
+    def interpolate_bilinear(self, xy):
+        xy = _f64(xy)
+        tsd = np.empty(len(xy))
+        st = np.empty(len(xy), dtype=np.int32)
+        check(lib().tsdg_interpolate_bilinear(self.h, len(xy), _d(xy), _d(tsd), st.ctypes.data_as(_ip)))
+        return tsd, st
+
+    def interpolate_normal(self, xy):
+        xy = _f64(xy)
+        nn = np.empty((len(xy), 2))
+        ok = np.empty(len(xy), dtype=np.int32)
+        check(lib().tsdg_interpolate_normal(self.h, len(xy), _d(xy), _d(nn), ok.ctypes.data_as(_ip)))
+        return nn, ok
+
+    def raycast_mask(self, scan: Scan, rays_world, coords=None, normals=None):
+        n = scan.n
+        rays = _f64(rays_world)
+        coords = np.zeros((n, 2)) if coords is None else coords
+        normals = np.zeros((n, 2)) if normals is None else normals
+        mask = np.zeros(n, dtype=np.uint8)
+        cnt = C.c_uint32()
+        check(lib().tsdg_raycast_mask(self.h, scan.byref(), _d(rays), _d(coords), _d(normals), mask.ctypes.data_as(_bp),
+                                      C.byref(cnt)))
+        return coords, normals, mask, int(cnt.value)
+
+    def raycast(self, scan: Scan, rays_world):
+        n = scan.n
+        rays = _f64(rays_world)
+        coords = np.zeros(2 * n)
+        normals = np.zeros(2 * n)
+        cnt = C.c_uint32()
+        check(lib().tsdg_raycast(self.h, scan.byref(), _d(rays), _d(coords), _d(normals), C.byref(cnt)))
+        k = int(cnt.value)
+        return coords[:k].reshape(-1, 2), normals[:k].reshape(-1, 2)
+
+    def raycast_steps(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(lib().tsdg_last_raycast_steps(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class Icp:
+    """obvious::Icp wired as ThreadLocalize.cpp:210-225, on the device."""
+
+    def __init__(self, max_iterations, dist_max, dist_min, bounds, device: int = 0):
+        b = _f64(bounds)
+        self.max_iterations = max_iterations
+        h = C.c_void_p()
+        check(lib().icp_create(max_iterations, dist_max, dist_min, (max_iterations - 10) & 0xFFFFFFFF, _d(b), device,
+                               C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().icp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, model, normals, scene, pose, Tinit44=None):
+        model, normals, scene, pose = _f64(model), _f64(normals), _f64(scene), _f64(pose)
+        Ti = None if Tinit44 is None else _f64(Tinit44)
+        T = np.empty((3, 3))
+        mse, pairs, its, st = C.c_double(), C.c_uint32(), C.c_uint32(), C.c_int32()
+        check(lib().icp_run(self.h, _d(model), _d(normals), len(model), _d(scene), len(scene), _d(pose),
+                            None if Ti is None else _d(Ti), _d(T), C.byref(mse), C.byref(pairs), C.byref(its), C.byref(st)))
+        return T, mse.value, pairs.value, its.value, st.value
+
+    def trace(self, cap):
+        mi = self.max_iterations
+        pm = np.zeros((mi, cap), dtype=np.uint32)
+        ps = np.zeros((mi, cap), dtype=np.uint32)
+        pc = np.zeros(mi, dtype=np.int32)
+        mse = np.zeros(mi)
+        Tf = np.zeros((mi, 4, 4))
+        nit = C.c_int32()
+        check(lib().icp_get_trace(self.h, mi, cap, pm.ctypes.data_as(_up), ps.ctypes.data_as(_up), pc.ctypes.data_as(_ip),
+                                  _d(mse), _d(Tf), C.byref(nit)))
+        return nit.value, pm, ps, pc, mse, Tf
+
+
+def _hyps(h):
+    h = np.ascontiguousarray(h, dtype=np.int32).reshape(-1, 2)
+    return h, h.ctypes.data_as(_hp)
+
+
+class Matcher:
+    """Hypothesis scorers of TSD_PDFMatching / RandomNormalMatching / PDFMatching on the device."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        check(lib().match_create(device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().match_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def score_tsd(self, grid: Grid, hyps, M, S, phi_m, phi_s, phi_max, control, t_sensor, zrand):
+        h, hp = _hyps(hyps)
+        M, S, phi_m, phi_s, control, t_sensor = map(_f64, (M, S, phi_m, phi_s, control, t_sensor))
+        score = np.empty(len(h))
+        best = C.c_int32()
+        T = np.empty((3, 3))
+        check(lib().match_score_tsd(self.h, grid.h, len(h), hp, len(M), _d(M), _d(S), _d(phi_m), _d(phi_s), phi_max,
+                                    control.shape[1], _d(control), _d(t_sensor), zrand, _d(score), C.byref(best), _d(T)))
+        return score, best.value, T
+
+    def score_rnm(self, hyps, M, S, phi_m, phi_s, phi_max, control, phi_control, model_valid, phi_valid, theta_min,
+                  theta_max, scale_distance, scale_orientation, cnt_thresh):
+        h, hp = _hyps(hyps)
+        M, S, phi_m, phi_s, control, phi_control, model_valid, phi_valid = map(
+            _f64, (M, S, phi_m, phi_s, control, phi_control, model_valid, phi_valid))
+        cnt = np.empty(len(h), dtype=np.int32)
+        mx = np.empty(len(h), dtype=np.int32)
+        err = np.empty(len(h))
+        best = C.c_int32()
+        T = np.empty((3, 3))
+        check(lib().match_score_rnm(self.h, len(h), hp, len(M), _d(M), _d(S), _d(phi_m), _d(phi_s), phi_max,
+                                    control.shape[1], _d(control), _d(phi_control), len(model_valid), _d(model_valid),
+                                    _d(phi_valid), theta_min, theta_max, scale_distance, scale_orientation, cnt_thresh,
+                                    cnt.ctypes.data_as(_ip), mx.ctypes.data_as(_ip), _d(err), C.byref(best), _d(T)))
+        return cnt, mx, err, best.value, T
+
+    def score_pdf(self, hyps, M, S, phi_m, phi_s, phi_max, control, model_angles, model_dists, params):
+        h, hp = _hyps(hyps)
+        M, S, phi_m, phi_s, control, model_angles, model_dists, params = map(
+            _f64, (M, S, phi_m, phi_s, control, model_angles, model_dists, params))
+        prob = np.empty(len(h))
+        fov = np.empty(len(h), dtype=np.int32)
+        best = C.c_int32()
+        T = np.empty((3, 3))
+        check(lib().match_score_pdf(self.h, len(h), hp, len(M), _d(M), _d(S), _d(phi_m), _d(phi_s), phi_max,
+                                    control.shape[1], _d(control), len(model_angles), _d(model_angles), _d(model_dists),
+                                    _d(params), _d(prob), fov.ctypes.data_as(_ip), C.byref(best), _d(T)))
+        return prob, fov, best.value, T

@@ -1,0 +1,214 @@
+// Shared host/device definitions of libtsdslam_b200 (sm_100a only; built with -fmad=false so that no
+// a*b+c is contracted: the reference is built for baseline x86-64, every product and sum rounds on its own,
+// SURVEY.md App. A.1).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/tsdslam_b200.h"
+#include "beam_index.cuh"
+
+#define TSD_TILE 32               // cells per partition edge (LAYOUT_32x32, SlamNode.cpp:77)
+#define TSD_TILE_CELLS 1024
+#define TSD_TILE_STRIDE 1104      // doubles per partition and array: 1024 interior + 65 border + 15 pad (8832 B = 69 * 128)
+#define TSD_BORDER_OFF 1024       // [0,32): column x=32, rows y=0..31 ; [32,64): row y=32, columns 0..31 ; 64: corner
+#define TSD_MAXWEIGHT 32.0        // reconstruct_defs.h:4
+#define TSD_NOT_OWNED 4           // sample status: partition belongs to another band (sharded grid only)
+
+namespace tsd
+{
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define TSD_CUDA(call)                                                                                   \
+  do                                                                                                     \
+  {                                                                                                      \
+    cudaError_t e__ = (call);                                                                            \
+    if(e__ != cudaSuccess)                                                                               \
+    {                                                                                                    \
+      tsd::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__));      \
+      return (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver) ? TSD_E_NO_DEVICE : TSD_E_CUDA; \
+    }                                                                                                    \
+  } while(0)
+
+#define TSD_LAUNCHED()                                                                                   \
+  do                                                                                                     \
+  {                                                                                                      \
+    tsd::g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
+    TSD_CUDA(cudaGetLastError());                                                                        \
+  } while(0)
+
+// mathbase.h:39-53 -- note the NaN asymmetry: ob_min(a,b) returns b when a is NaN
+__host__ __device__ __forceinline__ double ob_min(double a, double b) { return (a <= b) ? a : b; }
+__host__ __device__ __forceinline__ double ob_max(double a, double b) { return (a >= b) ? a : b; }
+
+// Read-only view of the cell state that the samplers need (raycast, interpolate, TSD matcher).
+struct GridView
+{
+  const double* tsd;     // owned partitions, TSD_TILE_STRIDE doubles each
+  const uint8_t* flags;  // all partitions of the grid: 1 = initialised
+  int cells_x, cells_y;
+  int parts_x, parts_y;
+  int row_begin, row_end;  // owned partition rows
+  double cell_size, inv_cell_size;
+};
+
+// The POD part of tsd_scan_t plus device pointers to the staged measurement.
+struct ScanDev
+{
+  const double* ranges;
+  const uint8_t* mask;
+  int n;
+  double P[9];     // pose
+  double Pi[9];    // pose inverse
+  double max_range, min_range, low_refl;
+  BeamModel bm;
+};
+
+#ifdef __CUDACC__
+
+// TsdGrid::coord2Cell + interpolateBilinear (TsdGrid.h:284-340) + TsdGridPartition::interpolateBilinear
+// (TsdGridPartition.h:214-221).  The replicated border of a partition lives behind its 1024 interior cells.
+__device__ __forceinline__ int sample_bilinear(const GridView& g, double cx, double cy, double* out)
+{
+  const double dCoordX = cx * g.inv_cell_size;
+  const double dCoordY = cy * g.inv_cell_size;
+  int xIdx = __double2int_rd(dCoordX);
+  int yIdx = __double2int_rd(dCoordY);
+  double dx = ((double)xIdx + 0.5) * g.cell_size;
+  double dy = ((double)yIdx + 0.5) * g.cell_size;
+  if(cx < dx) { xIdx--; dx -= g.cell_size; }
+  if(cy < dy) { yIdx--; dy -= g.cell_size; }
+  if((xIdx >= g.cells_x) || (xIdx < 0) || (yIdx >= g.cells_y) || (yIdx < 0)) return TSD_INTERPOLATE_INVALIDINDEX;
+  const int py = yIdx >> 5, px = xIdx >> 5;
+  const int p = py * g.parts_x + px;
+  const int x = xIdx & 31, y = yIdx & 31;
+  if(!g.flags[p]) return TSD_INTERPOLATE_EMPTYPARTITION;
+  if(py < g.row_begin || py >= g.row_end) return TSD_NOT_OWNED;
+  const double wx = fabs((cx - dx) * g.inv_cell_size);
+  const double wy = fabs((cy - dy) * g.inv_cell_size);
+  const double* t = g.tsd + (size_t)(p - g.row_begin * g.parts_x) * TSD_TILE_STRIDE;
+  const int i00 = y * 32 + x;
+  const int i10 = (y == 31) ? (TSD_BORDER_OFF + 32 + x) : (i00 + 32);                 // [y+1][x]
+  const int i01 = (x == 31) ? (TSD_BORDER_OFF + y) : (i00 + 1);                       // [y][x+1]
+  const int i11 = (x == 31) ? ((y == 31) ? (TSD_BORDER_OFF + 64) : (TSD_BORDER_OFF + y + 1))
+                            : ((y == 31) ? (TSD_BORDER_OFF + 32 + x + 1) : (i00 + 33)); // [y+1][x+1]
+  const double g00 = __ldg(t + i00), g10 = __ldg(t + i10), g01 = __ldg(t + i01), g11 = __ldg(t + i11);
+  const double v = g00 * (1. - wy) * (1. - wx) + g10 * wy * (1. - wx) + g01 * (1. - wy) * wx + g11 * wy * wx;
+  *out = v;
+  if(isnan(v)) return TSD_INTERPOLATE_ISNAN;
+  return TSD_INTERPOLATE_SUCCESS;
+}
+
+// TsdGrid::interpolateNormal (TsdGrid.cpp:517-546) + norm2 (mathbase.h:212-218)
+__device__ __forceinline__ bool sample_normal(const GridView& g, double cx, double cy, double* nx, double* ny)
+{
+  double inc = 0, dec = 0;
+  if(sample_bilinear(g, cx + g.cell_size, cy, &inc) != TSD_INTERPOLATE_SUCCESS) return false;
+  if(sample_bilinear(g, cx - g.cell_size, cy, &dec) != TSD_INTERPOLATE_SUCCESS) return false;
+  double n0 = inc - dec;
+  if(sample_bilinear(g, cx, cy + g.cell_size, &inc) != TSD_INTERPOLATE_SUCCESS) return false;
+  if(sample_bilinear(g, cx, cy - g.cell_size, &dec) != TSD_INTERPOLATE_SUCCESS) return false;
+  double n1 = inc - dec;
+  const double len = sqrt(n0 * n0 + n1 * n1);
+  if(!(fabs(len) <= 10e-6))
+  {
+    n0 /= len;
+    n1 /= len;
+  }
+  *nx = n0;
+  *ny = n1;
+  return true;
+}
+
+// `M = T * v` for a 3x3 T and a 3-vector v the way gslcblas dgemm NoTrans x NoTrans does it (k outer,
+// zero coefficients skipped).  Rows 0 and 1 only.
+__device__ __forceinline__ void mat3_vec_nn(const double* T, double v0, double v1, double v2, double* o0, double* o1)
+{
+  double r0 = 0.0, r1 = 0.0;
+  if(T[0] != 0.0) r0 += T[0] * v0;
+  if(T[3] != 0.0) r1 += T[3] * v0;
+  if(T[1] != 0.0) r0 += T[1] * v1;
+  if(T[4] != 0.0) r1 += T[4] * v1;
+  if(T[2] != 0.0) r0 += T[2] * v2;
+  if(T[5] != 0.0) r1 += T[5] * v2;
+  *o0 = r0;
+  *o1 = r1;
+}
+
+#endif  // __CUDACC__
+
+int fill_scan_dev(const tsd_scan_t* scan, ScanDev* out);  // scalars only (pointers are set by the caller)
+
+}  // namespace tsd
+
+// the grid handle is shared between grid.cu, raycast.cu and match.cu
+struct tsd_grid
+{
+  int device;
+  cudaStream_t stream;
+  int layout_grid;
+  int cells_x, cells_y, parts_x, parts_y, n_parts;
+  int row_begin, row_end, n_owned;  // owned partition rows / partitions
+  double cell_size, inv_cell_size, max_truncation;
+  double min_x, max_x, min_y, max_y;
+  bool pushed_once;
+
+  double* d_tsd;
+  double* d_weight;
+  uint8_t* d_flags;    // n_parts
+  double* d_initw;     // n_parts
+  // per-push work lists (capacity n_owned each) and their per-item data
+  uint32_t* d_active;  // bit 31: partition was initialised before this push
+  double* d_active_w;  // 0.01 * partWeight per active item
+  uint32_t* d_emptied;
+  uint32_t* d_pending; // partitions initialised/modified outside push: borders refreshed by the next push
+  uint32_t* d_counters;   // [0] active [1] emptied [2] pending [3] refresh-all flag [4] newly initialised [5] slow cells
+  unsigned long long* d_stats64;  // [0] cell updates
+  double* d_coltab;    // 3 * cells_x : A (0.0 + Pi00*X), B (0.0 + Pi10*X), D ((X-tx)^2)
+  double* d_rowtab;    // 3 * cells_y : A (Pi01*Y), B (Pi11*Y), D ((Y-ty)^2)
+  // sensor model tables
+  double2* d_dirs;
+  int dirs_n;
+  double dirs_phi_min, dirs_res;
+  // staged scan
+  int scan_cap;
+  double* d_ranges;
+  uint8_t* d_mask;
+  double* h_ranges;    // pinned
+  uint8_t* h_mask;     // pinned
+  // raycast buffers (sized with the scan)
+  double* d_rays;
+  double* d_rc_out;        // 4 doubles per beam: cx cy nx ny
+  unsigned long long* d_rc_keys;
+  unsigned long long* d_rc_steps;  // [0] fine [1] coarse
+  double* h_rc_out;        // pinned
+  unsigned long long* h_rc_keys;  // pinned
+  unsigned long long* h_rc_steps; // pinned
+  double* h_rays;          // pinned
+  // generic pinned / device scratch for batched queries
+  size_t scratch_cap;
+  void* d_scratch;
+  void* h_scratch;
+  // stats of the last push (pinned)
+  uint32_t* h_counters;
+  unsigned long long* h_stats64;
+  tsd_push_stats_t last_stats;
+  int sm_count;
+  tsd::ScanDev staged;  // scan staged by tsdg_stage_scan (device pointers + scalars)
+  bool has_staged;
+};
+
+namespace tsd
+{
+int grid_stage_scan(tsd_grid* g, const tsd_scan_t* scan, ScanDev* sd);  // H2D of ranges/mask (+dirs table)
+int grid_ensure_scratch(tsd_grid* g, size_t bytes);
+GridView grid_view(const tsd_grid* g);
+}

@@ -1,0 +1,1184 @@
+// TsdGrid on the device: dense SoA cell state in HBM, scan integration (push), border refresh,
+// bilinear sampling and partition accessors.
+//
+// Reference: src/obvision/reconstruct/grid/TsdGrid.{h,cpp}, TsdGridPartition.{h,cpp},
+// TsdGridComponent.cpp:43-124 (isInRange), SensorPolar2D.cpp:117-135 (backProject).
+//
+// Data layout (DESIGN.md "HBM layout"): two arrays `tsd` and `weight`, one block of TSD_TILE_STRIDE
+// doubles per partition: 32x32 interior cells row-major (8192 B, 128-B aligned) followed by the 65
+// replicated border cells.  One byte `flags` (initialised) and one double `initw` (TsdGridPartition::
+// _initWeight) per partition.  The homogeneous cell-coordinate matrices the reference stores per partition
+// (24.6 KB each) are not stored: they are recomputed from the cell index.
+//
+// One push = 5 launches on the handle's stream:
+//   k_tables    per grid column / row: the pose-inverse products and squared offsets shared by all cells
+//   k_classify  warp per partition: TsdGridComponent::isInRange incl. the emptiness side effect (K1)
+//   k_update    persistent CTAs over the active + emptied lists: addTsd per cell / increaseEmptiness (K2, K3)
+//   k_borders   warp per touched partition: TsdGrid::propagateBorders restricted to what changed (K4)
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tsd
+{
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_error = buf;
+}
+
+int fill_scan_dev(const tsd_scan_t* s, ScanDev* o)
+{
+  o->n = s->n;
+  for(int i = 0; i < 9; i++) { o->P[i] = s->pose[i]; o->Pi[i] = s->pose_inv[i]; }
+  o->max_range = s->max_range;
+  o->min_range = s->min_range;
+  o->low_refl = s->low_reflectivity_range;
+  BeamModel& bm = o->bm;
+  bm.phi_min = s->phi_min;
+  bm.res_inv = 1.0 / s->angular_res;  // SensorPolar2D.cpp:127
+  bm.phi_lower = s->phi_lower;
+  bm.phi_upper = s->phi_upper;
+  bm.phi_min_f = (float)s->phi_min;
+  bm.res_inv_f = (float)bm.res_inv;
+  bm.phi_lower_f = (float)s->phi_lower;
+  bm.phi_upper_f = (float)s->phi_upper;
+  bm.n = s->n;
+  const double pi = 3.14159265358979323846;
+  bm.fast_ok = (s->angular_res > 1e-9 && s->phi_lower >= -pi - 1e-9 && s->phi_upper <= pi + 1e-9 &&
+                s->phi_upper > s->phi_lower && s->n >= 1)
+                   ? 1
+                   : 0;
+  return TSD_OK;
+}
+
+GridView grid_view(const tsd_grid* g)
+{
+  GridView v;
+  v.tsd = g->d_tsd;
+  v.flags = g->d_flags;
+  v.cells_x = g->cells_x;
+  v.cells_y = g->cells_y;
+  v.parts_x = g->parts_x;
+  v.parts_y = g->parts_y;
+  v.row_begin = g->row_begin;
+  v.row_end = g->row_end;
+  v.cell_size = g->cell_size;
+  v.inv_cell_size = g->inv_cell_size;
+  return v;
+}
+
+}  // namespace tsd
+
+using namespace tsd;
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+struct PushParams
+{
+  ScanDev scan;
+  double cell_size;
+  double max_trunc;
+  double inv_max_trunc;  // 1.0 / maxTruncation (TsdGridPartition.cpp:94)
+  int cells_x, cells_y, parts_x, parts_y, n_parts;
+  int row_begin, row_end;
+  double* tsd;
+  double* weight;
+  uint8_t* flags;
+  double* initw;
+  uint32_t* active;
+  double* active_w;
+  uint32_t* emptied;
+  uint32_t* pending;
+  uint32_t* counters;
+  unsigned long long* stats64;
+  const double* coltab;
+  const double* rowtab;
+  const double2* dirs;
+};
+
+// Per grid column X = ((double)ix + 0.5) * cellSize (TsdGridPartition.cpp:127): the two products of
+// SensorPolar2D.cpp:125 that depend on X only, with gslcblas' accumulation order (temp = 0; temp += a*b ...),
+// and the squared offset of TsdGrid.cpp:262.  Same per grid row.
+__global__ void k_tables(PushParams pp, double* coltab, double* rowtab)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* Pi = pp.scan.Pi;
+  if(i < pp.cells_x)
+  {
+    const double X = ((double)i + 0.5) * pp.cell_size;
+    double a = 0.0;
+    a += Pi[0] * X;
+    double b = 0.0;
+    b += Pi[3] * X;
+    const double d = X - pp.scan.P[2];
+    coltab[i] = a;
+    coltab[pp.cells_x + i] = b;
+    coltab[2 * pp.cells_x + i] = d * d;
+  }
+  if(i < pp.cells_y)
+  {
+    const double Y = ((double)i + 0.5) * pp.cell_size;
+    const double d = Y - pp.scan.P[5];
+    rowtab[i] = Pi[1] * Y;
+    rowtab[pp.cells_y + i] = Pi[4] * Y;
+    rowtab[2 * pp.cells_y + i] = d * d;
+  }
+}
+
+// SensorPolar2D::backProject for one homogeneous point, complete (sign of zero included), for the 4 edge
+// points of a partition.
+__device__ __forceinline__ int back_project_edge(const ScanDev& s, const double2* dirs, double X, double Y)
+{
+  const double* P = s.Pi;
+  double tx = 0.0;
+  tx += P[0] * X;
+  tx += P[1] * Y;
+  tx += P[2] * 1.0;
+  double ty = 0.0;
+  ty += P[3] * X;
+  ty += P[4] * Y;
+  ty += P[5] * 1.0;
+  const double cx = 0.0 + 1.0 * tx;
+  const double cy = 0.0 + 1.0 * ty;
+  bool slow;
+  const int k = beam_index(s.bm, dirs, cx, cy, &slow);
+  if(k < 0 && !slow)
+  {
+    // the fast path decides "outside" but not which side when y' is a signed zero: take the exact route
+    if(cy == 0.0) return beam_index_exact(s.bm, cx, cy);
+  }
+  return k;
+}
+
+#define CLASSIFY_WARPS 8
+
+// K1: TsdGridComponent::isInRange (TsdGridComponent.cpp:43-124) for every partition, one warp each.
+__global__ void __launch_bounds__(CLASSIFY_WARPS * 32) k_classify(PushParams pp)
+{
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * CLASSIFY_WARPS + (threadIdx.x >> 5);
+  if(p >= pp.n_parts) return;
+  const ScanDev& s = pp.scan;
+  const int px = p % pp.parts_x, py = p / pp.parts_x;
+  const unsigned int x0 = px * TSD_TILE, y0 = py * TSD_TILE;
+  const double cs = pp.cell_size;
+
+  // TsdGridPartition.cpp:48-70 edge coordinates, centroid, circumradius
+  const double e0x = ((double)x0 + 0.5) * cs;
+  const double e0y = ((double)y0 + 0.5) * cs;
+  const double e1x = ((double)(x0 + TSD_TILE) + 0.5) * cs;
+  const double e2y = ((double)(y0 + TSD_TILE) + 0.5) * cs;
+  const double cenx = (e0x + e1x + e0x + e1x) / 4.0;
+  const double ceny = (e0y + e0y + e2y + e2y) / 4.0;
+  const double ddx = e1x - e0x, ddy = e2y - e0y;
+  const double circumradius = sqrt(ddx * ddx + ddy * ddy) * 0.5;
+
+  const double trx = s.P[2], try_ = s.P[5];
+  // euklideanDistance(pos, centroid) (mathbase.h:369-378)
+  double sqr = 0.0;
+  {
+    const double t0 = trx - cenx;
+    sqr += t0 * t0;
+    const double t1 = try_ - ceny;
+    sqr += t1 * t1;
+  }
+  const double distance = sqrt(sqr);
+  const double closest = distance - circumradius - pp.max_trunc;
+  if(closest > s.max_range) return;
+  const double farthest = distance + circumradius + pp.max_trunc;
+  if(farthest < s.min_range) return;
+
+  // lanes 0..3: the four edge points
+  int idxEdge = 0;
+  if(lane < 4)
+  {
+    const double X = (lane & 1) ? e1x : e0x;
+    const double Y = (lane & 2) ? e2y : e0y;
+    idxEdge = back_project_edge(s, pp.dirs, X, Y);
+  }
+  bool visibleEdge = true;
+  if(idxEdge == -1) { idxEdge = s.n - 1; visibleEdge = false; }
+  else if(idxEdge == -2) { idxEdge = 0; visibleEdge = false; }
+  if(idxEdge > s.n - 1) idxEdge = s.n - 1;  // the reference would read past the scan here
+  const unsigned vis4 = __ballot_sync(0xffffffffu, visibleEdge) & 0xfu;
+  if(vis4 == 0u) return;  // !isAnyEdgeVisible
+  const bool allVisible = (vis4 == 0xfu);
+  int minIdx = idxEdge, maxIdx = idxEdge;
+#pragma unroll
+  for(int o = 1; o < 4; o <<= 1)
+  {
+    const int a = __shfl_xor_sync(0xffffffffu, minIdx, o);
+    const int b = __shfl_xor_sync(0xffffffffu, maxIdx, o);
+    minIdx = min(minIdx, a);
+    maxIdx = max(maxIdx, b);
+  }
+  minIdx = __shfl_sync(0xffffffffu, minIdx, 0);
+  maxIdx = __shfl_sync(0xffffffffu, maxIdx, 0);
+
+  bool vis = false, empty = true;
+  for(int j = minIdx + lane; j <= maxIdx; j += 32)
+  {
+    const double d = s.ranges[j];
+    const bool m = s.mask[j] != 0;
+    vis = vis || ((d > closest) && m);
+    if(isinf(d)) empty = empty && (distance < s.low_refl);
+    else empty = empty && (d > farthest) && m;
+  }
+  if(!__any_sync(0xffffffffu, vis)) return;
+  const bool owned = (py >= pp.row_begin && py < pp.row_end);
+  const bool wasInit = pp.flags[p] != 0;
+  if(allVisible && __all_sync(0xffffffffu, empty))
+  {
+    // increaseEmptiness (TsdGridPartition.cpp:136-164)
+    if(lane == 0)
+    {
+      if(wasInit)
+      {
+        if(owned) pp.emptied[atomicAdd(&pp.counters[1], 1u)] = (uint32_t)p;
+      }
+      else
+      {
+        double w = pp.initw[p];
+        w += 1.0;
+        w = ob_min(w, TSD_MAXWEIGHT);
+        pp.initw[p] = w;
+      }
+      atomicAdd(&pp.counters[6], 1u);
+    }
+    return;
+  }
+  // active: TsdGrid.cpp:237-243
+  if(lane == 0)
+  {
+    double distCentroid = sqrt((cenx - trx) * (cenx - trx) + (ceny - try_) * (ceny - try_));
+    if(distCentroid > s.max_range) distCentroid = s.max_range;
+    double partWeight = (s.max_range - distCentroid) / s.max_range;
+    partWeight *= partWeight;
+    double w = 0.01;  // TsdGridPartition.h:194-196 (the fabs(sd) < _eps branch is dead: _eps < 0)
+    w *= partWeight;
+    if(owned)
+    {
+      const uint32_t slot = atomicAdd(&pp.counters[0], 1u);
+      pp.active[slot] = (uint32_t)p | (wasInit ? 0x80000000u : 0u);
+      pp.active_w[slot] = w;
+    }
+    if(!wasInit)
+    {
+      pp.flags[p] = 1;
+      atomicAdd(&pp.counters[4], 1u);
+    }
+    atomicAdd(&pp.counters[7], 1u);
+  }
+}
+
+#define UPDATE_THREADS 256
+
+// One cell of TsdGrid.cpp:250-274 + TsdGridPartition::addTsd (TsdGridPartition.h:170-212).
+// Returns true when the cell was rewritten.
+__device__ __forceinline__ bool update_cell(const PushParams& pp, const double* s_ranges, const uint8_t* s_mask,
+                                            const double2* s_dirs, double colA, double colB, double colD, double rowA,
+                                            double rowB, double rowD, double wTile, double& tsd, double& weight,
+                                            unsigned& slowCount)
+{
+  const ScanDev& s = pp.scan;
+  const double xs = (colA + rowA) + s.Pi[2] * 1.0;
+  const double ys = (colB + rowB) + s.Pi[5] * 1.0;
+  bool slow;
+  const int index = beam_index(s.bm, s_dirs, xs, ys, &slow);
+  slowCount += slow ? 1u : 0u;
+  if(index < 0) return false;
+  const int idx = min(index, s.n - 1);
+  if(!s_mask[idx]) return false;
+  const double r = s_ranges[idx];
+  const double dist = sqrt(colD + rowD);
+  double sd;
+  if(!isinf(r)) sd = r - dist;
+  else
+  {
+    if(!(dist < s.low_refl)) return false;
+    sd = pp.max_trunc;
+  }
+  if(!(sd >= -pp.max_trunc)) return false;
+  const double tsdNew = ob_min(sd * pp.inv_max_trunc, 1.0);
+  if(isnan(tsd))
+  {
+    tsd = tsdNew;
+    weight += wTile;
+  }
+  else
+  {
+    tsd = (tsd * weight + tsdNew * wTile) / (weight + wTile);
+    weight = ob_min(weight + wTile, TSD_MAXWEIGHT);
+  }
+  return true;
+}
+
+// increaseEmptiness for one cell (TsdGridPartition.cpp:140-157)
+__device__ __forceinline__ void empty_cell(double& tsd, double& weight)
+{
+  if(isnan(tsd))
+  {
+    weight += 1.0;
+    tsd = 1.0;
+  }
+  else
+  {
+    weight = ob_min(weight + 1, TSD_MAXWEIGHT);
+    tsd = (tsd * (weight - 1.0) + 1.0) / weight;
+  }
+}
+
+// K2 + K3.  Persistent CTAs; the scan and the beam-boundary table are staged in shared memory once per CTA.
+// Thread t of 256 owns the cell pair x = 2*(t%16), 2*(t%16)+1 in rows t/16 and t/16 + 16: a warp reads two
+// adjacent 256-B rows (512 contiguous bytes) per 16-byte vector load.
+__global__ void __launch_bounds__(UPDATE_THREADS) k_update(PushParams pp)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ScanDev& s = pp.scan;
+  const int n = s.n;
+  double2* s_dirs = reinterpret_cast<double2*>(smem);
+  double* s_ranges = reinterpret_cast<double*>(s_dirs + (n + 1));
+  uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_ranges + n);
+  for(int i = threadIdx.x; i <= n; i += blockDim.x) s_dirs[i] = pp.dirs[i];
+  for(int i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    s_ranges[i] = s.ranges[i];
+    s_mask[i] = s.mask[i];
+  }
+  __syncthreads();
+
+  const uint32_t nActive = pp.counters[0];
+  const uint32_t nEmptied = pp.counters[1];
+  const int t = threadIdx.x;
+  const int xp = (t & 15) * 2;
+  const int yb = t >> 4;
+  unsigned long long updates = 0;
+  unsigned slowCount = 0;
+
+  for(uint32_t item = blockIdx.x; item < nActive + nEmptied; item += gridDim.x)
+  {
+    if(item < nActive)
+    {
+      const uint32_t e = pp.active[item];
+      const uint32_t p = e & 0x7fffffffu;
+      const bool wasInit = (e & 0x80000000u) != 0;
+      const double wTile = pp.active_w[item];
+      const int px = p % pp.parts_x, py = p / pp.parts_x;
+      const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+      double* T = pp.tsd + base;
+      double* W = pp.weight + base;
+      const int gx = px * TSD_TILE + xp;
+      const double2 cA = *reinterpret_cast<const double2*>(pp.coltab + gx);
+      const double2 cB = *reinterpret_cast<const double2*>(pp.coltab + pp.cells_x + gx);
+      const double2 cD = *reinterpret_cast<const double2*>(pp.coltab + 2 * pp.cells_x + gx);
+      double initT = 0.0, initW = 0.0;
+      if(!wasInit)
+      {
+        // TsdGridPartition::init (TsdGridPartition.cpp:98-119)
+        initW = pp.initw[p];
+        initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
+      }
+#pragma unroll
+      for(int j = 0; j < 2; j++)
+      {
+        const int y = yb + 16 * j;
+        const int gy = py * TSD_TILE + y;
+        const double rA = pp.rowtab[gy];
+        const double rB = pp.rowtab[pp.cells_y + gy];
+        const double rD = pp.rowtab[2 * pp.cells_y + gy];
+        const int ci = y * TSD_TILE + xp;
+        double2 tv, wv;
+        if(wasInit)
+        {
+          tv = *reinterpret_cast<const double2*>(T + ci);
+          wv = *reinterpret_cast<const double2*>(W + ci);
+        }
+        else
+        {
+          tv = make_double2(initT, initT);
+          wv = make_double2(initW, initW);
+        }
+        const bool u0 = update_cell(pp, s_ranges, s_mask, s_dirs, cA.x, cB.x, cD.x, rA, rB, rD, wTile, tv.x, wv.x, slowCount);
+        const bool u1 = update_cell(pp, s_ranges, s_mask, s_dirs, cA.y, cB.y, cD.y, rA, rB, rD, wTile, tv.y, wv.y, slowCount);
+        updates += (u0 ? 1 : 0) + (u1 ? 1 : 0);
+        if(!wasInit || u0 || u1)
+        {
+          *reinterpret_cast<double2*>(T + ci) = tv;
+          *reinterpret_cast<double2*>(W + ci) = wv;
+        }
+      }
+      if(!wasInit && t < 65)
+      {
+        T[TSD_BORDER_OFF + t] = initT;
+        W[TSD_BORDER_OFF + t] = initW;
+      }
+    }
+    else
+    {
+      // K3: increaseEmptiness on an initialised partition, all 33x33 cells
+      const uint32_t p = pp.emptied[item - nActive];
+      const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+      double* T = pp.tsd + base;
+      double* W = pp.weight + base;
+#pragma unroll
+      for(int j = 0; j < 2; j++)
+      {
+        const int ci = (yb + 16 * j) * TSD_TILE + xp;
+        double2 tv = *reinterpret_cast<const double2*>(T + ci);
+        double2 wv = *reinterpret_cast<const double2*>(W + ci);
+        empty_cell(tv.x, wv.x);
+        empty_cell(tv.y, wv.y);
+        *reinterpret_cast<double2*>(T + ci) = tv;
+        *reinterpret_cast<double2*>(W + ci) = wv;
+      }
+      if(t < 65)
+      {
+        double tv = T[TSD_BORDER_OFF + t], wv = W[TSD_BORDER_OFF + t];
+        empty_cell(tv, wv);
+        T[TSD_BORDER_OFF + t] = tv;
+        W[TSD_BORDER_OFF + t] = wv;
+      }
+      if(t == 0) updates += 33 * 33;
+    }
+  }
+
+  // one atomic per CTA
+  __shared__ unsigned long long s_upd[UPDATE_THREADS / 32];
+  __shared__ unsigned s_slow[UPDATE_THREADS / 32];
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1)
+  {
+    updates += __shfl_xor_sync(0xffffffffu, updates, o);
+    slowCount += __shfl_xor_sync(0xffffffffu, slowCount, o);
+  }
+  if((t & 31) == 0) { s_upd[t >> 5] = updates; s_slow[t >> 5] = slowCount; }
+  __syncthreads();
+  if(t == 0)
+  {
+    unsigned long long u = 0;
+    unsigned sl = 0;
+    for(int i = 0; i < UPDATE_THREADS / 32; i++) { u += s_upd[i]; sl += s_slow[i]; }
+    if(u) atomicAdd(&pp.stats64[0], u);
+    if(sl) atomicAdd(&pp.counters[5], sl);
+  }
+}
+
+// K4: TsdGrid::propagateBorders (TsdGrid.cpp:372-427) restricted to the partitions whose cells changed
+// in this push (active, emptied) or since the last one (pending): a touched partition refreshes its own
+// right/top/corner border from its +x/+y/+xy neighbours, and the border of its -x/-y/-xy neighbours that
+// mirrors its first column / row / cell.  Untouched pairs keep the values of the previous push, which is
+// what the reference's full pass would rewrite them with.
+__device__ __forceinline__ void refresh_borders_of(const PushParams& pp, int px, int py, int lane)
+{
+  // cur = (px,py) must be initialised and owned
+  const int p = py * pp.parts_x + px;
+  const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+  double* T = pp.tsd + base;
+  double* W = pp.weight + base;
+  if(px < pp.parts_x - 1 && pp.flags[p + 1])
+  {
+    const size_t nb = base + TSD_TILE_STRIDE;
+    T[TSD_BORDER_OFF + lane] = pp.tsd[nb + lane * TSD_TILE];
+    W[TSD_BORDER_OFF + lane] = pp.weight[nb + lane * TSD_TILE];
+  }
+  if(py < pp.parts_y - 1 && py + 1 < pp.row_end && pp.flags[p + pp.parts_x])
+  {
+    const size_t nb = base + (size_t)pp.parts_x * TSD_TILE_STRIDE;
+    T[TSD_BORDER_OFF + 32 + lane] = pp.tsd[nb + lane];
+    W[TSD_BORDER_OFF + 32 + lane] = pp.weight[nb + lane];
+  }
+  if(lane == 0 && px < pp.parts_x - 1 && py < pp.parts_y - 1 && py + 1 < pp.row_end && pp.flags[p + pp.parts_x + 1])
+  {
+    const size_t nb = base + (size_t)(pp.parts_x + 1) * TSD_TILE_STRIDE;
+    T[TSD_BORDER_OFF + 64] = pp.tsd[nb];
+    W[TSD_BORDER_OFF + 64] = pp.weight[nb];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_borders(PushParams pp, int all)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  if(all || pp.counters[3])
+  {
+    for(int p = pp.row_begin * pp.parts_x + warp; p < pp.row_end * pp.parts_x; p += nwarps)
+      if(pp.flags[p]) refresh_borders_of(pp, p % pp.parts_x, p / pp.parts_x, lane);
+    return;
+  }
+  const uint32_t nA = pp.counters[0], nE = pp.counters[1], nP = pp.counters[2];
+  for(uint32_t item = warp; item < nA + nE + nP; item += nwarps)
+  {
+    uint32_t p;
+    if(item < nA) p = pp.active[item] & 0x7fffffffu;
+    else if(item < nA + nE) p = pp.emptied[item - nA];
+    else p = pp.pending[item - nA - nE];
+    const int px = p % pp.parts_x, py = p / pp.parts_x;
+    if(!pp.flags[p]) continue;
+    refresh_borders_of(pp, px, py, lane);
+    // neighbours whose border mirrors this partition
+    if(px > 0 && pp.flags[p - 1]) refresh_borders_of(pp, px - 1, py, lane);
+    if(py > pp.row_begin && pp.flags[p - pp.parts_x]) refresh_borders_of(pp, px, py - 1, lane);
+    if(px > 0 && py > pp.row_begin && pp.flags[p - pp.parts_x - 1]) refresh_borders_of(pp, px - 1, py - 1, lane);
+  }
+}
+
+// TsdGrid::freeFootprint (TsdGrid.cpp:609-638), phase 1: initialise the partitions under the footprint
+__global__ void k_footprint_init(PushParams pp, int pxMin, int pxMax, int pyMin, int pyMax)
+{
+  const int w = pxMax - pxMin + 1;
+  const int tile = blockIdx.x;
+  const int px = pxMin + tile % w, py = pyMin + tile / w;
+  if(py > pyMax) return;
+  const int p = py * pp.parts_x + px;
+  if(pp.flags[p]) return;
+  if(py >= pp.row_begin && py < pp.row_end)
+  {
+    const double initW = pp.initw[p];
+    const double initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
+    const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+    for(int i = threadIdx.x; i < TSD_BORDER_OFF + 65; i += blockDim.x)
+    {
+      pp.tsd[base + i] = initT;
+      pp.weight[base + i] = initW;
+    }
+    if(threadIdx.x == 0) pp.pending[atomicAdd(&pp.counters[2], 1u)] = (uint32_t)p;
+  }
+  __syncthreads();
+  if(threadIdx.x == 0) pp.flags[p] = 1;
+}
+
+// phase 2: tsd = TSDINC for every cell of the footprint rectangle
+__global__ void k_footprint_set(PushParams pp, unsigned minX, unsigned maxX, unsigned minY, unsigned maxY)
+{
+  const unsigned w = maxX - minX;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(w == 0 || i >= w * (maxY - minY)) return;
+  const unsigned cols = minX + i % w, rows = minY + i / w;
+  const int py = rows >> 5, px = cols >> 5;
+  if(py < pp.row_begin || py >= pp.row_end) return;
+  const int p = py * pp.parts_x + px;
+  const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+  pp.tsd[base + (rows & 31) * TSD_TILE + (cols & 31)] = 1.0;
+}
+
+__global__ void k_fill(PushParams pp, double tsd, double weight)
+{
+  const size_t total = (size_t)(pp.row_end - pp.row_begin) * pp.parts_x * TSD_TILE_STRIDE;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+  {
+    pp.tsd[i] = tsd;
+    pp.weight[i] = weight;
+  }
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)pp.n_parts; i += (size_t)gridDim.x * blockDim.x)
+    pp.flags[i] = 1;
+}
+
+__global__ void k_interpolate(GridView g, int n, const double* xy, double* tsd, int* status)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  double v = __longlong_as_double(0x7ff8000000000000LL);
+  status[i] = sample_bilinear(g, xy[2 * i], xy[2 * i + 1], &v);
+  tsd[i] = v;
+}
+
+__global__ void k_interpolate_normal(GridView g, int n, const double* xy, double* normals, int* ok)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  double nx = __longlong_as_double(0x7ff8000000000000LL), ny = nx;
+  ok[i] = sample_normal(g, xy[2 * i], xy[2 * i + 1], &nx, &ny) ? 1 : 0;
+  normals[2 * i] = nx;
+  normals[2 * i + 1] = ny;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+
+static PushParams make_params(const tsd_grid* g)
+{
+  PushParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.cell_size = g->cell_size;
+  pp.max_trunc = g->max_truncation;
+  pp.inv_max_trunc = 1.0 / g->max_truncation;
+  pp.cells_x = g->cells_x;
+  pp.cells_y = g->cells_y;
+  pp.parts_x = g->parts_x;
+  pp.parts_y = g->parts_y;
+  pp.n_parts = g->n_parts;
+  pp.row_begin = g->row_begin;
+  pp.row_end = g->row_end;
+  pp.tsd = g->d_tsd;
+  pp.weight = g->d_weight;
+  pp.flags = g->d_flags;
+  pp.initw = g->d_initw;
+  pp.active = g->d_active;
+  pp.active_w = g->d_active_w;
+  pp.emptied = g->d_emptied;
+  pp.pending = g->d_pending;
+  pp.counters = g->d_counters;
+  pp.stats64 = g->d_stats64;
+  pp.coltab = g->d_coltab;
+  pp.rowtab = g->d_rowtab;
+  pp.dirs = g->d_dirs;
+  return pp;
+}
+
+namespace tsd
+{
+
+int grid_ensure_scratch(tsd_grid* g, size_t bytes)
+{
+  if(bytes <= g->scratch_cap) return TSD_OK;
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  if(g->d_scratch) cudaFree(g->d_scratch);
+  if(g->h_scratch) cudaFreeHost(g->h_scratch);
+  g->d_scratch = g->h_scratch = nullptr;
+  g->scratch_cap = 0;
+  size_t cap = 1 << 16;
+  while(cap < bytes) cap <<= 1;
+  TSD_CUDA(cudaMalloc(&g->d_scratch, cap));
+  TSD_CUDA(cudaMallocHost(&g->h_scratch, cap));
+  g->scratch_cap = cap;
+  return TSD_OK;
+}
+
+static int ensure_scan_capacity(tsd_grid* g, int n)
+{
+  if(n <= g->scan_cap) return TSD_OK;
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  cudaFree(g->d_ranges); cudaFree(g->d_mask); cudaFree(g->d_dirs); cudaFree(g->d_rays); cudaFree(g->d_rc_out);
+  cudaFree(g->d_rc_keys);
+  cudaFreeHost(g->h_ranges); cudaFreeHost(g->h_mask); cudaFreeHost(g->h_rc_out); cudaFreeHost(g->h_rc_keys);
+  cudaFreeHost(g->h_rays);
+  const int cap = ((n + 63) / 64) * 64 + 64;
+  TSD_CUDA(cudaMalloc(&g->d_ranges, sizeof(double) * cap));
+  TSD_CUDA(cudaMalloc(&g->d_mask, cap));
+  TSD_CUDA(cudaMalloc(&g->d_dirs, sizeof(double2) * (cap + 1)));
+  TSD_CUDA(cudaMalloc(&g->d_rays, sizeof(double) * 2 * cap));
+  TSD_CUDA(cudaMalloc(&g->d_rc_out, sizeof(double) * 4 * cap));
+  TSD_CUDA(cudaMalloc(&g->d_rc_keys, sizeof(unsigned long long) * cap));
+  TSD_CUDA(cudaMallocHost(&g->h_ranges, sizeof(double) * cap));
+  TSD_CUDA(cudaMallocHost(&g->h_mask, cap));
+  TSD_CUDA(cudaMallocHost(&g->h_rc_out, sizeof(double) * 4 * cap));
+  TSD_CUDA(cudaMallocHost(&g->h_rc_keys, sizeof(unsigned long long) * cap));
+  TSD_CUDA(cudaMallocHost(&g->h_rays, sizeof(double) * 2 * cap));
+  g->scan_cap = cap;
+  g->dirs_n = -1;
+  return TSD_OK;
+}
+
+int grid_stage_scan(tsd_grid* g, const tsd_scan_t* scan, ScanDev* sd)
+{
+  if(!scan || scan->n < 1 || !scan->ranges || !scan->mask) { set_error("invalid scan"); return TSD_E_INVALID; }
+  int rc = ensure_scan_capacity(g, scan->n);
+  if(rc) return rc;
+  fill_scan_dev(scan, sd);
+  // the previous call's async copies out of the pinned staging buffers must have drained
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  memcpy(g->h_ranges, scan->ranges, sizeof(double) * scan->n);
+  memcpy(g->h_mask, scan->mask, scan->n);
+  TSD_CUDA(cudaMemcpyAsync(g->d_ranges, g->h_ranges, sizeof(double) * scan->n, cudaMemcpyHostToDevice, g->stream));
+  TSD_CUDA(cudaMemcpyAsync(g->d_mask, g->h_mask, scan->n, cudaMemcpyHostToDevice, g->stream));
+  sd->ranges = g->d_ranges;
+  sd->mask = g->d_mask;
+  if(g->dirs_n != scan->n || g->dirs_phi_min != scan->phi_min || g->dirs_res != scan->angular_res)
+  {
+    // directions of the half-beam boundaries B_k = phiMin + (k - 1/2) res, k = 0..n (beam_index.cuh)
+    std::vector<double2> dirs(scan->n + 1);
+    for(int k = 0; k <= scan->n; k++)
+    {
+      const double b = scan->phi_min + ((double)k - 0.5) * scan->angular_res;
+      dirs[k].x = cos(b);
+      dirs[k].y = sin(b);
+    }
+    TSD_CUDA(cudaMemcpyAsync(g->d_dirs, dirs.data(), sizeof(double2) * (scan->n + 1), cudaMemcpyHostToDevice, g->stream));
+    TSD_CUDA(cudaStreamSynchronize(g->stream));
+    g->dirs_n = scan->n;
+    g->dirs_phi_min = scan->phi_min;
+    g->dirs_res = scan->angular_res;
+  }
+  return TSD_OK;
+}
+
+}  // namespace tsd
+
+extern "C" {
+
+const char* tsd_last_error(void) { return tsd::t_error.c_str(); }
+
+int tsd_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+uint64_t tsd_kernel_launches(void) { return tsd::g_launches.load(); }
+
+// Same statement order as the GSL-shim LU the oracle runs (oracle/shim/gsl_shim.c, oracle/port/grid.c):
+// partial pivoting with first maximum, reciprocal scaling, rank-1 update, column-wise forward/back solves.
+int tsd_invert3x3(const double in[9], double out[9])
+{
+  if(!in || !out) return TSD_E_INVALID;
+  double A[3][3];
+  int perm[3] = {0, 1, 2};
+  for(int i = 0; i < 3; i++) for(int j = 0; j < 3; j++) A[i][j] = in[3 * i + j];
+  for(int j = 0; j < 3; j++)
+  {
+    double max = fabs(A[j][j]);
+    int ip = j;
+    for(int i = j + 1; i < 3; i++)
+    {
+      const double a = fabs(A[i][j]);
+      if(a > max) { max = a; ip = i; }
+    }
+    if(ip != j)
+    {
+      for(int k = 0; k < 3; k++) { const double t = A[j][k]; A[j][k] = A[ip][k]; A[ip][k] = t; }
+      const int t = perm[j]; perm[j] = perm[ip]; perm[ip] = t;
+    }
+    const double ajj = A[j][j];
+    if(fabs(ajj) >= 2.2250738585072014e-308)
+    {
+      const double inv = 1.0 / ajj;
+      for(int i = j + 1; i < 3; i++) A[i][j] *= inv;
+    }
+    else
+    {
+      for(int i = j + 1; i < 3; i++) A[i][j] /= ajj;
+    }
+    for(int i = j + 1; i < 3; i++)
+    {
+      const double tmp = -1.0 * A[i][j];
+      for(int k = j + 1; k < 3; k++) A[i][k] += A[j][k] * tmp;
+    }
+  }
+  for(int c = 0; c < 3; c++)
+  {
+    double x[3];
+    for(int i = 0; i < 3; i++) x[i] = (perm[i] == c) ? 1.0 : 0.0;
+    for(int i = 1; i < 3; i++)
+    {
+      double t = x[i];
+      for(int j = 0; j < i; j++) t -= A[i][j] * x[j];
+      x[i] = t;
+    }
+    x[2] = x[2] / A[2][2];
+    for(int i = 1; i >= 0; i--)
+    {
+      double t = x[i];
+      for(int j = i + 1; j < 3; j++) t -= A[i][j] * x[j];
+      x[i] = t / A[i][i];
+    }
+    for(int i = 0; i < 3; i++) out[3 * i + c] = x[i];
+  }
+  return TSD_OK;
+}
+
+int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, int device, int part_row_begin,
+                     int part_row_end, tsd_grid_t** out)
+{
+  if(!out) return TSD_E_INVALID;
+  *out = nullptr;
+  if(layout_partition != 5) { set_error("only LAYOUT_32x32 partitions are supported (the node's layout)"); return TSD_E_INVALID; }
+  if(layout_grid < 5 || layout_grid > 16 || !(cell_size > 0.0)) { set_error("invalid grid layout"); return TSD_E_INVALID; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if(e != cudaSuccess || ndev == 0)
+  {
+    cudaGetLastError();
+    set_error("no CUDA device: libtsdslam_b200 has no CPU path");
+    return TSD_E_NO_DEVICE;
+  }
+  if(device < 0 || device >= ndev) { set_error("invalid device ordinal %d", device); return TSD_E_INVALID; }
+  TSD_CUDA(cudaSetDevice(device));
+  tsd_grid* g = new tsd_grid();
+  memset(g, 0, sizeof(*g));
+  g->device = device;
+  g->layout_grid = layout_grid;
+  g->cell_size = cell_size;
+  g->inv_cell_size = 1.0 / cell_size;   // TsdGrid.cpp:117
+  g->cells_x = 1 << layout_grid;
+  g->cells_y = g->cells_x;
+  g->parts_x = g->cells_x / TSD_TILE;
+  g->parts_y = g->cells_y / TSD_TILE;
+  g->n_parts = g->parts_x * g->parts_y;
+  if(part_row_begin < 0) part_row_begin = 0;
+  if(part_row_end < 0 || part_row_end > g->parts_y) part_row_end = g->parts_y;
+  if(part_row_begin >= part_row_end) { delete g; set_error("empty band"); return TSD_E_INVALID; }
+  g->row_begin = part_row_begin;
+  g->row_end = part_row_end;
+  g->n_owned = (part_row_end - part_row_begin) * g->parts_x;
+  g->max_truncation = 2.0 * cell_size;  // TsdGrid.cpp:136
+  g->min_x = 0.0;
+  g->max_x = ((double)g->cells_x + 0.5) * cell_size;  // TsdGrid.cpp:141-144
+  g->min_y = 0.0;
+  g->max_y = ((double)g->cells_y + 0.5) * cell_size;
+  g->dirs_n = -1;
+  cudaDeviceProp prop;
+  TSD_CUDA(cudaGetDeviceProperties(&prop, device));
+  g->sm_count = prop.multiProcessorCount;
+  TSD_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  const size_t cellBytes = sizeof(double) * (size_t)g->n_owned * TSD_TILE_STRIDE;
+  e = cudaMalloc(&g->d_tsd, cellBytes);
+  if(e == cudaSuccess) e = cudaMalloc(&g->d_weight, cellBytes);
+  if(e != cudaSuccess)
+  {
+    cudaGetLastError();
+    set_error("cudaMalloc of %zu bytes of cell state failed: %s", 2 * cellBytes, cudaGetErrorString(e));
+    tsdg_destroy(g);
+    return TSD_E_NOMEM;
+  }
+  TSD_CUDA(cudaMalloc(&g->d_flags, g->n_parts));
+  TSD_CUDA(cudaMalloc(&g->d_initw, sizeof(double) * g->n_parts));
+  TSD_CUDA(cudaMalloc(&g->d_active, sizeof(uint32_t) * g->n_owned));
+  TSD_CUDA(cudaMalloc(&g->d_active_w, sizeof(double) * g->n_owned));
+  TSD_CUDA(cudaMalloc(&g->d_emptied, sizeof(uint32_t) * g->n_owned));
+  TSD_CUDA(cudaMalloc(&g->d_pending, sizeof(uint32_t) * g->n_owned));
+  TSD_CUDA(cudaMalloc(&g->d_counters, sizeof(uint32_t) * 16));
+  TSD_CUDA(cudaMalloc(&g->d_stats64, sizeof(unsigned long long) * 4));
+  TSD_CUDA(cudaMalloc(&g->d_coltab, sizeof(double) * 3 * g->cells_x));
+  TSD_CUDA(cudaMalloc(&g->d_rowtab, sizeof(double) * 3 * g->cells_y));
+  TSD_CUDA(cudaMalloc(&g->d_rc_steps, sizeof(unsigned long long) * 2));
+  TSD_CUDA(cudaMallocHost(&g->h_counters, sizeof(uint32_t) * 16));
+  TSD_CUDA(cudaMallocHost(&g->h_stats64, sizeof(unsigned long long) * 4));
+  TSD_CUDA(cudaMallocHost(&g->h_rc_steps, sizeof(unsigned long long) * 2));
+  TSD_CUDA(cudaMemsetAsync(g->d_flags, 0, g->n_parts, g->stream));
+  TSD_CUDA(cudaMemsetAsync(g->d_initw, 0, sizeof(double) * g->n_parts, g->stream));
+  TSD_CUDA(cudaMemsetAsync(g->d_counters, 0, sizeof(uint32_t) * 16, g->stream));
+  TSD_CUDA(cudaMemsetAsync(g->d_stats64, 0, sizeof(unsigned long long) * 4, g->stream));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  *out = g;
+  return TSD_OK;
+}
+
+int tsdg_create(double cell_size, int layout_partition, int layout_grid, int device, tsd_grid_t** out)
+{
+  return tsdg_create_band(cell_size, layout_partition, layout_grid, device, 0, -1, out);
+}
+
+int tsdg_destroy(tsd_grid_t* g)
+{
+  if(!g) return TSD_OK;
+  cudaSetDevice(g->device);
+  if(g->stream) cudaStreamSynchronize(g->stream);
+  cudaFree(g->d_tsd); cudaFree(g->d_weight); cudaFree(g->d_flags); cudaFree(g->d_initw); cudaFree(g->d_active);
+  cudaFree(g->d_active_w); cudaFree(g->d_emptied); cudaFree(g->d_pending); cudaFree(g->d_counters);
+  cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_dirs); cudaFree(g->d_ranges);
+  cudaFree(g->d_mask); cudaFree(g->d_rays); cudaFree(g->d_rc_out); cudaFree(g->d_rc_keys); cudaFree(g->d_rc_steps);
+  cudaFree(g->d_scratch);
+  cudaFreeHost(g->h_ranges); cudaFreeHost(g->h_mask); cudaFreeHost(g->h_rc_out); cudaFreeHost(g->h_rc_keys);
+  cudaFreeHost(g->h_rays); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters); cudaFreeHost(g->h_stats64);
+  cudaFreeHost(g->h_rc_steps);
+  if(g->stream) cudaStreamDestroy(g->stream);
+  cudaGetLastError();
+  delete g;
+  return TSD_OK;
+}
+
+int tsdg_set_max_truncation(tsd_grid_t* g, double val)
+{
+  if(!g) return TSD_E_INVALID;
+  if(val < 2 * g->cell_size) val = 2 * g->cell_size;  // TsdGrid.cpp:208-212
+  g->max_truncation = val;
+  return TSD_OK;
+}
+
+int tsdg_get_geometry(const tsd_grid_t* g, int32_t* cells_x, int32_t* cells_y, int32_t* partition_size,
+                      double* cell_size, double* min_x, double* max_x, double* min_y, double* max_y,
+                      double* max_truncation)
+{
+  if(!g) return TSD_E_INVALID;
+  if(cells_x) *cells_x = g->cells_x;
+  if(cells_y) *cells_y = g->cells_y;
+  if(partition_size) *partition_size = TSD_TILE;
+  if(cell_size) *cell_size = g->cell_size;
+  if(min_x) *min_x = g->min_x;
+  if(max_x) *max_x = g->max_x;
+  if(min_y) *min_y = g->min_y;
+  if(max_y) *max_y = g->max_y;
+  if(max_truncation) *max_truncation = g->max_truncation;
+  return TSD_OK;
+}
+
+int tsdg_free_footprint(tsd_grid_t* g, double cx, double cy, double width, double height)
+{
+  if(!g) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  // TsdGrid.cpp:611-622
+  const unsigned minX = static_cast<unsigned int>((cx - width * 0.5) / g->cell_size + 0.5);
+  const unsigned maxX = static_cast<unsigned int>((cx + width * 0.5) / g->cell_size + 0.5);
+  const unsigned minY = static_cast<unsigned int>((cy - height * 0.5) / g->cell_size + 0.5);
+  const unsigned maxY = static_cast<unsigned int>((cy + height * 0.5) / g->cell_size + 0.5);
+  if((minX > (unsigned)g->cells_x) || (maxX > (unsigned)g->cells_x) || (minY > (unsigned)g->cells_y) ||
+     (maxY > (unsigned)g->cells_y))
+  {
+    set_error("freeFootprint: indices out of bounds");
+    return TSD_E_RANGE;
+  }
+  if(maxX <= minX || maxY <= minY) return TSD_OK;
+  PushParams pp = make_params(g);
+  const int pxMin = minX >> 5, pxMax = (maxX - 1) >> 5, pyMin = minY >> 5, pyMax = (maxY - 1) >> 5;
+  const int tiles = (pxMax - pxMin + 1) * (pyMax - pyMin + 1);
+  k_footprint_init<<<tiles, 256, 0, g->stream>>>(pp, pxMin, pxMax, pyMin, pyMax);
+  TSD_LAUNCHED();
+  const unsigned cells = (maxX - minX) * (maxY - minY);
+  k_footprint_set<<<(cells + 255) / 256, 256, 0, g->stream>>>(pp, minX, maxX, minY, maxY);
+  TSD_LAUNCHED();
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  return TSD_OK;
+}
+
+int tsdg_stage_scan(tsd_grid_t* g, const tsd_scan_t* scan)
+{
+  if(!g) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  int rc = grid_stage_scan(g, scan, &g->staged);
+  if(rc) return rc;
+  g->has_staged = true;
+  return TSD_OK;
+}
+
+int tsdg_push_staged(tsd_grid_t* g)
+{
+  if(!g || !g->has_staged) { set_error("no staged scan"); return TSD_E_INVALID; }
+  TSD_CUDA(cudaSetDevice(g->device));
+  PushParams pp = make_params(g);
+  pp.scan = g->staged;
+  pp.dirs = g->d_dirs;
+  const tsd::ScanDev* scan = &g->staged;
+  // counters [0] active [1] emptied are per push; [2] pending and [3] refresh-all persist until consumed below
+  TSD_CUDA(cudaMemsetAsync(g->d_counters, 0, sizeof(uint32_t) * 2, g->stream));
+  TSD_CUDA(cudaMemsetAsync(g->d_counters + 4, 0, sizeof(uint32_t) * 4, g->stream));
+  TSD_CUDA(cudaMemsetAsync(g->d_stats64, 0, sizeof(unsigned long long) * 4, g->stream));
+  const int nmax = g->cells_x > g->cells_y ? g->cells_x : g->cells_y;
+  k_tables<<<(nmax + 255) / 256, 256, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
+  TSD_LAUNCHED();
+  k_classify<<<(g->n_parts + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS, CLASSIFY_WARPS * 32, 0, g->stream>>>(pp);
+  TSD_LAUNCHED();
+  const size_t smem = sizeof(double2) * (scan->n + 1) + sizeof(double) * scan->n + scan->n + 16;
+  if(smem > 48 * 1024)
+  {
+    TSD_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  int ctas = g->sm_count * 4;
+  if(ctas > g->n_owned) ctas = g->n_owned;
+  k_update<<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+  TSD_LAUNCHED();
+  int bctas = g->sm_count * 4;
+  k_borders<<<bctas, 256, 0, g->stream>>>(pp, 0);
+  TSD_LAUNCHED();
+  TSD_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, g->stream));
+  TSD_CUDA(cudaMemcpyAsync(g->h_stats64, g->d_stats64, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, g->stream));
+  // pending list and refresh-all flag are consumed
+  TSD_CUDA(cudaMemsetAsync(g->d_counters + 2, 0, sizeof(uint32_t) * 2, g->stream));
+  g->pushed_once = true;
+  return TSD_OK;
+}
+
+int tsdg_push_async(tsd_grid_t* g, const tsd_scan_t* scan)
+{
+  int rc = tsdg_stage_scan(g, scan);
+  if(rc) return rc;
+  return tsdg_push_staged(g);
+}
+
+void* tsdg_stream(tsd_grid_t* g) { return g ? (void*)g->stream : nullptr; }
+
+int tsdg_sync(tsd_grid_t* g)
+{
+  if(!g) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  return TSD_OK;
+}
+
+int tsdg_push(tsd_grid_t* g, const tsd_scan_t* scan)
+{
+  int rc = tsdg_push_async(g, scan);
+  if(rc) return rc;
+  return tsdg_sync(g);
+}
+
+int tsdg_last_push_stats(tsd_grid_t* g, tsd_push_stats_t* out)
+{
+  if(!g || !out) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  out->cell_updates = g->h_stats64[0];
+  out->active_tiles = g->h_counters[7];
+  out->cell_visits = (uint64_t)g->h_counters[0] * TSD_TILE_CELLS;
+  out->emptied_tiles = g->h_counters[6];
+  out->newly_initialized = g->h_counters[4];
+  out->fallback_cells = g->h_counters[5];
+  return TSD_OK;
+}
+
+int tsdg_interpolate_bilinear(tsd_grid_t* g, int32_t n, const double* xy, double* tsd, int32_t* status)
+{
+  if(!g || n < 0 || (n > 0 && (!xy || !tsd || !status))) return TSD_E_INVALID;
+  if(n == 0) return TSD_OK;
+  TSD_CUDA(cudaSetDevice(g->device));
+  const size_t bytes = (size_t)n * (sizeof(double) * 3 + sizeof(int));
+  int rc = grid_ensure_scratch(g, bytes);
+  if(rc) return rc;
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  double* h = (double*)g->h_scratch;
+  double* d = (double*)g->d_scratch;
+  memcpy(h, xy, sizeof(double) * 2 * n);
+  TSD_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, g->stream));
+  double* d_tsd = d + 2 * (size_t)n;
+  int* d_st = (int*)(d_tsd + n);
+  k_interpolate<<<(n + 127) / 128, 128, 0, g->stream>>>(grid_view(g), n, d, d_tsd, d_st);
+  TSD_LAUNCHED();
+  TSD_CUDA(cudaMemcpyAsync(h + 2 * (size_t)n, d_tsd, sizeof(double) * n + sizeof(int) * n, cudaMemcpyDeviceToHost, g->stream));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  memcpy(tsd, h + 2 * (size_t)n, sizeof(double) * n);
+  memcpy(status, h + 3 * (size_t)n, sizeof(int) * n);
+  return TSD_OK;
+}
+
+int tsdg_interpolate_normal(tsd_grid_t* g, int32_t n, const double* xy, double* normals, int32_t* ok)
+{
+  if(!g || n < 0 || (n > 0 && (!xy || !normals || !ok))) return TSD_E_INVALID;
+  if(n == 0) return TSD_OK;
+  TSD_CUDA(cudaSetDevice(g->device));
+  const size_t bytes = (size_t)n * (sizeof(double) * 4 + sizeof(int));
+  int rc = grid_ensure_scratch(g, bytes);
+  if(rc) return rc;
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  double* h = (double*)g->h_scratch;
+  double* d = (double*)g->d_scratch;
+  memcpy(h, xy, sizeof(double) * 2 * n);
+  TSD_CUDA(cudaMemcpyAsync(d, h, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, g->stream));
+  double* d_n = d + 2 * (size_t)n;
+  int* d_ok = (int*)(d_n + 2 * (size_t)n);
+  k_interpolate_normal<<<(n + 127) / 128, 128, 0, g->stream>>>(grid_view(g), n, d, d_n, d_ok);
+  TSD_LAUNCHED();
+  TSD_CUDA(cudaMemcpyAsync(h + 2 * (size_t)n, d_n, sizeof(double) * 2 * n + sizeof(int) * n, cudaMemcpyDeviceToHost, g->stream));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  memcpy(normals, h + 2 * (size_t)n, sizeof(double) * 2 * n);
+  memcpy(ok, h + 4 * (size_t)n, sizeof(int) * n);
+  return TSD_OK;
+}
+
+int tsdg_num_partitions(const tsd_grid_t* g, int32_t* n)
+{
+  if(!g || !n) return TSD_E_INVALID;
+  *n = g->n_parts;
+  return TSD_OK;
+}
+
+int tsdg_partition_states(tsd_grid_t* g, int32_t* state, double* init_weight)
+{
+  if(!g || !state) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  std::vector<uint8_t> flags(g->n_parts);
+  std::vector<double> iw(g->n_parts);
+  TSD_CUDA(cudaMemcpy(flags.data(), g->d_flags, g->n_parts, cudaMemcpyDeviceToHost));
+  TSD_CUDA(cudaMemcpy(iw.data(), g->d_initw, sizeof(double) * g->n_parts, cudaMemcpyDeviceToHost));
+  for(int p = 0; p < g->n_parts; p++)
+  {
+    // TsdGridPartition.h:66,72 isInitialized / isEmpty
+    state[p] = flags[p] ? TSD_PARTITION_CONTENT : (iw[p] > 0.0 ? TSD_PARTITION_EMPTY : TSD_PARTITION_UNINITIALIZED);
+    if(init_weight) init_weight[p] = iw[p];
+  }
+  return TSD_OK;
+}
+
+static void tile_to_33(const double* tile, double* out33)
+{
+  for(int y = 0; y < 32; y++)
+  {
+    for(int x = 0; x < 32; x++) out33[y * 33 + x] = tile[y * 32 + x];
+    out33[y * 33 + 32] = tile[TSD_BORDER_OFF + y];
+  }
+  for(int x = 0; x < 32; x++) out33[32 * 33 + x] = tile[TSD_BORDER_OFF + 32 + x];
+  out33[32 * 33 + 32] = tile[TSD_BORDER_OFF + 64];
+}
+
+static void tile_from_33(const double* in33, double* tile)
+{
+  for(int y = 0; y < 32; y++)
+  {
+    for(int x = 0; x < 32; x++) tile[y * 32 + x] = in33[y * 33 + x];
+    tile[TSD_BORDER_OFF + y] = in33[y * 33 + 32];
+  }
+  for(int x = 0; x < 32; x++) tile[TSD_BORDER_OFF + 32 + x] = in33[32 * 33 + x];
+  tile[TSD_BORDER_OFF + 64] = in33[32 * 33 + 32];
+  for(int i = TSD_BORDER_OFF + 65; i < TSD_TILE_STRIDE; i++) tile[i] = 0.0;
+}
+
+int tsdg_download_partition(tsd_grid_t* g, int32_t p, double* tsd, double* weight)
+{
+  if(!g || p < 0 || p >= g->n_parts || !tsd || !weight) return TSD_E_INVALID;
+  const int py = p / g->parts_x;
+  if(py < g->row_begin || py >= g->row_end) { set_error("partition %d is not owned by this band", p); return TSD_E_INVALID; }
+  TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  uint8_t flag = 0;
+  TSD_CUDA(cudaMemcpy(&flag, g->d_flags + p, 1, cudaMemcpyDeviceToHost));
+  if(!flag) return TSD_E_INVALID;
+  double tile[TSD_TILE_STRIDE];
+  const size_t base = (size_t)(p - g->row_begin * g->parts_x) * TSD_TILE_STRIDE;
+  TSD_CUDA(cudaMemcpy(tile, g->d_tsd + base, sizeof(tile), cudaMemcpyDeviceToHost));
+  tile_to_33(tile, tsd);
+  TSD_CUDA(cudaMemcpy(tile, g->d_weight + base, sizeof(tile), cudaMemcpyDeviceToHost));
+  tile_to_33(tile, weight);
+  return TSD_OK;
+}
+
+int tsdg_upload_partition(tsd_grid_t* g, int32_t p, const double* tsd, const double* weight)
+{
+  if(!g || p < 0 || p >= g->n_parts || !tsd || !weight) return TSD_E_INVALID;
+  const int py = p / g->parts_x;
+  if(py < g->row_begin || py >= g->row_end) { set_error("partition %d is not owned by this band", p); return TSD_E_INVALID; }
+  TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  double tile[TSD_TILE_STRIDE];
+  const size_t base = (size_t)(p - g->row_begin * g->parts_x) * TSD_TILE_STRIDE;
+  tile_from_33(tsd, tile);
+  TSD_CUDA(cudaMemcpy(g->d_tsd + base, tile, sizeof(tile), cudaMemcpyHostToDevice));
+  tile_from_33(weight, tile);
+  TSD_CUDA(cudaMemcpy(g->d_weight + base, tile, sizeof(tile), cudaMemcpyHostToDevice));
+  const uint8_t one = 1;
+  TSD_CUDA(cudaMemcpy(g->d_flags + p, &one, 1, cudaMemcpyHostToDevice));
+  const uint32_t all = 1;  // the next push refreshes every border, like the reference's full propagateBorders
+  TSD_CUDA(cudaMemcpy(g->d_counters + 3, &all, sizeof(all), cudaMemcpyHostToDevice));
+  return TSD_OK;
+}
+
+int tsdg_fill(tsd_grid_t* g, double tsd, double weight)
+{
+  if(!g) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  PushParams pp = make_params(g);
+  k_fill<<<g->sm_count * 8, 256, 0, g->stream>>>(pp, tsd, weight);
+  TSD_LAUNCHED();
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  const uint32_t all = 1;
+  TSD_CUDA(cudaMemcpy(g->d_counters + 3, &all, sizeof(all), cudaMemcpyHostToDevice));
+  return TSD_OK;
+}
+
+}  // extern "C"
