@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- TsdGrid::push throughput (+ raycast + ICP) of the B200-native hot path on BASELINE.json
+configs[1] (double-laser, 4096^2 grid), dense regime.  One JSON line on stdout (rank 0).
+
+  python bench.py --gpus 1 --steps 50 --warmup 5            # CUDA arm (the product, through its C ABI)
+  python bench.py --impl reference --steps 3 --warmup 1     # the reference's own CPU code (oracle/_ref)
+  torchrun ... bench.py --gpus N ...                        # N ranks, one replica of the workload per GPU
+
+A step = one scan cycle of both lasers: two TsdGrid::push calls.  `value` times the pushes with the scans
+already staged in HBM; `e2e` times the same pushes through tsdg_push() with host buffers (H2D of the scan and
+D2H of the push statistics inside the timed region)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "tsd_push_cell_updates_per_s"
+UNIT = "Gcell-updates/s"
+ALG_BYTES_PER_UPDATE = 32  # read + write of {tsd, weight} in FP64
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    from ohm_tsd_slam_b200 import capi
+    from ohm_tsd_slam_b200.workload import DoubleLaserWorkload
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if capi.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = DoubleLaserWorkload(args.workload, invert=capi.invert3x3, seed_offset=rank)
+    cfg = wl.cfg
+    grid = capi.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid, device=local)
+    grid.set_max_truncation(cfg.max_truncation)
+    wl.build_map(grid)
+    grid.set_timing(True)
+    launches0 = capi.kernel_launches()
+    stream = torch.cuda.ExternalStream(grid.stream_ptr, device=torch.device("cuda", local))
+    n_steps = len(wl.step_scans)
+
+    # ---------------- device-resident leg: scans staged in HBM, one staged handle per laser and step
+    # (staging buffers are per grid handle: re-stage outside the timed region is not possible for 2 lasers x n
+    #  steps, so the two lasers' scans of step i are staged right before their pushes from PINNED host memory by
+    #  tsdg_stage_scan; to keep H2D out of `value`, value times push_staged only, via CUDA events per push).
+    def resident_step(i, acc):
+        for sc in wl.step_scans[i % n_steps]:
+            grid.stage_scan(sc)      # H2D (not timed in `value`)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            grid.push_staged()
+            e1.record(stream)
+            acc.append((e0, e1))
+
+    for i in range(args.warmup):
+        resident_step(i, [])
+    grid.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = []
+    upd_total = 0
+    kms = []
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        resident_step(i, evs)
+        # per-push statistics are read back outside the event brackets
+        st = grid.last_push_stats()
+        km = grid.last_push_kernel_ms()
+        upd_total += 2 * st["cell_updates"]  # both lasers of a step see the same map: counted from the second, doubled below exactly
+        kms.append(km)
+    grid.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+
+    # exact update count per step: measure each laser's push once
+    upd_per_step = 0
+    for sc in wl.step_scans[0]:
+        grid.push(sc)
+        upd_per_step += grid.last_push_stats()["cell_updates"]
+    upd_avg_per_push = upd_per_step / 2.0
+
+    # ---------------- end-to-end leg: host buffers through tsdg_push (blocking; H2D + stats D2H inside)
+    for i in range(args.warmup):
+        for sc in wl.step_scans[i % n_steps]:
+            grid.push(sc)
+    barrier()
+    e2e_updates = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        for sc in wl.step_scans[i % n_steps]:
+            grid.push(sc)
+            e2e_updates += grid.last_push_stats()["cell_updates"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    # ---------------- raycast + ICP through the C ABI (host buffers), for the scans/s part of the metric
+    icp = capi.Icp(30, 0.4, 0.02, grid.bounds, device=local)
+    sc0, rays0 = wl.step_scans[0][0], wl.step_rays[0][0]
+    hs = wl.sensors[0]
+    scene = None
+    rc_ms = icp_ms = None
+    reps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        c, nrm, m, cnt = grid.raycast_mask(sc0, rays0)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        c, nrm, m, cnt = grid.raycast_mask(sc0, rays0)
+    rc_ms = (time.perf_counter() - t0) / reps * 1e3
+    valid = (~np.isinf(sc0.ranges)) & (sc0.mask != 0)
+    scene = np.stack([hs.rays_local[0, valid] * sc0.ranges[valid], hs.rays_local[1, valid] * sc0.ranges[valid]], axis=1)
+    icp_out = None
+    if cnt > 2:
+        for _ in range(2):
+            icp_out = icp.run(c[m > 0], nrm[m > 0], scene, sc0.pose)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            icp_out = icp.run(c[m > 0], nrm[m > 0], scene, sc0.pose)
+        icp_ms = (time.perf_counter() - t0) / reps * 1e3
+
+    launches = capi.kernel_launches() - launches0
+
+    # max over ranks of the timed durations, sum of the work
+    dev_ms_t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    work_t = torch.tensor([float(upd_per_step * args.steps), float(e2e_updates)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dev_ms_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work_t, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = dev_ms_t.tolist()
+    work_dev, work_e2e = work_t.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        upd_ms = float(np.mean([k["update"] for k in kms]))
+        achieved = ALG_BYTES_PER_UPDATE * upd_avg_per_push / (upd_ms * 1e-3) / 1e9
+        value = work_dev / (dev_ms_max * 1e-3) / 1e9
+        e2e_value = work_e2e / (e2e_ms_max * 1e-3) / 1e9
+        n = sc0.n
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "cuda",
+            "config": dict(wl.describe(), parallelism=f"replicas x{world}" if world > 1 else "single GPU",
+                           cell_updates_per_step=upd_per_step),
+            "hbm_gbs_algorithmic": value * ALG_BYTES_PER_UPDATE,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * (n * 8 + n + 8 * 25), "d2h_bytes_per_step": 2 * (16 * 4 + 4 * 8),
+                    "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_update (TsdGrid::push cell update, K2+K3)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "kernel_ms": upd_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE * upd_avg_per_push},
+            "push_kernel_ms": {k: float(np.mean([x[k] for x in kms])) for k in kms[0]},
+            "raycast_icp": {"raycast_ms": rc_ms, "icp_ms": icp_ms, "raycast_hits": int(cnt),
+                            "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
+                            "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / 2) if icp_ms else None,
+                            "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
+            "clocks": sampler.summary(),
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload, steps=1, warmup=0, threads=None)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload: str, steps: int, warmup: int, threads):
+    """The reference's own push (oracle/_ref, compiled from the reference sources) or, where that prebuilt
+    library is absent, the plain-C port, on the host cores; bounded sample of the same workload."""
+    from ohm_tsd_slam_b200.workload import DoubleLaserWorkload
+    from oracle import port, ref
+    use_ref = ref.available()
+    inv = ref.invert if use_ref else port.invert3x3
+    wl = DoubleLaserWorkload(workload, invert=inv, n_map=2)
+    cfg = wl.cfg
+    cores = os.cpu_count() or 1
+    if use_ref:
+        nthreads = threads or cores
+        ref.set_threads(nthreads)
+        g = ref.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)
+        g.set_max_truncation(cfg.max_truncation)
+        sensor = ref.Sensor(cfg.sensor)
+
+        def push(sc):
+            sensor.set_data(sc.ranges, sc.mask)
+            sensor.pose = sc.pose
+            g.push(sensor)
+
+        kind = "reference"
+    else:
+        nthreads = 1
+        g = port.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)
+        g.set_max_truncation(cfg.max_truncation)
+        push = g.push
+        kind = "port"
+    pg = port.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)  # counts cell updates (the reference does not)
+    pg.set_max_truncation(cfg.max_truncation)
+    for sc in wl.map_scans:
+        push(sc)
+        pg.push(sc)
+    g.fill(1.0, 1.0, only_uninitialized=True)
+    pg.fill(1.0, 1.0, only_uninitialized=True)
+    n_steps = len(wl.step_scans)
+    for i in range(warmup):
+        for sc in wl.step_scans[i % n_steps]:
+            push(sc)
+            pg.push(sc)
+    updates = 0
+    t = 0.0
+    for i in range(steps):
+        for sc in wl.step_scans[i % n_steps]:
+            t0 = time.perf_counter()
+            push(sc)
+            t += time.perf_counter() - t0
+            pg.push(sc)
+            updates += pg.last_push_stats()["cell_updates"]
+    return {"value": updates / t / 1e9, "unit": UNIT, "cores": nthreads, "kind": kind,
+            "sample": f"{2 * steps} TsdGrid::push calls ({steps} step(s)) of the same workload after the same map build, "
+                      f"{updates} cell updates, {t:.2f} s on {nthreads} thread(s) of {cores} host cores",
+            "ms_per_step": t / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = max(0, min(args.warmup, 1))
+    b = cpu_baseline(args.workload, steps=steps, warmup=warmup, threads=None)
+    from ohm_tsd_slam_b200.workload import DoubleLaserWorkload
+    wl = DoubleLaserWorkload(args.workload, invert=lambda T: np.eye(3), n_map=0, n_steps=1)
+    line = {
+        "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps,
+        "warmup": warmup, "ms_per_step": b["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": dict(wl.describe(), parallelism="host cores (OpenMP)"),
+        "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,10 @@ int tsdg_stage_scan(tsd_grid_t* grid, const tsd_scan_t* scan);
 int tsdg_push_staged(tsd_grid_t* grid);
 /* The handle's cudaStream_t, for callers that time or order work with CUDA events. */
 void* tsdg_stream(tsd_grid_t* grid);
+/* Measurement aid: with timing enabled every push records CUDA events around its kernels on the handle's
+ * stream; ms = {tables + classify, update (K2+K3), borders (K4), whole push} of the last completed push. */
+int tsdg_set_timing(tsd_grid_t* grid, int enable);
+int tsdg_last_push_kernel_ms(tsd_grid_t* grid, float ms[4]);
 
 /* Counters of the most recent completed push. */
 typedef struct tsd_push_stats
@@ -149,8 +153,9 @@ int tsdg_partition_states(tsd_grid_t* grid, int32_t* state, double* init_weight)
  * Returns TSD_E_INVALID for an uninitialised partition. */
 int tsdg_download_partition(tsd_grid_t* grid, int32_t p, double* tsd, double* weight);
 int tsdg_upload_partition(tsd_grid_t* grid, int32_t p, const double* tsd, const double* weight);
-/* Mark every partition initialised with the given cell value (bench: the dense, bandwidth-bound regime). */
-int tsdg_fill(tsd_grid_t* grid, double tsd, double weight);
+/* Allocate partitions with the given cell value: all of them, or only those not yet initialised
+ * (bench: the dense regime, where every in-range partition of a push is already allocated). */
+int tsdg_fill(tsd_grid_t* grid, double tsd, double weight, int only_uninitialized);
 
 /* ------------------------------------------------------------------------------------------------
  * RayCastPolar2D  (reconstruct/grid/RayCastPolar2D.h/.cpp)

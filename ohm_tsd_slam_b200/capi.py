@@ -24,7 +24,7 @@ EXPORTS = [
     "tsd_last_error", "tsd_device_count", "tsd_kernel_launches", "tsd_invert3x3",
     "tsdg_create", "tsdg_create_band", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
     "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged",
-    "tsdg_stream", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
+    "tsdg_stream", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
     "icp_create", "icp_destroy", "icp_run", "icp_get_trace",
@@ -64,6 +64,8 @@ def lib():
     L.tsdg_sync.argtypes = [C.c_void_p]
     L.tsdg_stream.restype = C.c_void_p
     L.tsdg_stream.argtypes = [C.c_void_p]
+    L.tsdg_set_timing.argtypes = [C.c_void_p, C.c_int]
+    L.tsdg_last_push_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tsdg_last_push_stats.argtypes = [C.c_void_p, C.POINTER(PushStats)]
     L.tsdg_interpolate_bilinear.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
     L.tsdg_interpolate_normal.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
@@ -71,7 +73,7 @@ def lib():
     L.tsdg_partition_states.argtypes = [C.c_void_p, _ip, _dp]
     L.tsdg_download_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
     L.tsdg_upload_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
-    L.tsdg_fill.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.tsdg_fill.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
     L.tsdg_raycast_mask.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _bp, _up]
     L.tsdg_raycast.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _up]
     L.tsdg_last_raycast_steps.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -188,6 +190,14 @@ class Grid:
         check(lib().tsdg_last_push_stats(self.h, C.byref(st)))
         return st.as_dict()
 
+    def set_timing(self, enable: bool = True):
+        check(lib().tsdg_set_timing(self.h, 1 if enable else 0))
+
+    def last_push_kernel_ms(self):
+        ms = (C.c_float * 4)()
+        check(lib().tsdg_last_push_kernel_ms(self.h, ms))
+        return dict(classify=ms[0], update=ms[1], borders=ms[2], total=ms[3])
+
     def partition_states(self):
         st = np.empty(self.n_partitions, dtype=np.int32)
         iw = np.empty(self.n_partitions)
@@ -206,8 +216,8 @@ class Grid:
         tsd, w = _f64(tsd), _f64(w)
         check(lib().tsdg_upload_partition(self.h, p, _d(tsd), _d(w)))
 
-    def fill(self, tsd, weight):
-        check(lib().tsdg_fill(self.h, tsd, weight))
+    def fill(self, tsd, weight, only_uninitialized: bool = False):
+        check(lib().tsdg_fill(self.h, tsd, weight, 1 if only_uninitialized else 0))
 
     def interpolate_bilinear(self, xy):
         xy = _f64(xy)

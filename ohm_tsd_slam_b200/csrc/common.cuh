@@ -204,6 +204,8 @@ struct tsd_grid
   int sm_count;
   tsd::ScanDev staged;  // scan staged by tsdg_stage_scan (device pointers + scalars)
   bool has_staged;
+  bool timing;          // record CUDA events around the push kernels (bench.py's live roofline)
+  cudaEvent_t ev[4];
 };
 
 namespace tsd

@@ -577,16 +577,26 @@ __global__ void k_footprint_set(PushParams pp, unsigned minX, unsigned maxX, uns
   pp.tsd[base + (rows & 31) * TSD_TILE + (cols & 31)] = 1.0;
 }
 
-__global__ void k_fill(PushParams pp, double tsd, double weight)
+// one CTA-iteration per partition; only_uninit: leave allocated partitions alone
+__global__ void k_fill(PushParams pp, double tsd, double weight, int only_uninit)
 {
-  const size_t total = (size_t)(pp.row_end - pp.row_begin) * pp.parts_x * TSD_TILE_STRIDE;
-  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+  for(int p = blockIdx.x; p < pp.n_parts; p += gridDim.x)
   {
-    pp.tsd[i] = tsd;
-    pp.weight[i] = weight;
+    const bool skip = only_uninit && pp.flags[p];
+    __syncthreads();
+    if(skip) continue;
+    const int py = p / pp.parts_x;
+    if(py >= pp.row_begin && py < pp.row_end)
+    {
+      const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+      for(int i = threadIdx.x; i < TSD_BORDER_OFF + 65; i += blockDim.x)
+      {
+        pp.tsd[base + i] = tsd;
+        pp.weight[base + i] = weight;
+      }
+    }
+    if(threadIdx.x == 0) pp.flags[p] = 1;
   }
-  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)pp.n_parts; i += (size_t)gridDim.x * blockDim.x)
-    pp.flags[i] = 1;
 }
 
 __global__ void k_interpolate(GridView g, int n, const double* xy, double* tsd, int* status)
@@ -889,6 +899,7 @@ int tsdg_destroy(tsd_grid_t* g)
   cudaFreeHost(g->h_ranges); cudaFreeHost(g->h_mask); cudaFreeHost(g->h_rc_out); cudaFreeHost(g->h_rc_keys);
   cudaFreeHost(g->h_rays); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters); cudaFreeHost(g->h_stats64);
   cudaFreeHost(g->h_rc_steps);
+  for(int i = 0; i < 4; i++) if(g->ev[i]) cudaEventDestroy(g->ev[i]);
   if(g->stream) cudaStreamDestroy(g->stream);
   cudaGetLastError();
   delete g;
@@ -971,10 +982,12 @@ int tsdg_push_staged(tsd_grid_t* g)
   TSD_CUDA(cudaMemsetAsync(g->d_counters + 4, 0, sizeof(uint32_t) * 4, g->stream));
   TSD_CUDA(cudaMemsetAsync(g->d_stats64, 0, sizeof(unsigned long long) * 4, g->stream));
   const int nmax = g->cells_x > g->cells_y ? g->cells_x : g->cells_y;
+  if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[0], g->stream));
   k_tables<<<(nmax + 255) / 256, 256, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
   TSD_LAUNCHED();
   k_classify<<<(g->n_parts + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS, CLASSIFY_WARPS * 32, 0, g->stream>>>(pp);
   TSD_LAUNCHED();
+  if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[1], g->stream));
   const size_t smem = sizeof(double2) * (scan->n + 1) + sizeof(double) * scan->n + scan->n + 16;
   if(smem > 48 * 1024)
   {
@@ -984,9 +997,11 @@ int tsdg_push_staged(tsd_grid_t* g)
   if(ctas > g->n_owned) ctas = g->n_owned;
   k_update<<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   TSD_LAUNCHED();
+  if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[2], g->stream));
   int bctas = g->sm_count * 4;
   k_borders<<<bctas, 256, 0, g->stream>>>(pp, 0);
   TSD_LAUNCHED();
+  if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[3], g->stream));
   TSD_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, g->stream));
   TSD_CUDA(cudaMemcpyAsync(g->h_stats64, g->d_stats64, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, g->stream));
   // pending list and refresh-all flag are consumed
@@ -1003,6 +1018,28 @@ int tsdg_push_async(tsd_grid_t* g, const tsd_scan_t* scan)
 }
 
 void* tsdg_stream(tsd_grid_t* g) { return g ? (void*)g->stream : nullptr; }
+
+int tsdg_set_timing(tsd_grid_t* g, int enable)
+{
+  if(!g) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  if(enable && !g->ev[0])
+    for(int i = 0; i < 4; i++) TSD_CUDA(cudaEventCreate(&g->ev[i]));
+  g->timing = enable != 0;
+  return TSD_OK;
+}
+
+int tsdg_last_push_kernel_ms(tsd_grid_t* g, float ms[4])
+{
+  if(!g || !ms || !g->timing || !g->pushed_once) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  TSD_CUDA(cudaEventElapsedTime(&ms[0], g->ev[0], g->ev[1]));
+  TSD_CUDA(cudaEventElapsedTime(&ms[1], g->ev[1], g->ev[2]));
+  TSD_CUDA(cudaEventElapsedTime(&ms[2], g->ev[2], g->ev[3]));
+  TSD_CUDA(cudaEventElapsedTime(&ms[3], g->ev[0], g->ev[3]));
+  return TSD_OK;
+}
 
 int tsdg_sync(tsd_grid_t* g)
 {
@@ -1168,12 +1205,12 @@ int tsdg_upload_partition(tsd_grid_t* g, int32_t p, const double* tsd, const dou
   return TSD_OK;
 }
 
-int tsdg_fill(tsd_grid_t* g, double tsd, double weight)
+int tsdg_fill(tsd_grid_t* g, double tsd, double weight, int only_uninitialized)
 {
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   PushParams pp = make_params(g);
-  k_fill<<<g->sm_count * 8, 256, 0, g->stream>>>(pp, tsd, weight);
+  k_fill<<<g->sm_count * 8, 256, 0, g->stream>>>(pp, tsd, weight, only_uninitialized);
   TSD_LAUNCHED();
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   const uint32_t all = 1;

@@ -55,7 +55,7 @@ def lib():
         L.port_grid_partition_states.argtypes = [C.c_void_p, _ip, _dp]
         L.port_grid_download_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
         L.port_grid_upload_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
-        L.port_grid_fill.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.port_grid_fill.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
         L.port_back_project.argtypes = [_sp, C.c_int32, _dp, _ip]
         L.port_raycast_mask.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _bp, _up]
         L.port_raycast_steps.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -178,8 +178,8 @@ class Grid:
         tsd, w = _f64(tsd), _f64(w)
         lib().port_grid_upload_partition(self.h, p, _d(tsd), _d(w))
 
-    def fill(self, tsd, weight):
-        lib().port_grid_fill(self.h, tsd, weight)
+    def fill(self, tsd, weight, only_uninitialized: bool = False):
+        lib().port_grid_fill(self.h, tsd, weight, 1 if only_uninitialized else 0)
 
     def interpolate_bilinear(self, xy):
         xy = _f64(xy)

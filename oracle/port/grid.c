@@ -507,12 +507,13 @@ int port_grid_upload_partition(port_grid_t* g, int32_t p, const double* tsd, con
   return TSD_OK;
 }
 
-void port_grid_fill(port_grid_t* g, double tsd, double weight)
+void port_grid_fill(port_grid_t* g, double tsd, double weight, int only_uninitialized)
 {
   const int n = (g->dim + 1) * (g->dim + 1);
   for(int i = 0; i < g->parts_x * g->parts_y; i++)
   {
     part_t* part = &g->parts[i];
+    if(part->initialized && only_uninitialized) continue;
     if(!part->initialized) part_init(g, part, g->max_truncation);
     for(int k = 0; k < n; k++) { part->grid[k].tsd = tsd; part->grid[k].weight = weight; }
   }

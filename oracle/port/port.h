@@ -35,7 +35,7 @@ int32_t port_grid_num_partitions(const port_grid_t* g);
 void port_grid_partition_states(port_grid_t* g, int32_t* state, double* init_weight);
 int port_grid_download_partition(port_grid_t* g, int32_t p, double* tsd, double* weight);
 int port_grid_upload_partition(port_grid_t* g, int32_t p, const double* tsd, const double* weight);
-void port_grid_fill(port_grid_t* g, double tsd, double weight);
+void port_grid_fill(port_grid_t* g, double tsd, double weight, int only_uninitialized);
 void port_back_project(const tsd_scan_t* scan, int32_t n, const double* xy, int32_t* idx);
 
 int port_raycast_mask(port_grid_t* g, const tsd_scan_t* scan, const double* rays_world, double* coords,

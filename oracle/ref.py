@@ -46,6 +46,7 @@ def lib():
         L.ref_grid_cells_x.argtypes = [C.c_void_p]
         L.ref_grid_free_footprint.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
         L.ref_grid_push.argtypes = [C.c_void_p, C.c_void_p]
+        L.ref_grid_fill.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
         L.ref_grid_num_partitions.argtypes = [C.c_void_p]
         L.ref_grid_partition_state.argtypes = [C.c_void_p, C.c_int, _dp]
         L.ref_grid_partition_states.argtypes = [C.c_void_p, _ip, _dp]
@@ -213,11 +214,31 @@ class Sensor:
         return coords, mask, int(valid)
 
 
+class _quiet_stdout:
+    """TsdGrid::init prints "init" with std::cout (TsdGrid.cpp:114): keep it off the caller's stdout."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
 class Grid:
     """obvious::TsdGrid"""
 
     def __init__(self, cell_size: float, layout_partition: int, layout_grid: int, handle=None):
-        self.h = handle if handle is not None else lib().ref_grid_create(cell_size, layout_partition, layout_grid)
+        if handle is None:
+            L = lib()
+            with _quiet_stdout():
+                handle = L.ref_grid_create(cell_size, layout_partition, layout_grid)
+        self.h = handle
         self.cell_size = cell_size
         self.dim = 1 << layout_partition
         self.cells = 1 << layout_grid
@@ -242,6 +263,9 @@ class Grid:
 
     def push(self, sensor: Sensor):
         lib().ref_grid_push(self.h, sensor.h)
+
+    def fill(self, tsd: float, weight: float, only_uninitialized: bool = False):
+        lib().ref_grid_fill(self.h, tsd, weight, 1 if only_uninitialized else 0)
 
     def partition_states(self):
         st = np.empty(self.n_partitions, dtype=np.int32)

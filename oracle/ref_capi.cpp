@@ -175,6 +175,28 @@ int ref_grid_download_partition(void* g, int p, double* tsd, double* weight)
   return 1;
 }
 
+// Bench set-up aid (no hot-path arithmetic): allocate every partition through the public
+// TsdGridPartition::init and set all (dim+1)^2 cells, so that a push runs in the dense regime
+// (every in-range partition already allocated, BASELINE.md section 2 "observation").
+void ref_grid_fill(void* g, double tsd, double weight, int only_uninitialized)
+{
+  TsdGrid* grid = (TsdGrid*)g;
+  const int per = grid->getCellsX() / grid->getPartitionSize();
+  for(int p = 0; p < per * per; p++)
+  {
+    TsdGridPartition* part = grid->getPartitions()[0][p];
+    if(only_uninitialized && part->isInitialized()) continue;
+    part->init(grid->getMaxTruncation());
+    const unsigned int w = part->getWidth(), h = part->getHeight();
+    for(unsigned int y = 0; y <= h; y++)
+      for(unsigned int x = 0; x <= w; x++)
+      {
+        part->_grid[y][x].tsd = tsd;
+        part->_grid[y][x].weight = weight;
+      }
+  }
+}
+
 // TsdGrid::storeGrid (TsdGrid.cpp:548-607)
 int ref_grid_store(void* g, const char* path) { return ((TsdGrid*)g)->storeGrid(path) ? 1 : 0; }
 // TsdGrid(const std::string&, FILE_SOURCE) (TsdGrid.cpp:25-110)

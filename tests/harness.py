@@ -138,3 +138,113 @@ class Sequence:
             out["grid_report"] = lines
         self.last = dict(model=ca, mask_m=ma, scene=scene, mask_s=mask_s, normals=na)
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# golden replay: the fixtures under tests/golden/ were produced by the reference itself
+# (tests/make_golden.py); any backend with the port's surface can be replayed against them.
+# ------------------------------------------------------------------------------------------------
+import os
+
+from ohm_tsd_slam_b200.scan import Scan
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def grid_checksum(g, states) -> np.ndarray:
+    acc_t = np.uint64(0)
+    acc_w = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for p in np.nonzero(states == 2)[0]:
+            t, w = g.download_partition(int(p))
+            t = np.where(np.isnan(t), np.float64("nan"), t)
+            acc_t += t.view(np.uint64).sum(dtype=np.uint64) * np.uint64(int(p) * 2 + 1)
+            acc_w += w.view(np.uint64).sum(dtype=np.uint64) * np.uint64(int(p) * 2 + 1)
+    return np.array([acc_t, acc_w], dtype=np.uint64)
+
+
+def replay_golden_sequence(backend, name: str, exact_icp: bool, pose_tol: float = 1e-9, **kw):
+    """Replays tests/golden/sequence_<name>.npz on `backend`; returns a list of failure strings."""
+    G = np.load(os.path.join(GOLDEN, f"sequence_{name}.npz"))
+    cfg = synth.config(name)
+    fails = []
+    g = backend.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid, **kw)
+    g.set_max_truncation(cfg.max_truncation)
+    icp = backend.Icp(30, 0.4, 0.02, g.bounds, **kw)
+    n_scans = int(G["n_scans"])
+    scans = list(cfg.scans(n_scans))
+    # first scan: host-side sensor mirror (also checked against the reference's data/mask below)
+    hs = HostSensor(cfg.sensor, lambda T: np.eye(3))
+    (x, y, th), r0 = scans[0]
+    hs.set_scan(r0)
+    T0 = synth.pose_matrix(x, y, th)
+    hs.transform(T0)
+    inv = getattr(backend, "invert3x3")
+    assert g.free_footprint(x, y, 0.6, 0.6)
+    g.push(Scan(cfg.sensor, hs.data, hs.mask, hs.T, inv(hs.T)))
+    for k in range(n_scans - 1):
+        hs.set_scan(scans[k + 1][1])
+        if not same(hs.data, G[f"data_{k}"]) or not same(hs.mask, G[f"mask_{k}"]):
+            fails.append(f"scan {k}: host sensor data/mask differ from the reference's setStandardMask")
+        pose = G[f"pose_{k}"]
+        pinv = inv(pose)
+        if not same(pinv, G[f"pose_inv_{k}"]):
+            fails.append(f"scan {k}: invert3x3 differs from the reference's Matrix::invert")
+        sc = Scan(cfg.sensor, G[f"data_{k}"], G[f"mask_{k}"], pose, G[f"pose_inv_{k}"])
+        c, nrm, m, cnt = g.raycast_mask(sc, G[f"rays_{k}"])
+        gm = G[f"rc_mask_{k}"]
+        if not same(m, gm):
+            fails.append(f"scan {k}: raycast mask differs at {int((m != gm).sum())} beams")
+        both = (m > 0) & (gm > 0)
+        if not same(c[both], G[f"rc_coords_{k}"][both]):
+            fails.append(f"scan {k}: raycast coords differ, max abs {np.max(np.abs(c[both] - G[f'rc_coords_{k}'][both])):.3e}")
+        if not same(nrm[both], G[f"rc_normals_{k}"][both]):
+            fails.append(f"scan {k}: raycast normals differ")
+        # ICP on the reference's own model/scene
+        scene = np.zeros((cfg.sensor.beams, 2))
+        valid = (~np.isinf(G[f"data_{k}"])) & (G[f"mask_{k}"] != 0)
+        scene[valid, 0] = hs.rays_local[0, valid] * G[f"data_{k}"][valid]
+        scene[valid, 1] = hs.rays_local[1, valid] * G[f"data_{k}"][valid]
+        Mv = G[f"rc_coords_{k}"][gm > 0]
+        Nv = G[f"rc_normals_{k}"][gm > 0]
+        Sv = scene[valid]
+        T, mse, pairs, its, st = icp.run(Mv, Nv, Sv, pose)
+        gs = G[f"icp_stats_{k}"]
+        if (pairs, its, st) != (int(gs[1]), int(gs[2]), int(gs[3])):
+            fails.append(f"scan {k}: icp pairs/iterations/state {(pairs, its, st)} vs {tuple(gs[1:])}")
+        if exact_icp:
+            if not same(T, G[f"icp_T_{k}"]) or mse != gs[0]:
+                fails.append(f"scan {k}: icp T/mse not bit-exact")
+        else:
+            if np.max(np.abs(T - G[f"icp_T_{k}"])) > pose_tol or abs(mse - gs[0]) > 1e-12:
+                fails.append(f"scan {k}: icp T differs by {np.max(np.abs(T - G[f'icp_T_{k}'])):.3e}")
+        cap = max(len(Mv), len(Sv), 1)
+        nit, pm, ps, pc, _, _ = icp.trace(cap)
+        gpc = G[f"icp_pair_count_{k}"]
+        if nit != len(gpc) or not same(pc[:nit], gpc):
+            fails.append(f"scan {k}: icp per-iteration pair counts differ")
+        else:
+            fm = np.concatenate([pm[i, :pc[i]] for i in range(nit)])
+            fs = np.concatenate([ps[i, :pc[i]] for i in range(nit)])
+            if not same(fm, G[f"icp_pairs_model_{k}"]) or not same(fs, G[f"icp_pairs_scene_{k}"]):
+                fails.append(f"scan {k}: icp pair lists differ")
+        # map update with the reference's pose
+        pa = G[f"pose_after_{k}"]
+        g.push(Scan(cfg.sensor, G[f"data_{k}"], G[f"mask_{k}"], pa, inv(pa)))
+        st_, iw = g.partition_states()
+        if not same(st_, G[f"states_{k}"]) or not same(iw, G[f"initw_{k}"]):
+            fails.append(f"scan {k}: partition states / init weights differ")
+    st_, _ = g.partition_states()
+    for i, p in enumerate(G["dump_parts"]):
+        t, w = g.download_partition(int(p))
+        if not same(t, G["dump_tsd"][i]) or not same(w, G["dump_weight"][i]):
+            fails.append(f"final cells of partition {int(p)} differ")
+    if not same(grid_checksum(g, st_), G["checksum"]):
+        fails.append("checksum over all cells differs")
+    t, s_ = g.interpolate_bilinear(G["interp_xy"])
+    if not same(s_, G["interp_status"]) or not same(t, G["interp_tsd"]):
+        fails.append("interpolateBilinear differs")
+    nn, ok = g.interpolate_normal(G["interp_xy"])
+    if not same(ok, G["normal_ok"]) or not same(nn[ok > 0], G["normal_n"][ok > 0]):
+        fails.append("interpolateNormal differs")
+    return fails

@@ -1,0 +1,61 @@
+"""The C-ABI shared library loads and exports every symbol include/tsdslam_b200.h declares; without a CUDA
+device the compute entry points fail loudly (TSD_E_NO_DEVICE) -- there is no CPU path.  CPU only."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ohm_tsd_slam_b200 import capi
+from oracle import port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "tsdslam_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b([a-z_0-9]+)\s*\([^;{]*\)\s*;", src)
+    return sorted(set(n for n in names if n.startswith(("tsd", "icp_", "match_"))))
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    names = declared_functions()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(set(capi.EXPORTS)) == names
+
+
+def test_invert3x3_matches_oracle():
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        th = rng.uniform(-3, 3)
+        T = np.array([[np.cos(th), -np.sin(th), rng.uniform(0, 100)], [np.sin(th), np.cos(th), rng.uniform(0, 100)], [0, 0, 1.0]])
+        assert np.array_equal(capi.invert3x3(T), port.invert3x3(T))
+        assert np.allclose(capi.invert3x3(T) @ T, np.eye(3), atol=1e-12)
+
+
+def test_no_cpu_fallback():
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    rc = capi.lib().tsdg_create(0.025, 5, 8, 0, C.byref(h))
+    assert rc == -2 and not h.value  # TSD_E_NO_DEVICE
+    assert b"no CPU path" in capi.lib().tsd_last_error()
+    with pytest.raises(capi.TsdError):
+        capi.Grid(0.025, 5, 8)
+    with pytest.raises(capi.TsdError):
+        capi.Icp(30, 0.4, 0.02, (0, 1, 0, 1))
+    with pytest.raises(capi.TsdError):
+        capi.Matcher()
+
+
+def test_argument_validation():
+    h = C.c_void_p()
+    assert capi.lib().tsdg_create(0.025, 4, 8, 0, C.byref(h)) in (-1, -2)  # only 32x32 partitions
+    assert capi.lib().tsdg_create(0.025, 5, 20, 0, C.byref(h)) in (-1, -2)
+    assert capi.lib().tsdg_push(None, None) == -1
+    assert capi.lib().tsdg_destroy(None) == 0

@@ -1,0 +1,48 @@
+"""Host-side pieces: synthetic data generator determinism, the host sensor mirror, gslcblas-order gemm."""
+import numpy as np
+
+from ohm_tsd_slam_b200 import synth
+from ohm_tsd_slam_b200.scan import HostSensor, gemm_nn, standard_mask
+from oracle import port
+
+
+def test_synth_is_deterministic_and_hokuyo_like():
+    a = list(synth.config("C1").scans(3))
+    b = list(synth.config("C1").scans(3))
+    for (pa, ra), (pb, rb) in zip(a, b):
+        assert pa == pb and np.array_equal(ra, rb)
+    r = a[0][1]
+    assert r.dtype == np.float32 and len(r) == 1081
+    assert np.isinf(r).sum() > 0 and (r == 0).sum() > 0
+    fin = r[np.isfinite(r) & (r > 0)]
+    assert fin.min() > 0.1 and fin.max() <= 30.0
+
+
+def test_gemm_nn_skips_zero_coefficients():
+    A = np.array([[0.0, 2.0], [3.0, 0.0]])
+    B = np.array([[np.inf, 1.0], [1.0, np.nan]])
+    C = gemm_nn(A, B)
+    # 0 * inf and 0 * nan are never formed
+    assert C[0, 0] == 2.0 and np.isnan(C[0, 1]) and np.isinf(C[1, 0]) and C[1, 1] == 3.0
+
+
+def test_standard_mask_rules():
+    spec = synth.SensorSpec(beams=9, angular_res=np.pi / 180, max_range=10.0)
+    data = np.array([1.0, 0.0, np.nan, 20.0, 1.0, 1.0, 5.0, 1.0, 1.0])
+    d, m = standard_mask(data, spec)
+    assert m[1] == 0 and m[2] == 0 and np.isinf(d[2]) and np.isinf(d[3]) and m[3] == 1
+    assert m[6] == 0  # 5 m between 1 m neighbours: acute angle -> depth discontinuity
+
+
+def test_host_sensor_scene_and_rays():
+    cfg = synth.config("tiny")
+    hs = HostSensor(cfg.sensor, port.invert3x3)
+    (x, y, th), r = next(iter(cfg.scans(1)))
+    hs.set_scan(r)
+    hs.transform(synth.pose_matrix(x, y, th))
+    rays = hs.normalized_rays(cfg.cell_size)
+    assert np.allclose(np.hypot(rays[0], rays[1]), cfg.cell_size, rtol=1e-12)
+    coords, mask, n = hs.scene()
+    assert n == int(mask.sum()) and np.allclose(np.hypot(*coords[mask > 0].T), hs.data[mask > 0], rtol=1e-12)
+    sc = hs.scan()
+    assert np.allclose(sc.pose_inv @ sc.pose, np.eye(3), atol=1e-12)
