@@ -196,7 +196,9 @@ int icp_destroy(tsd_icp_t* icp);
 int icp_run(tsd_icp_t* icp, const double* model, const double* normals, int32_t n_model, const double* scene,
             int32_t n_scene, const double pose[9], const double* t_init, double t_out[9], double* mse,
             uint32_t* pairs, uint32_t* iterations, int32_t* state);
-/* Parity aid: pair list, mse and accumulated 4x4 of every iteration of the last icp_run.
+/* Parity aid, off by default: record the pair list of every iteration (icp_get_trace). */
+int icp_set_trace(tsd_icp_t* icp, int enable);
+/* Parity aid: pair list, mse and accumulated 4x4 of every iteration of the last icp_run (tracing enabled).
  * pair_model/pair_scene: max_it x cap; returns iterations stored through *n_it. */
 int icp_get_trace(tsd_icp_t* icp, int32_t max_it, int32_t cap, uint32_t* pair_model, uint32_t* pair_scene,
                   int32_t* pair_count, double* mse, double* t_final16, int32_t* n_it);

@@ -27,7 +27,7 @@ EXPORTS = [
     "tsdg_stream", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
-    "icp_create", "icp_destroy", "icp_run", "icp_get_trace",
+    "icp_create", "icp_destroy", "icp_run", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
 
@@ -80,6 +80,7 @@ def lib():
     L.icp_create.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_uint32, _dp, C.c_int, _vpp]
     L.icp_destroy.argtypes = [C.c_void_p]
     L.icp_run.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _up, _up, _ip]
+    L.icp_set_trace.argtypes = [C.c_void_p, C.c_int]
     L.icp_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _up, _up, _ip, _dp, _dp, _ip]
     L.match_create.argtypes = [C.c_int, _vpp]
     L.match_destroy.argtypes = [C.c_void_p]
@@ -270,6 +271,11 @@ class Icp:
         check(lib().icp_create(max_iterations, dist_max, dist_min, (max_iterations - 10) & 0xFFFFFFFF, _d(b), device,
                                C.byref(h)))
         self.h = h
+        self._tracing = False
+
+    def set_trace(self, enable: bool = True):
+        check(lib().icp_set_trace(self.h, 1 if enable else 0))
+        self._tracing = enable
 
     def close(self):
         if getattr(self, "h", None):

@@ -107,6 +107,62 @@ __device__ __forceinline__ int sample_bilinear(const GridView& g, double cx, dou
   return TSD_INTERPOLATE_SUCCESS;
 }
 
+// sample_bilinear split in two so that a caller can put independent work between the loads and their first
+// use: sample_issue() computes the cell, issues the flag + 4 cell loads from clamped, always-valid addresses;
+// sample_finish() forms the same sum and status as sample_bilinear.
+struct SampleLoads
+{
+  double g00, g10, g01, g11, wx, wy;
+  int pre;  // 0, or the status already known from the geometry (INVALIDINDEX / NOT_OWNED)
+  unsigned char flag;
+};
+
+__device__ __forceinline__ SampleLoads sample_issue(const GridView& g, double cx, double cy)
+{
+  SampleLoads L;
+  const double dCoordX = cx * g.inv_cell_size;
+  const double dCoordY = cy * g.inv_cell_size;
+  int xIdx = __double2int_rd(dCoordX);
+  int yIdx = __double2int_rd(dCoordY);
+  double dx = ((double)xIdx + 0.5) * g.cell_size;
+  double dy = ((double)yIdx + 0.5) * g.cell_size;
+  if(cx < dx) { xIdx--; dx -= g.cell_size; }
+  if(cy < dy) { yIdx--; dy -= g.cell_size; }
+  const bool inb = !((xIdx >= g.cells_x) || (xIdx < 0) || (yIdx >= g.cells_y) || (yIdx < 0));
+  const int xc = inb ? xIdx : 0, yc = inb ? yIdx : g.row_begin * 32;
+  const int py = yc >> 5, px = xc >> 5;
+  const int p = py * g.parts_x + px;
+  const int x = xc & 31, y = yc & 31;
+  L.flag = __ldg(g.flags + p);
+  const bool owned = !(py < g.row_begin || py >= g.row_end);
+  L.wx = fabs((cx - dx) * g.inv_cell_size);
+  L.wy = fabs((cy - dy) * g.inv_cell_size);
+  const double* t = g.tsd + (size_t)(owned ? (p - g.row_begin * g.parts_x) : 0) * TSD_TILE_STRIDE;
+  const int i00 = y * 32 + x;
+  const int i10 = (y == 31) ? (TSD_BORDER_OFF + 32 + x) : (i00 + 32);
+  const int i01 = (x == 31) ? (TSD_BORDER_OFF + y) : (i00 + 1);
+  const int i11 = (x == 31) ? ((y == 31) ? (TSD_BORDER_OFF + 64) : (TSD_BORDER_OFF + y + 1))
+                            : ((y == 31) ? (TSD_BORDER_OFF + 32 + x + 1) : (i00 + 33));
+  L.g00 = __ldg(t + i00);
+  L.g10 = __ldg(t + i10);
+  L.g01 = __ldg(t + i01);
+  L.g11 = __ldg(t + i11);
+  L.pre = !inb ? TSD_INTERPOLATE_INVALIDINDEX : (!owned ? TSD_NOT_OWNED : 0);
+  return L;
+}
+
+__device__ __forceinline__ int sample_finish(const SampleLoads& L, double* out)
+{
+  const double v = L.g00 * (1. - L.wy) * (1. - L.wx) + L.g10 * L.wy * (1. - L.wx) + L.g01 * (1. - L.wy) * L.wx +
+                   L.g11 * L.wy * L.wx;
+  *out = v;
+  if(L.pre == TSD_INTERPOLATE_INVALIDINDEX) return TSD_INTERPOLATE_INVALIDINDEX;
+  if(!L.flag) return TSD_INTERPOLATE_EMPTYPARTITION;
+  if(L.pre == TSD_NOT_OWNED) return TSD_NOT_OWNED;
+  if(isnan(v)) return TSD_INTERPOLATE_ISNAN;
+  return TSD_INTERPOLATE_SUCCESS;
+}
+
 // TsdGrid::interpolateNormal (TsdGrid.cpp:517-546) + norm2 (mathbase.h:212-218)
 __device__ __forceinline__ bool sample_normal(const GridView& g, double cx, double cy, double* nx, double* ny)
 {
@@ -178,12 +234,18 @@ struct tsd_grid
   double2* d_dirs;
   int dirs_n;
   double dirs_phi_min, dirs_res;
-  // staged scan
+  // staged scan + rays: one device block and one pinned mirror (grid.cu ensure_scan_capacity)
   int scan_cap;
+  size_t in_bytes, rc_bytes;
+  unsigned char* d_in;
+  unsigned char* h_in;   // pinned
+  unsigned char* d_rc;
+  unsigned char* h_rc;   // pinned
+  unsigned long long rc_steps_prev[2];
   double* d_ranges;
   uint8_t* d_mask;
-  double* h_ranges;    // pinned
-  uint8_t* h_mask;     // pinned
+  double* h_ranges;
+  uint8_t* h_mask;
   // raycast buffers (sized with the scan)
   double* d_rays;
   double* d_rc_out;        // 4 doubles per beam: cx cy nx ny
@@ -210,7 +272,7 @@ struct tsd_grid
 
 namespace tsd
 {
-int grid_stage_scan(tsd_grid* g, const tsd_scan_t* scan, ScanDev* sd);  // H2D of ranges/mask (+dirs table)
+int grid_stage_scan(tsd_grid* g, const tsd_scan_t* scan, ScanDev* sd, const double* rays_world);  // one H2D copy
 int grid_ensure_scratch(tsd_grid* g, size_t bytes);
 GridView grid_view(const tsd_grid* g);
 }

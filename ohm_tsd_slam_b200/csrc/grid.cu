@@ -346,7 +346,7 @@ __device__ __forceinline__ void empty_cell(double& tsd, double& weight)
 // K2 + K3.  Persistent CTAs; the scan and the beam-boundary table are staged in shared memory once per CTA.
 // Thread t of 256 owns the cell pair x = 2*(t%16), 2*(t%16)+1 in rows t/16 and t/16 + 16: a warp reads two
 // adjacent 256-B rows (512 contiguous bytes) per 16-byte vector load.
-__global__ void __launch_bounds__(UPDATE_THREADS) k_update(PushParams pp)
+__global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   const ScanDev& s = pp.scan;
@@ -372,6 +372,20 @@ __global__ void __launch_bounds__(UPDATE_THREADS) k_update(PushParams pp)
 
   for(uint32_t item = blockIdx.x; item < nActive + nEmptied; item += gridDim.x)
   {
+    {
+      // pull the next partition of this CTA towards L2 while this one is being computed
+      const uint32_t nxt = item + gridDim.x;
+      if(nxt < nActive + nEmptied)
+      {
+        const uint32_t e = (nxt < nActive) ? pp.active[nxt] : (pp.emptied[nxt - nActive] | 0x80000000u);
+        if(e & 0x80000000u)
+        {
+          const size_t nb = (size_t)((e & 0x7fffffffu) - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE + (size_t)t * 4;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp.tsd + nb));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp.weight + nb));
+        }
+      }
+    }
     if(item < nActive)
     {
       const uint32_t e = pp.active[item];
@@ -671,43 +685,60 @@ int grid_ensure_scratch(tsd_grid* g, size_t bytes)
   return TSD_OK;
 }
 
+// One device block and one pinned mirror hold everything a scan brings with it, so that staging is a single
+// H2D copy:  [ ranges: cap doubles | mask: cap bytes | rays: 2*cap doubles ].  The ray-caster's results come
+// back in one D2H copy of  [ out: 4*cap doubles | keys: cap u64 | steps: 2 u64 ].
 static int ensure_scan_capacity(tsd_grid* g, int n)
 {
   if(n <= g->scan_cap) return TSD_OK;
   TSD_CUDA(cudaStreamSynchronize(g->stream));
-  cudaFree(g->d_ranges); cudaFree(g->d_mask); cudaFree(g->d_dirs); cudaFree(g->d_rays); cudaFree(g->d_rc_out);
-  cudaFree(g->d_rc_keys);
-  cudaFreeHost(g->h_ranges); cudaFreeHost(g->h_mask); cudaFreeHost(g->h_rc_out); cudaFreeHost(g->h_rc_keys);
-  cudaFreeHost(g->h_rays);
+  cudaFree(g->d_in); cudaFree(g->d_dirs); cudaFree(g->d_rc);
+  cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc);
   const int cap = ((n + 63) / 64) * 64 + 64;
-  TSD_CUDA(cudaMalloc(&g->d_ranges, sizeof(double) * cap));
-  TSD_CUDA(cudaMalloc(&g->d_mask, cap));
+  g->in_bytes = sizeof(double) * cap + cap + sizeof(double) * 2 * cap;
+  g->rc_bytes = sizeof(double) * 4 * cap + sizeof(unsigned long long) * cap + sizeof(unsigned long long) * 2;
+  TSD_CUDA(cudaMalloc(&g->d_in, g->in_bytes));
+  TSD_CUDA(cudaMalloc(&g->d_rc, g->rc_bytes));
   TSD_CUDA(cudaMalloc(&g->d_dirs, sizeof(double2) * (cap + 1)));
-  TSD_CUDA(cudaMalloc(&g->d_rays, sizeof(double) * 2 * cap));
-  TSD_CUDA(cudaMalloc(&g->d_rc_out, sizeof(double) * 4 * cap));
-  TSD_CUDA(cudaMalloc(&g->d_rc_keys, sizeof(unsigned long long) * cap));
-  TSD_CUDA(cudaMallocHost(&g->h_ranges, sizeof(double) * cap));
-  TSD_CUDA(cudaMallocHost(&g->h_mask, cap));
-  TSD_CUDA(cudaMallocHost(&g->h_rc_out, sizeof(double) * 4 * cap));
-  TSD_CUDA(cudaMallocHost(&g->h_rc_keys, sizeof(unsigned long long) * cap));
-  TSD_CUDA(cudaMallocHost(&g->h_rays, sizeof(double) * 2 * cap));
+  TSD_CUDA(cudaMallocHost(&g->h_in, g->in_bytes));
+  TSD_CUDA(cudaMallocHost(&g->h_rc, g->rc_bytes));
+  TSD_CUDA(cudaMemsetAsync(g->d_rc, 0, g->rc_bytes, g->stream));
+  memset(g->h_rc, 0, g->rc_bytes);
+  g->d_ranges = reinterpret_cast<double*>(g->d_in);
+  g->d_mask = g->d_in + sizeof(double) * cap;
+  g->d_rays = reinterpret_cast<double*>(g->d_in + sizeof(double) * cap + cap);
+  g->h_ranges = reinterpret_cast<double*>(g->h_in);
+  g->h_mask = g->h_in + sizeof(double) * cap;
+  g->h_rays = reinterpret_cast<double*>(g->h_in + sizeof(double) * cap + cap);
+  g->d_rc_out = reinterpret_cast<double*>(g->d_rc);
+  g->d_rc_keys = reinterpret_cast<unsigned long long*>(g->d_rc + sizeof(double) * 4 * cap);
+  g->d_rc_steps = g->d_rc_keys + cap;
+  g->h_rc_out = reinterpret_cast<double*>(g->h_rc);
+  g->h_rc_keys = reinterpret_cast<unsigned long long*>(g->h_rc + sizeof(double) * 4 * cap);
+  g->h_rc_steps = g->h_rc_keys + cap;
+  g->rc_steps_prev[0] = g->rc_steps_prev[1] = 0;
   g->scan_cap = cap;
   g->dirs_n = -1;
   return TSD_OK;
 }
 
-int grid_stage_scan(tsd_grid* g, const tsd_scan_t* scan, ScanDev* sd)
+int grid_stage_scan(tsd_grid* g, const tsd_scan_t* scan, ScanDev* sd, const double* rays_world)
 {
   if(!scan || scan->n < 1 || !scan->ranges || !scan->mask) { set_error("invalid scan"); return TSD_E_INVALID; }
   int rc = ensure_scan_capacity(g, scan->n);
   if(rc) return rc;
   fill_scan_dev(scan, sd);
-  // the previous call's async copies out of the pinned staging buffers must have drained
+  // the previous call's async copy out of the pinned staging block must have drained
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   memcpy(g->h_ranges, scan->ranges, sizeof(double) * scan->n);
   memcpy(g->h_mask, scan->mask, scan->n);
-  TSD_CUDA(cudaMemcpyAsync(g->d_ranges, g->h_ranges, sizeof(double) * scan->n, cudaMemcpyHostToDevice, g->stream));
-  TSD_CUDA(cudaMemcpyAsync(g->d_mask, g->h_mask, scan->n, cudaMemcpyHostToDevice, g->stream));
+  size_t bytes = sizeof(double) * g->scan_cap + scan->n;
+  if(rays_world)
+  {
+    memcpy(g->h_rays, rays_world, sizeof(double) * 2 * scan->n);
+    bytes = sizeof(double) * g->scan_cap + g->scan_cap + sizeof(double) * 2 * scan->n;
+  }
+  TSD_CUDA(cudaMemcpyAsync(g->d_in, g->h_in, bytes, cudaMemcpyHostToDevice, g->stream));
   sd->ranges = g->d_ranges;
   sd->mask = g->d_mask;
   if(g->dirs_n != scan->n || g->dirs_phi_min != scan->phi_min || g->dirs_res != scan->angular_res)
@@ -868,10 +899,8 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMalloc(&g->d_stats64, sizeof(unsigned long long) * 4));
   TSD_CUDA(cudaMalloc(&g->d_coltab, sizeof(double) * 3 * g->cells_x));
   TSD_CUDA(cudaMalloc(&g->d_rowtab, sizeof(double) * 3 * g->cells_y));
-  TSD_CUDA(cudaMalloc(&g->d_rc_steps, sizeof(unsigned long long) * 2));
   TSD_CUDA(cudaMallocHost(&g->h_counters, sizeof(uint32_t) * 16));
   TSD_CUDA(cudaMallocHost(&g->h_stats64, sizeof(unsigned long long) * 4));
-  TSD_CUDA(cudaMallocHost(&g->h_rc_steps, sizeof(unsigned long long) * 2));
   TSD_CUDA(cudaMemsetAsync(g->d_flags, 0, g->n_parts, g->stream));
   TSD_CUDA(cudaMemsetAsync(g->d_initw, 0, sizeof(double) * g->n_parts, g->stream));
   TSD_CUDA(cudaMemsetAsync(g->d_counters, 0, sizeof(uint32_t) * 16, g->stream));
@@ -893,12 +922,10 @@ int tsdg_destroy(tsd_grid_t* g)
   if(g->stream) cudaStreamSynchronize(g->stream);
   cudaFree(g->d_tsd); cudaFree(g->d_weight); cudaFree(g->d_flags); cudaFree(g->d_initw); cudaFree(g->d_active);
   cudaFree(g->d_active_w); cudaFree(g->d_emptied); cudaFree(g->d_pending); cudaFree(g->d_counters);
-  cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_dirs); cudaFree(g->d_ranges);
-  cudaFree(g->d_mask); cudaFree(g->d_rays); cudaFree(g->d_rc_out); cudaFree(g->d_rc_keys); cudaFree(g->d_rc_steps);
-  cudaFree(g->d_scratch);
-  cudaFreeHost(g->h_ranges); cudaFreeHost(g->h_mask); cudaFreeHost(g->h_rc_out); cudaFreeHost(g->h_rc_keys);
-  cudaFreeHost(g->h_rays); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters); cudaFreeHost(g->h_stats64);
-  cudaFreeHost(g->h_rc_steps);
+  cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_dirs); cudaFree(g->d_in);
+  cudaFree(g->d_rc); cudaFree(g->d_scratch);
+  cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters);
+  cudaFreeHost(g->h_stats64);
   for(int i = 0; i < 4; i++) if(g->ev[i]) cudaEventDestroy(g->ev[i]);
   if(g->stream) cudaStreamDestroy(g->stream);
   cudaGetLastError();
@@ -963,7 +990,7 @@ int tsdg_stage_scan(tsd_grid_t* g, const tsd_scan_t* scan)
 {
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
-  int rc = grid_stage_scan(g, scan, &g->staged);
+  int rc = grid_stage_scan(g, scan, &g->staged, nullptr);
   if(rc) return rc;
   g->has_staged = true;
   return TSD_OK;

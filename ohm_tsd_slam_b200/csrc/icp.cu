@@ -8,11 +8,12 @@
 // assign/filter/OutOfBoundsFilter2D.cpp:27-37, DistanceFilter.cpp:32-64, ReciprocalFilter.cpp:32-78;
 // ClosedFormEstimator2D.cpp:36-109.  Wiring: src/ThreadLocalize.cpp:210-225, :571-581.
 //
-// Pairing replaces FLANN's kd-tree by a uniform bucket grid over the model points, built once per run
-// (the model does not move during ICP).  The search is EXACT: rings of buckets are visited until the best
-// squared distance is strictly below the squared distance to everything unvisited, or until everything
-// unvisited is beyond the distance filter's current threshold (such a pair is dropped by
-// DistanceFilter.cpp:38 whatever its model index).  Distances are computed as FLANN's L2 functor does
+// Pairing replaces FLANN's kd-tree by a spatial hash over the model points (cells of edge h = dist_max / 4,
+// hashed into ICP_SLOTS buckets), built once per run (the model does not move during ICP).  The search is
+// EXACT: square rings of cells around the query are visited until the best squared distance is strictly
+// below the squared distance to everything unvisited, or until everything unvisited is beyond the distance
+// filter's current threshold (such a pair is dropped by DistanceFilter.cpp:38 whatever its model index).
+// Hash collisions only add candidates, never remove any.  Distances are computed as FLANN's L2 functor does
 // ((0 + dx*dx) + dy*dy); ties go to the lowest model index, the rule the oracle's FLANN stand-in uses.
 //
 // Sums of the estimator are block reductions with a fixed tree, so results are deterministic but not
@@ -28,7 +29,7 @@ using namespace tsd;
 
 #define ICP_THREADS 1024
 #define ICP_MAX_POINTS 2048
-#define ICP_G 64  // bucket grid is ICP_G x ICP_G
+#define ICP_SLOTS 4096  // hash buckets
 
 struct IcpParams
 {
@@ -41,11 +42,15 @@ struct IcpParams
   double pose[9];
   double t_init[16];
   int has_init;
+  double hash_h;        // cell edge of the spatial hash over the model
+  double coarse_h;      // cell edge of the coarse occupancy bitmap (>= the largest distance threshold)
+  int max_rings;        // rings after which everything unvisited is beyond the distance filter
   const double* model;  // nM x 2
   const double* scene;  // nS x 2
   // outputs
   double* result;       // [0..8] T 3x3, [9] mse, [10] pairs, [11] iterations, [12] state
   // trace
+  int trace;            // 0: skip the per-iteration pair lists (icp_set_trace)
   int cap;
   unsigned* tr_model;
   unsigned* tr_scene;
@@ -71,30 +76,45 @@ struct tsd_icp
   double* h_stage;   // pinned: model + scene
   double* h_result;  // pinned
   int last_nM, last_nS;
+  int trace;
 };
 
-__device__ __forceinline__ double block_sum(double v, double* s_red, int tid)
+// cell coordinate of a point; clamped so that the hash input stays small and rings never overflow
+__device__ __forceinline__ int cell_of(double v, double v0, double invh)
 {
-#pragma unroll
-  for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if((tid & 31) == 0) s_red[tid >> 5] = v;
-  __syncthreads();
-  double r = (tid < ICP_THREADS / 32) ? s_red[tid] : 0.0;
-  if(tid < 32)
-  {
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    if(tid == 0) s_red[32] = r;
-  }
-  __syncthreads();
-  return s_red[32];
+  const double t = floor((v - v0) * invh);
+  return (int)fmin(fmax(t, -1.0e6), 1.0e6);
 }
 
-__device__ __forceinline__ int bucket_of(double v, double v0, double invh)
+__device__ __forceinline__ unsigned slot_of(int cx, int cy)
 {
-  int b = __double2int_rd((v - v0) * invh);
-  return min(max(b, 0), ICP_G - 1);
+  const unsigned hsh = (unsigned)cx * 73856093u ^ (unsigned)cy * 19349663u;
+  return (hsh ^ (hsh >> 15)) & (ICP_SLOTS - 1);
+}
+
+// sums NV values per thread over the block; results land in s_red[64 + k]
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double* v, double* s_red, int tid)
+{
+#pragma unroll
+  for(int k = 0; k < NV; k++)
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  __syncthreads();
+  if((tid & 31) == 0)
+#pragma unroll
+    for(int k = 0; k < NV; k++) s_red[k * 32 + (tid >> 5)] = v[k];
+  __syncthreads();
+  if(tid < 32 * NV)
+  {
+    double r = s_red[tid];  // warp k holds the 32 partials of value k
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    if((tid & 31) == 0) s_red[192 + (tid >> 5)] = r;
+  }
+  __syncthreads();
+#pragma unroll
+  for(int k = 0; k < NV; k++) v[k] = s_red[192 + k];
 }
 
 __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
@@ -107,71 +127,67 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
   double* s_my = s_mx + nM;
   double* s_sx = s_my + nM;
   double* s_sy = s_sx + nS;
-  double* s_d2 = s_sy + nS;                                          // nS
-  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_d2 + nS);  // nM
-  double* s_red = reinterpret_cast<double*>(s_best + nM);           // 136 (block_sum: 33, bounding box: 128)
-  double* s_T = s_red + 136;                                         // Tfinal 16, Tlast 16, misc 8
-  unsigned* s_win = reinterpret_cast<unsigned*>(s_T + 40);           // nM
-  int* s_nn = reinterpret_cast<int*>(s_win + nM);                    // nS
-  unsigned* s_scan = reinterpret_cast<unsigned*>(s_nn + nS);         // 40
-  unsigned short* s_bstart = reinterpret_cast<unsigned short*>(s_scan + 40);  // ICP_G*ICP_G + 1
-  unsigned short* s_bidx = s_bstart + (ICP_G * ICP_G + 2);           // nM
-  unsigned short* s_bcnt = s_bidx + ((nM + 1) & ~1);                 // ICP_G*ICP_G
+  double* s_d2 = s_sy + nS;                                                        // nS
+  double* s_lb = s_d2 + nS;                                                        // nS: lower bound of the NN distance
+  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_lb + nS);  // nM
+  double* s_red = reinterpret_cast<double*>(s_best + nM);                          // 208
+  double* s_T = s_red + 208;                                                       // Tfinal 16, Tlast 16
+  unsigned* s_win = reinterpret_cast<unsigned*>(s_T + 32);                         // nM
+  int* s_nn = reinterpret_cast<int*>(s_win + nM);                                  // nS
+  unsigned* s_scan = reinterpret_cast<unsigned*>(s_nn + nS);                       // 40
+  unsigned short* s_bstart = reinterpret_cast<unsigned short*>(s_scan + 40);       // ICP_SLOTS + 2
+  unsigned short* s_bcnt = s_bstart + (ICP_SLOTS + 2);                             // ICP_SLOTS
+  unsigned short* s_bidx = s_bcnt + ICP_SLOTS;                                     // nM (+1 pad)
+  unsigned* s_coarse = reinterpret_cast<unsigned*>(s_bidx + ((nM + 2) & ~1));      // 128 words: coarse occupancy bitmap
+  unsigned* s_occ = s_coarse + 128;                                                // 128 words: non-empty hash slots
 
   for(int i = tid; i < nM; i += ICP_THREADS) { s_mx[i] = P.model[2 * i]; s_my[i] = P.model[2 * i + 1]; }
-  for(int i = tid; i < nS; i += ICP_THREADS) { s_sx[i] = P.scene[2 * i]; s_sy[i] = P.scene[2 * i + 1]; }
-  for(int i = tid; i < ICP_G * ICP_G; i += ICP_THREADS) s_bcnt[i] = 0;
+  for(int i = tid; i < nS; i += ICP_THREADS) { s_sx[i] = P.scene[2 * i]; s_sy[i] = P.scene[2 * i + 1]; s_lb[i] = 0.0; }
+  for(int i = tid; i < ICP_SLOTS; i += ICP_THREADS) s_bcnt[i] = 0;
+  if(tid < 128) { s_coarse[tid] = 0u; s_occ[tid] = 0u; }
   if(tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0 : 0.0; s_T[16 + tid] = s_T[tid]; }
   __syncthreads();
 
-  // ---- bucket grid over the model (bounding box by block reduction with min/max) ----
-  double bx0, by0, invh, h;
-  {
-    double lx = 1e300, ly = 1e300, hx = -1e300, hy = -1e300;
-    for(int i = tid; i < nM; i += ICP_THREADS)
-    {
-      lx = fmin(lx, s_mx[i]); hx = fmax(hx, s_mx[i]);
-      ly = fmin(ly, s_my[i]); hy = fmax(hy, s_my[i]);
-    }
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1)
-    {
-      lx = fmin(lx, __shfl_xor_sync(0xffffffffu, lx, o)); hx = fmax(hx, __shfl_xor_sync(0xffffffffu, hx, o));
-      ly = fmin(ly, __shfl_xor_sync(0xffffffffu, ly, o)); hy = fmax(hy, __shfl_xor_sync(0xffffffffu, hy, o));
-    }
-    double* s_bb = s_red;  // scratch: 4 x 32
-    if((tid & 31) == 0) { s_bb[tid >> 5] = lx; s_bb[32 + (tid >> 5)] = hx; s_bb[64 + (tid >> 5)] = ly; s_bb[96 + (tid >> 5)] = hy; }
-    __syncthreads();
-    if(tid == 0)
-    {
-      for(int w = 1; w < ICP_THREADS / 32; w++)
-      {
-        lx = fmin(lx, s_bb[w]); hx = fmax(hx, s_bb[32 + w]); ly = fmin(ly, s_bb[64 + w]); hy = fmax(hy, s_bb[96 + w]);
-      }
-      double ext = fmax(hx - lx, hy - ly);
-      if(!(ext > 1e-6)) ext = 1e-6;
-      const double hh = ext / ICP_G * (1.0 + 1e-9);
-      s_T[32] = lx; s_T[33] = ly; s_T[34] = hh; s_T[35] = 1.0 / hh;
-    }
-    __syncthreads();
-    bx0 = s_T[32]; by0 = s_T[33]; h = s_T[34]; invh = s_T[35];
-  }
+  // ---- spatial hash of the model: counting sort of the points by hash slot ----
+  const double h = P.hash_h, invh = 1.0 / P.hash_h;
+  const double invhc = 1.0 / P.coarse_h;  // coarse cells: edge >= the distance filter's largest threshold
+  const double bx0 = s_mx[0], by0 = s_my[0];
   for(int i = tid; i < nM; i += ICP_THREADS)
   {
-    const int b = bucket_of(s_my[i], by0, invh) * ICP_G + bucket_of(s_mx[i], bx0, invh);
+    const unsigned b = slot_of(cell_of(s_mx[i], bx0, invh), cell_of(s_my[i], by0, invh));
     atomicAdd(reinterpret_cast<unsigned*>(s_bcnt) + (b >> 1), (b & 1) ? 0x10000u : 1u);  // u16 counters, nM <= 2048
+    const unsigned c = slot_of(cell_of(s_mx[i], bx0, invhc), cell_of(s_my[i], by0, invhc));
+    atomicOr(&s_coarse[c >> 5], 1u << (c & 31));
+    atomicOr(&s_occ[b >> 5], 1u << (b & 31));
   }
   __syncthreads();
-  if(tid == 0)
   {
-    unsigned acc = 0;
-    for(int b = 0; b < ICP_G * ICP_G; b++) { s_bstart[b] = (unsigned short)acc; acc += s_bcnt[b]; s_bcnt[b] = 0; }
-    s_bstart[ICP_G * ICP_G] = (unsigned short)acc;
+    // exclusive prefix over ICP_SLOTS = 4 * ICP_THREADS counters
+    const unsigned c0 = s_bcnt[4 * tid], c1 = s_bcnt[4 * tid + 1], c2 = s_bcnt[4 * tid + 2], c3 = s_bcnt[4 * tid + 3];
+    const unsigned mine = c0 + c1 + c2 + c3;
+    unsigned incl = mine;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1)
+    {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if((tid & 31) >= o) incl += t;
+    }
+    if((tid & 31) == 31) s_scan[tid >> 5] = incl;
+    __syncthreads();
+    unsigned off = incl - mine;
+    for(int w = 0; w < (tid >> 5); w++) off += s_scan[w];
+    s_bstart[4 * tid] = (unsigned short)off;
+    s_bstart[4 * tid + 1] = (unsigned short)(off + c0);
+    s_bstart[4 * tid + 2] = (unsigned short)(off + c0 + c1);
+    s_bstart[4 * tid + 3] = (unsigned short)(off + c0 + c1 + c2);
+    if(tid == ICP_THREADS - 1) s_bstart[ICP_SLOTS] = (unsigned short)(off + mine);
+    __syncthreads();
+    s_bcnt[4 * tid] = 0; s_bcnt[4 * tid + 1] = 0; s_bcnt[4 * tid + 2] = 0; s_bcnt[4 * tid + 3] = 0;
+    __syncthreads();
   }
-  __syncthreads();
   for(int i = tid; i < nM; i += ICP_THREADS)
   {
-    const int b = bucket_of(s_my[i], by0, invh) * ICP_G + bucket_of(s_mx[i], bx0, invh);
+    const unsigned b = slot_of(cell_of(s_mx[i], bx0, invh), cell_of(s_my[i], by0, invh));
     const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(s_bcnt) + (b >> 1), (b & 1) ? 0x10000u : 1u);
     const unsigned within = (b & 1) ? (old >> 16) : (old & 0xffffu);
     s_bidx[s_bstart[b] + within] = (unsigned short)i;
@@ -223,30 +239,58 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
     __syncthreads();
 
     // ---- A: pre-filter + exact 1-NN + distance filter ----
-    for(int i = tid; i < nS; i += ICP_THREADS)
+    // Queries [0, ICP_THREADS) : one per thread, ring search.  Queries beyond (nS > 1024) : one per warp,
+    // the lanes scan the cells of the (2R+1)^2 window that covers the distance filter's radius in parallel,
+    // so that the few left-over queries do not double the time of the whole phase.
+    const int nFirst = min(nS, ICP_THREADS);
+    if(tid < nFirst)
     {
+      const int i = tid;
       const double x = s_sx[i], y = s_sy[i];
       // OutOfBoundsFilter2D.cpp:27-37: S.transform(pose) = S * R^T + t
       double tx = 0.0; tx += x * P.pose[0]; tx += y * P.pose[1]; tx = 0.0 + 1.0 * tx; tx += P.pose[2];
       double ty = 0.0; ty += x * P.pose[3]; ty += y * P.pose[4]; ty = 0.0 + 1.0 * ty; ty += P.pose[5];
-      const bool masked = (tx < P.x_min || tx > P.x_max || ty < P.y_min || ty > P.y_max);
+      bool search = !(tx < P.x_min || tx > P.x_max || ty < P.y_min || ty > P.y_max);
       int best = -1;
       double bestD = __longlong_as_double(0x7ff0000000000000LL);
-      if(!masked)
+      // A point whose nearest model point is provably farther than the distance filter's threshold cannot
+      // yield a pair (DistanceFilter.cpp:38): its search is skipped.  s_lb[i] is a lower bound of that
+      // distance, carried over from the last search and reduced by how far the point moved since.
+      double lbNew = s_lb[i];
+      if(search && lbNew * lbNew > distSqr) search = false;
+      else if(search) lbNew = 0.0;
+      if(search)
       {
-        const int qx = bucket_of(x, bx0, invh), qy = bucket_of(y, by0, invh);
-        for(int r = 0; r < ICP_G; r++)
+        // a model point within the distance filter's radius lies in the 3x3 coarse cells around the query
+        const int cqx = cell_of(x, bx0, invhc), cqy = cell_of(y, by0, invhc);
+        unsigned any = 0;
+#pragma unroll
+        for(int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for(int dx = -1; dx <= 1; dx++)
+          {
+            const unsigned c = slot_of(cqx + dx, cqy + dy);
+            any |= (s_coarse[c >> 5] >> (c & 31)) & 1u;
+          }
+        search = any != 0;
+        if(!search) lbNew = P.coarse_h * (1.0 - 1e-6);  // nothing within one coarse cell
+      }
+      if(search)
+      {
+        const int qx = cell_of(x, bx0, invh), qy = cell_of(y, by0, invh);
+        for(int r = 0; r <= P.max_rings; r++)
         {
           const int x0 = qx - r, x1 = qx + r, y0 = qy - r, y1 = qy + r;
-          for(int by = max(y0, 0); by <= min(y1, ICP_G - 1); by++)
+          for(int by = y0; by <= y1; by++)
           {
             const bool edgeRow = (by == y0 || by == y1);
             const int step = edgeRow ? 1 : max(x1 - x0, 1);
             for(int bx = x0; bx <= x1; bx += step)
             {
-              if(bx < 0 || bx >= ICP_G) continue;
-              const int b = by * ICP_G + bx;
-              for(int k = s_bstart[b]; k < s_bstart[b + 1]; k++)
+              const unsigned b = slot_of(bx, by);
+              if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
+              const int k1 = s_bstart[b + 1];
+              for(int k = s_bstart[b]; k < k1; k++)
               {
                 const int m = s_bidx[k];
                 const double d0 = x - s_mx[m];
@@ -254,21 +298,75 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
                 double d = 0.0;
                 d += d0 * d0;
                 d += d1 * d1;
-                if(d < bestD || (d == bestD && m < best)) { bestD = d; best = m; }
+                if(d < bestD) { bestD = d; best = m; }
+                else if(d == bestD && m < best) best = m;
               }
             }
           }
-          // everything unvisited is farther than r*h (conservatively)
+          // everything unvisited lies in cells at Chebyshev distance > r, i.e. farther than r*h
           const double lb = (double)r * h * (1.0 - 1e-9);
           const double lb2 = lb * lb;
-          if(bestD < lb2 || distSqr < lb2) break;
-          if(x0 <= 0 && y0 <= 0 && x1 >= ICP_G - 1 && y1 >= ICP_G - 1) break;
+          if(bestD < lb2 || distSqr < lb2)
+          {
+            // nearest distance >= min(sqrt(bestD), lb), shaved by a relative 1e-9 against rounding
+            lbNew = fmin(sqrt(bestD), lb) * (1.0 - 1e-9);
+            break;
+          }
         }
       }
+      s_lb[i] = lbNew;
       const bool keep = (best >= 0) && (bestD <= distSqr);  // DistanceFilter.cpp:38
       s_nn[i] = keep ? best : -1;
       s_d2[i] = bestD;
       if(keep) atomicMin(&s_best[best], (unsigned long long)__double_as_longlong(bestD));
+    }
+    for(int i = ICP_THREADS + (tid >> 5); i < nS; i += ICP_THREADS / 32)
+    {
+      const int lane = tid & 31;
+      const double x = s_sx[i], y = s_sy[i];
+      double tx = 0.0; tx += x * P.pose[0]; tx += y * P.pose[1]; tx = 0.0 + 1.0 * tx; tx += P.pose[2];
+      double ty = 0.0; ty += x * P.pose[3]; ty += y * P.pose[4]; ty = 0.0 + 1.0 * ty; ty += P.pose[5];
+      const bool masked = (tx < P.x_min || tx > P.x_max || ty < P.y_min || ty > P.y_max);
+      int best = -1;
+      double bestD = __longlong_as_double(0x7ff0000000000000LL);
+      if(!masked)
+      {
+        // smallest R with (R * h)^2 > distSqr: the window then holds every point the distance filter keeps
+        int R = 1;
+        while(R < P.max_rings && !(distSqr < ((double)R * h * (1.0 - 1e-9)) * ((double)R * h * (1.0 - 1e-9)))) R++;
+        const int W = 2 * R + 1;
+        const int qx = cell_of(x, bx0, invh), qy = cell_of(y, by0, invh);
+        for(int c = lane; c < W * W; c += 32)
+        {
+          const unsigned b = slot_of(qx - R + c % W, qy - R + c / W);
+          if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
+          const int k1 = s_bstart[b + 1];
+          for(int k = s_bstart[b]; k < k1; k++)
+          {
+            const int m = s_bidx[k];
+            const double d0 = x - s_mx[m];
+            const double d1 = y - s_my[m];
+            double d = 0.0;
+            d += d0 * d0;
+            d += d1 * d1;
+            if(d < bestD || (d == bestD && m < best)) { bestD = d; best = m; }
+          }
+        }
+      }
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1)
+      {
+        const double od = __shfl_xor_sync(0xffffffffu, bestD, o);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+        if(ob >= 0 && (best < 0 || od < bestD || (od == bestD && ob < best))) { bestD = od; best = ob; }
+      }
+      if(lane == 0)
+      {
+        const bool keep = (best >= 0) && (bestD <= distSqr);
+        s_nn[i] = keep ? best : -1;
+        s_d2[i] = bestD;
+        if(keep) atomicMin(&s_best[best], (unsigned long long)__double_as_longlong(bestD));
+      }
     }
     __syncthreads();
     // ---- B: ReciprocalFilter.cpp:32-78: closest scene point per model point (lowest scene index on ties) ----
@@ -282,53 +380,64 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
     distSqr *= P.multiplier;
     if(distSqr < P.min_dist_sqr) distSqr = P.min_dist_sqr;
 
-    // ---- C: pair list in model order (trace) + ClosedFormEstimator2D::setPairs ----
-    double cm0 = 0, cm1 = 0, cs0 = 0, cs1 = 0, r = 0;
-    unsigned baseCount = 0;
-    for(int m0 = 0; m0 < nM; m0 += ICP_THREADS)
+    // ---- C: ClosedFormEstimator2D::setPairs (+ the pair list in model order when tracing) ----
+    double acc[6] = {0, 0, 0, 0, 0, 0};  // cm0 cm1 cs0 cs1 r count
+    if(P.trace)
     {
-      const int m = m0 + tid;
-      const bool has = (m < nM) && (s_win[m] != 0xffffffffu);
-      const unsigned bal = __ballot_sync(0xffffffffu, has);
-      if((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
-      __syncthreads();
-      unsigned off = baseCount;
-      for(int w = 0; w < (tid >> 5); w++) off += s_scan[w];
-      unsigned total = 0;
-      for(int w = 0; w < ICP_THREADS / 32; w++) total += s_scan[w];
-      if(has)
+      unsigned baseCount = 0;
+      for(int m0 = 0; m0 < nM; m0 += ICP_THREADS)
       {
-        const unsigned pos = off + __popc(bal & ((1u << (tid & 31)) - 1u));
-        const unsigned sidx = s_win[m];
-        if((int)iter < P.max_iterations && pos < (unsigned)P.cap)
+        const int m = m0 + tid;
+        const bool has = (m < nM) && (s_win[m] != 0xffffffffu);
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
+        __syncthreads();
+        unsigned off = baseCount;
+        unsigned total = 0;
+        for(int w = 0; w < ICP_THREADS / 32; w++)
         {
-          P.tr_model[(size_t)iter * P.cap + pos] = (unsigned)m;
-          P.tr_scene[(size_t)iter * P.cap + pos] = sidx;
+          const unsigned c = s_scan[w];
+          if(w < (tid >> 5)) off += c;
+          total += c;
         }
-        cm0 += s_mx[m]; cm1 += s_my[m];
-        cs0 += s_sx[sidx]; cs1 += s_sy[sidx];
+        if(has)
+        {
+          const unsigned pos = off + __popc(bal & ((1u << (tid & 31)) - 1u));
+          if((int)iter < P.max_iterations && pos < (unsigned)P.cap)
+          {
+            P.tr_model[(size_t)iter * P.cap + pos] = (unsigned)m;
+            P.tr_scene[(size_t)iter * P.cap + pos] = s_win[m];
+          }
+        }
+        baseCount += total;
+        __syncthreads();
+      }
+    }
+    for(int m = tid; m < nM; m += ICP_THREADS)
+    {
+      const unsigned sidx = s_win[m];
+      if(sidx != 0xffffffffu)
+      {
+        acc[0] += s_mx[m]; acc[1] += s_my[m];
+        acc[2] += s_sx[sidx]; acc[3] += s_sy[sidx];
         const double dx = s_sx[sidx] - s_mx[m];
         const double dy = s_sy[sidx] - s_my[m];
-        r += dx * dx + dy * dy;
+        acc[4] += dx * dx + dy * dy;
+        acc[5] += 1.0;
       }
-      baseCount += total;
-      __syncthreads();
     }
-    pairs = baseCount;
+    block_sum_n<6>(acc, s_red, tid);
+    pairs = (unsigned)acc[5];
 
     int retval = TSD_ICP_PROCESSING;
     if(pairs > 2)
     {
-      cm0 = block_sum(cm0, s_red, tid);
-      cm1 = block_sum(cm1, s_red, tid);
-      cs0 = block_sum(cs0, s_red, tid);
-      cs1 = block_sum(cs1, s_red, tid);
-      r = block_sum(r, s_red, tid);
       const double sizeInv = 1.0 / (double)pairs;
-      r *= sizeInv; cm0 *= sizeInv; cm1 *= sizeInv; cs0 *= sizeInv; cs1 *= sizeInv;
+      const double r = acc[4] * sizeInv;
+      const double cm0 = acc[0] * sizeInv, cm1 = acc[1] * sizeInv, cs0 = acc[2] * sizeInv, cs1 = acc[3] * sizeInv;
       rms = r;
       // estimateTransformation (ClosedFormEstimator2D.cpp:74-109)
-      double nom = 0, den = 0;
+      double nd[2] = {0, 0};
       for(int m = tid; m < nM; m += ICP_THREADS)
       {
         const unsigned sidx = s_win[m];
@@ -336,15 +445,14 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
         {
           const double xFCm = s_mx[m] - cm0, yFCm = s_my[m] - cm1;
           const double xSCs = s_sx[sidx] - cs0, ySCs = s_sy[sidx] - cs1;
-          nom += yFCm * xSCs - xFCm * ySCs;
-          den += xFCm * xSCs + yFCm * ySCs;
+          nd[0] += yFCm * xSCs - xFCm * ySCs;
+          nd[1] += xFCm * xSCs + yFCm * ySCs;
         }
       }
-      nom = block_sum(nom, s_red, tid);
-      den = block_sum(den, s_red, tid);
+      block_sum_n<2>(nd, s_red, tid);
       if(tid == 0)
       {
-        const double deltaTheta = atan2(nom, den);
+        const double deltaTheta = atan2(nd[0], nd[1]);
         const double c = cos(deltaTheta), s = sin(deltaTheta);
         const double deltaX = (cm0 - (c * cs0 - s * cs1));
         const double deltaY = (cm1 - (c * cs1 + s * cs0));
@@ -375,8 +483,13 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
           const double x = s_sx[i], y = s_sy[i];
           double a = 0.0; a += x * r00; a += y * r01; a = 0.0 + 1.0 * a;
           double b = 0.0; b += x * r10; b += y * r11; b = 0.0 + 1.0 * b;
-          s_sx[i] = a + t0;
-          s_sy[i] = b + t1;
+          const double nx = a + t0, ny = b + t1;
+          s_sx[i] = nx;
+          s_sy[i] = ny;
+          // the point moved by |(nx,ny) - (x,y)|: its nearest-neighbour distance shrank by at most that
+          const double mvx = nx - x, mvy = ny - y;
+          const double lb = s_lb[i] - sqrt(mvx * mvx + mvy * mvy) * (1.0 + 1e-9) - 1e-12;
+          s_lb[i] = lb > 0.0 ? lb : 0.0;
         }
       }
     }
@@ -417,11 +530,11 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
 static size_t icp_smem_bytes(int nM, int nS)
 {
   size_t b = 0;
-  b += sizeof(double) * (2 * (size_t)nM + 2 * (size_t)nS + nS);  // mx my sx sy d2
+  b += sizeof(double) * (2 * (size_t)nM + 2 * (size_t)nS + 2 * (size_t)nS);  // mx my sx sy d2 lb
   b += sizeof(unsigned long long) * nM;                           // best
-  b += sizeof(double) * 176;                                      // red + T
+  b += sizeof(double) * (208 + 32);                               // red + T
   b += sizeof(unsigned) * nM + sizeof(int) * nS + sizeof(unsigned) * 40;
-  b += sizeof(unsigned short) * (ICP_G * ICP_G + 2 + ((nM + 1) & ~1) + ICP_G * ICP_G);
+  b += sizeof(unsigned short) * (ICP_SLOTS + 2 + ICP_SLOTS + (size_t)nM + 2) + sizeof(unsigned) * 256;
   return b + 64;
 }
 
@@ -455,6 +568,16 @@ int icp_create(uint32_t max_iterations, double dist_max, double dist_min, uint32
   if(dist_iterations < 1) it = 1.0;
   p.multiplier = pow((dist_min / dist_max), 1.0 / it);
   p.x_min = bounds[0]; p.x_max = bounds[1]; p.y_min = bounds[2]; p.y_max = bounds[3];
+  {
+    double hh = fabs(dist_max) / 4.0;
+    if(!(hh >= 1e-3)) hh = 1e-3;
+    if(hh > 1e6) hh = 1e6;
+    p.hash_h = hh;
+    p.coarse_h = (fabs(dist_max) > hh ? fabs(dist_max) : hh) * (1.0 + 1e-9);
+    double rings = ceil(fabs(dist_max) / hh) + 2.0;
+    if(!(rings < 64.0)) rings = 64.0;
+    p.max_rings = (int)rings;
+  }
   h->cap = ICP_MAX_POINTS;
   TSD_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   TSD_CUDA(cudaMalloc(&h->d_model, sizeof(double) * 2 * h->cap));
@@ -521,6 +644,7 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   p.scene = h->d_scene;
   p.result = h->d_result;
   p.cap = h->cap;
+  p.trace = h->trace;
   p.tr_model = h->d_tr_model;
   p.tr_scene = h->d_tr_scene;
   p.tr_count = h->d_tr_count;
@@ -538,6 +662,13 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   *state = (int32_t)h->h_result[12];
   h->last_nM = n_model;
   h->last_nS = n_scene;
+  return TSD_OK;
+}
+
+int icp_set_trace(tsd_icp_t* h, int enable)
+{
+  if(!h) return TSD_E_INVALID;
+  h->trace = enable != 0;
   return TSD_OK;
 }
 

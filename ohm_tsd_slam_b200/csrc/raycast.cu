@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
   const int xDim = g.cells_x, yDim = g.cells_y;
   const double cellSize = g.cell_size;
 
+  __shared__ double2 s_pos[RC_WARPS][64];  // two passes of 32 positions per warp
   unsigned long long key = NO_EVENT;
   unsigned long long nFine = 0, nCoarse = 0;
   bool found = false;
@@ -105,27 +106,65 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
       carry = (sample_bilinear(g, pos0, pos1, &v) == TSD_INTERPOLATE_SUCCESS) ? v : __longlong_as_double(0x7ff8000000000000LL);
     }
 
-    // :243-270 fine loop, 32 steps per pass
-    double i = idxMin;
+    // :243-270 fine loop, 32 steps per pass.
+    // The position chain of a pass is computed by all lanes (uniform DADDs), lane 0 parks the 32 positions in
+    // shared memory and every lane picks up its own; the chain of pass c+1 is issued between the loads and the
+    // use of pass c's samples, so the L2 latency of the samples hides behind it.
+    // The loop counter `i += 1.0` of the reference only decides when the loop ends: it is replayed exactly
+    // (serially) only for passes that come within 2 steps of idxMax; elsewhere idxMin + k decides safely.
+    double2* buf = s_pos[threadIdx.x >> 5];
+    double iExact = idxMin;          // i of iteration kExact (exact serial value)
+    unsigned long long kExact = 0;
     unsigned long long base = 0;
+    int cur = 0;
+#pragma unroll 8
+    for(int k = 0; k < 32; k++)
+    {
+      pos0 += ray0;
+      pos1 += ray1;
+      if(lane == 0) buf[k] = make_double2(pos0, pos1);
+    }
+    __syncwarp();
     while(true)
     {
-      double mx = 0, my = 0, mi = 0;
+      const double2 mp = buf[cur * 32 + lane];
+      const double mx = mp.x, my = mp.y;
+      // validity of this lane's iteration: i_k <= idxMax
+      const double est = idxMin + (double)(base + (unsigned)lane);
+      bool valid;
+      const bool nearEnd = !(idxMin + (double)(base + 31u) + 2.0 < idxMax);
+      if(!nearEnd) valid = true;
+      else
+      {
+        double mi = 0.0;
+        // replay the reference's counter up to this pass (uniform), keep this lane's value
+        while(kExact < base) { iExact += 1.0; kExact++; }
+        double ii = iExact;
 #pragma unroll 8
-      for(int k = 0; k < 32; k++)
-      {
-        pos0 += ray0;
-        pos1 += ray1;
-        if(k == lane) { mx = pos0; my = pos1; mi = i; }
-        i += 1.0;
+        for(int k = 0; k < 32; k++)
+        {
+          if(k == lane) mi = ii;
+          ii += 1.0;
+        }
+        valid = mi <= idxMax;
+        (void)est;
       }
-      const bool valid = mi <= idxMax;
       double v = __longlong_as_double(0x7ff8000000000000LL);
-      if(valid)
+      double t = 0.0;
+      const SampleLoads sl = sample_issue(g, mx, my);  // all lanes: addresses are clamped, results masked below
+      // next pass's positions while the loads above are in flight
       {
-        double t;
-        if(sample_bilinear(g, mx, my, &t) == TSD_INTERPOLATE_SUCCESS) v = t;
+        double2* nb = buf + (cur ^ 1) * 32;
+#pragma unroll 8
+        for(int k = 0; k < 32; k++)
+        {
+          pos0 += ray0;
+          pos1 += ray1;
+          if(lane == 0) nb[k] = make_double2(pos0, pos1);
+        }
       }
+      const int rv = sample_finish(sl, &t);
+      if(valid && rv == TSD_INTERPOLATE_SUCCESS) v = t;
       double prev = __shfl_up_sync(0xffffffffu, v, 1);
       if(lane == 0) prev = carry;
       const bool hit = valid && (prev > 0) && (v < 0);
@@ -167,6 +206,8 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
       nFine += 32;
       base += 32;
       carry = __shfl_sync(0xffffffffu, v, 31);
+      cur ^= 1;
+      __syncwarp();
     }
   }
 
@@ -199,12 +240,11 @@ static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* r
   TSD_CUDA(cudaSetDevice(g->device));
   RayParams rp;
   memset(&rp, 0, sizeof(rp));
-  int rc = grid_stage_scan(g, scan, &rp.scan);
+  int rc = grid_stage_scan(g, scan, &rp.scan, rays_world);
   if(rc) return rc;
   const int n = scan->n;
-  memcpy(g->h_rays, rays_world, sizeof(double) * 2 * n);
-  TSD_CUDA(cudaMemcpyAsync(g->d_rays, g->h_rays, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, g->stream));
-  TSD_CUDA(cudaMemsetAsync(g->d_rc_steps, 0, sizeof(unsigned long long) * 2, g->stream));
+  g->rc_steps_prev[0] = g->h_rc_steps[0];  // the device counters run on; a call's steps are the difference
+  g->rc_steps_prev[1] = g->h_rc_steps[1];
   rp.g = grid_view(g);
   rp.rays = g->d_rays;
   rp.out = g->d_rc_out;
@@ -224,9 +264,7 @@ static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* r
   rp.idxMax = scan->max_range / g->cell_size;
   k_raycast<<<(n + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, g->stream>>>(rp);
   TSD_LAUNCHED();
-  TSD_CUDA(cudaMemcpyAsync(g->h_rc_out, g->d_rc_out, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, g->stream));
-  TSD_CUDA(cudaMemcpyAsync(g->h_rc_keys, g->d_rc_keys, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, g->stream));
-  TSD_CUDA(cudaMemcpyAsync(g->h_rc_steps, g->d_rc_steps, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, g->stream));
+  TSD_CUDA(cudaMemcpyAsync(g->h_rc, g->d_rc, g->rc_bytes, cudaMemcpyDeviceToHost, g->stream));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   return TSD_OK;
 }
@@ -283,8 +321,9 @@ int tsdg_raycast(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world
 int tsdg_last_raycast_steps(tsd_grid_t* g, uint64_t* fine_steps, uint64_t* coarse_steps)
 {
   if(!g) return TSD_E_INVALID;
-  if(fine_steps) *fine_steps = g->h_rc_steps[0];
-  if(coarse_steps) *coarse_steps = g->h_rc_steps[1];
+  if(!g->h_rc_steps) return TSD_E_INVALID;
+  if(fine_steps) *fine_steps = g->h_rc_steps[0] - g->rc_steps_prev[0];
+  if(coarse_steps) *coarse_steps = g->h_rc_steps[1] - g->rc_steps_prev[1];
   return TSD_OK;
 }
 

@@ -238,6 +238,9 @@ class Icp:
                            None if Ti is None else _d(Ti), _d(T), C.byref(mse), C.byref(pairs), C.byref(its), C.byref(st))
         return T, mse.value, pairs.value, its.value, st.value
 
+    def set_trace(self, enable: bool = True):
+        pass  # the port always records
+
     def trace(self, cap):
         mi = self.max_iterations
         pm = np.zeros((mi, cap), dtype=np.uint32)

@@ -74,6 +74,8 @@ class Sequence:
         self.sensor = HostSensor(cfg.sensor, invert)
         self.icp_a = backend_a.Icp(icp_iterations, dist[0], dist[1], self.ga.bounds)
         self.icp_b = backend_b.Icp(icp_iterations, dist[0], dist[1], self.gb.bounds, **b_kwargs)
+        self.icp_a.set_trace(True)
+        self.icp_b.set_trace(True)
         self.log = []
 
     def start(self, pose_xyt, ranges, footprint=(0.6, 0.6)):
@@ -171,6 +173,7 @@ def replay_golden_sequence(backend, name: str, exact_icp: bool, pose_tol: float 
     g = backend.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid, **kw)
     g.set_max_truncation(cfg.max_truncation)
     icp = backend.Icp(30, 0.4, 0.02, g.bounds, **kw)
+    icp.set_trace(True)
     n_scans = int(G["n_scans"])
     scans = list(cfg.scans(n_scans))
     # first scan: host-side sensor mirror (also checked against the reference's data/mask below)
