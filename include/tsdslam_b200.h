@@ -99,6 +99,13 @@ int tsdg_create(double cell_size, int layout_partition, int layout_grid, int dev
  * one halo partition row above the band is kept for the replicated borders. */
 int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, int device, int part_row_begin,
                      int part_row_end, tsd_grid_t** out);
+/* On a band, tsdg_push / tsdg_push_async / tsdg_push_staged stop after the cell update.  The caller then
+ * exchanges boundary partition rows with the neighbouring bands (tsdg_band_row: which 0/1 = my lowest /
+ * highest row to send, 2/3 = the halo slots below / above to receive into; count doubles each of tsd and
+ * weight; NULL when there is no such neighbour), calls tsdg_band_push_finish (replicated borders, K4) and
+ * exchanges the rows once more so that the halos carry the refreshed borders (ray casting reads them). */
+int tsdg_band_push_finish(tsd_grid_t* grid);
+int tsdg_band_row(tsd_grid_t* grid, int which, double** tsd, double** weight, uint64_t* count);
 int tsdg_destroy(tsd_grid_t* grid);
 
 /* TsdGrid::setMaxTruncation (TsdGrid.cpp:206-215; SlamNode.cpp:78).  Must precede the first push. */
@@ -170,9 +177,12 @@ int tsdg_raycast_mask(tsd_grid_t* grid, const tsd_scan_t* scan, const double* ra
 int tsdg_raycast(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_world, double* coords,
                  double* normals, uint32_t* count);
 
-/* Sharded grid: per-beam first event of this band.  key[i] = 2*step + (abort ? 1 : 0) (lower wins;
- * UINT64_MAX = no event); payload[i] = {cx, cy, nx, ny} in the sensor frame (valid for a hit).  The caller
- * min-reduces the keys over all bands (NCCL) and takes the payload of the winner. */
+/* Sharded grid: per-beam first event among the steps whose sample lies in THIS band.
+ * key[i] = 4*step + code (code 0: hit, 1: hit whose normal lookup failed, 2: abort; INT64_MAX: none);
+ * payload[i] = {cx, cy, nx, ny} in the sensor frame for a hit, zeros otherwise.  Both stay on the device
+ * (pointers valid until the next raycast on this handle).  The caller min-reduces the keys over all bands
+ * (ncclAllReduce min), zeroes the payload of the beams it did not win and sum-reduces the payloads; a beam
+ * is a hit iff the winning key has code 0 (ohm_tsd_slam_b200/sharded.py). */
 int tsdg_raycast_band_keys(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_world,
                            uint64_t** dev_keys, double** dev_payload);
 /* step counters of the most recent raycast on this handle */

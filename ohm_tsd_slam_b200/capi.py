@@ -22,7 +22,7 @@ _vpp = C.POINTER(C.c_void_p)
 
 EXPORTS = [
     "tsd_last_error", "tsd_device_count", "tsd_kernel_launches", "tsd_invert3x3",
-    "tsdg_create", "tsdg_create_band", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
+    "tsdg_create", "tsdg_create_band", "tsdg_band_push_finish", "tsdg_band_row", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
     "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged",
     "tsdg_stream", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
@@ -54,6 +54,9 @@ def lib():
     L.tsdg_create.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, _vpp]
     L.tsdg_create_band.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vpp]
     L.tsdg_destroy.argtypes = [C.c_void_p]
+    L.tsdg_band_push_finish.argtypes = [C.c_void_p]
+    L.tsdg_band_row.argtypes = [C.c_void_p, C.c_int, _vpp, _vpp, C.POINTER(C.c_uint64)]
+    L.tsdg_raycast_band_keys.argtypes = [C.c_void_p, _sp, _dp, _vpp, _vpp]
     L.tsdg_set_max_truncation.argtypes = [C.c_void_p, C.c_double]
     L.tsdg_get_geometry.argtypes = [C.c_void_p, _ip, _ip, _ip] + [_dp] * 6
     L.tsdg_free_footprint.argtypes = [C.c_void_p] + [C.c_double] * 4
@@ -254,6 +257,22 @@ class Grid:
         check(lib().tsdg_raycast(self.h, scan.byref(), _d(rays), _d(coords), _d(normals), C.byref(cnt)))
         k = int(cnt.value)
         return coords[:k].reshape(-1, 2), normals[:k].reshape(-1, 2)
+
+    def band_push_finish(self):
+        check(lib().tsdg_band_push_finish(self.h))
+
+    def band_row(self, which: int):
+        """(tsd_ptr, weight_ptr, count_doubles) of a boundary / halo partition row; (0, 0, 0) if absent."""
+        t, w, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        check(lib().tsdg_band_row(self.h, which, C.byref(t), C.byref(w), C.byref(n)))
+        return int(t.value or 0), int(w.value or 0), int(n.value)
+
+    def raycast_band_keys(self, scan: Scan, rays_world):
+        """Device pointers (keys u64[n], payload f64[4n]) of this band's first events."""
+        rays = _f64(rays_world)
+        k, p = C.c_void_p(), C.c_void_p()
+        check(lib().tsdg_raycast_band_keys(self.h, scan.byref(), _d(rays), C.byref(k), C.byref(p)))
+        return int(k.value), int(p.value)
 
     def raycast_steps(self):
         a, b = C.c_uint64(), C.c_uint64()

@@ -56,7 +56,8 @@ struct GridView
   const uint8_t* flags;  // all partitions of the grid: 1 = initialised
   int cells_x, cells_y;
   int parts_x, parts_y;
-  int row_begin, row_end;  // owned partition rows
+  int row_begin, row_end;      // owned partition rows
+  int alloc_begin, alloc_end;  // readable partition rows: owned + one halo row on each side of a band
   double cell_size, inv_cell_size;
 };
 
@@ -91,10 +92,10 @@ __device__ __forceinline__ int sample_bilinear(const GridView& g, double cx, dou
   const int p = py * g.parts_x + px;
   const int x = xIdx & 31, y = yIdx & 31;
   if(!g.flags[p]) return TSD_INTERPOLATE_EMPTYPARTITION;
-  if(py < g.row_begin || py >= g.row_end) return TSD_NOT_OWNED;
+  if(py < g.alloc_begin || py >= g.alloc_end) return TSD_NOT_OWNED;
   const double wx = fabs((cx - dx) * g.inv_cell_size);
   const double wy = fabs((cy - dy) * g.inv_cell_size);
-  const double* t = g.tsd + (size_t)(p - g.row_begin * g.parts_x) * TSD_TILE_STRIDE;
+  const double* t = g.tsd + (size_t)(p - g.alloc_begin * g.parts_x) * TSD_TILE_STRIDE;
   const int i00 = y * 32 + x;
   const int i10 = (y == 31) ? (TSD_BORDER_OFF + 32 + x) : (i00 + 32);                 // [y+1][x]
   const int i01 = (x == 31) ? (TSD_BORDER_OFF + y) : (i00 + 1);                       // [y][x+1]
@@ -114,6 +115,7 @@ struct SampleLoads
 {
   double g00, g10, g01, g11, wx, wy;
   int pre;  // 0, or the status already known from the geometry (INVALIDINDEX / NOT_OWNED)
+  int py;   // partition row of the sample (decides which band owns the step)
   unsigned char flag;
 };
 
@@ -133,11 +135,12 @@ __device__ __forceinline__ SampleLoads sample_issue(const GridView& g, double cx
   const int py = yc >> 5, px = xc >> 5;
   const int p = py * g.parts_x + px;
   const int x = xc & 31, y = yc & 31;
+  L.py = inb ? py : -1;
   L.flag = __ldg(g.flags + p);
-  const bool owned = !(py < g.row_begin || py >= g.row_end);
+  const bool owned = !(py < g.alloc_begin || py >= g.alloc_end);  // readable here
   L.wx = fabs((cx - dx) * g.inv_cell_size);
   L.wy = fabs((cy - dy) * g.inv_cell_size);
-  const double* t = g.tsd + (size_t)(owned ? (p - g.row_begin * g.parts_x) : 0) * TSD_TILE_STRIDE;
+  const double* t = g.tsd + (size_t)(owned ? (p - g.alloc_begin * g.parts_x) : 0) * TSD_TILE_STRIDE;
   const int i00 = y * 32 + x;
   const int i10 = (y == 31) ? (TSD_BORDER_OFF + 32 + x) : (i00 + 32);
   const int i01 = (x == 31) ? (TSD_BORDER_OFF + y) : (i00 + 1);
@@ -213,6 +216,9 @@ struct tsd_grid
   int layout_grid;
   int cells_x, cells_y, parts_x, parts_y, n_parts;
   int row_begin, row_end, n_owned;  // owned partition rows / partitions
+  int alloc_begin, alloc_end, n_alloc;  // allocated rows: owned + halo rows (bands only)
+  bool band;                        // sharded grid: push runs in two phases around the halo exchange
+  bool band_push_open;
   double cell_size, inv_cell_size, max_truncation;
   double min_x, max_x, min_y, max_y;
   bool pushed_once;

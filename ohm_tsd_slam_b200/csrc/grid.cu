@@ -75,6 +75,8 @@ GridView grid_view(const tsd_grid* g)
   v.parts_y = g->parts_y;
   v.row_begin = g->row_begin;
   v.row_end = g->row_end;
+  v.alloc_begin = g->alloc_begin;
+  v.alloc_end = g->alloc_end;
   v.cell_size = g->cell_size;
   v.inv_cell_size = g->inv_cell_size;
   return v;
@@ -96,6 +98,8 @@ struct PushParams
   double inv_max_trunc;  // 1.0 / maxTruncation (TsdGridPartition.cpp:94)
   int cells_x, cells_y, parts_x, parts_y, n_parts;
   int row_begin, row_end;
+  int alloc_begin, alloc_end;
+  int band;
   double* tsd;
   double* weight;
   uint8_t* flags;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
         const uint32_t e = (nxt < nActive) ? pp.active[nxt] : (pp.emptied[nxt - nActive] | 0x80000000u);
         if(e & 0x80000000u)
         {
-          const size_t nb = (size_t)((e & 0x7fffffffu) - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE + (size_t)t * 4;
+          const size_t nb = (size_t)((e & 0x7fffffffu) - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE + (size_t)t * 4;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(pp.tsd + nb));
           asm volatile("prefetch.global.L2 [%0];" ::"l"(pp.weight + nb));
         }
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
       const bool wasInit = (e & 0x80000000u) != 0;
       const double wTile = pp.active_w[item];
       const int px = p % pp.parts_x, py = p / pp.parts_x;
-      const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+      const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
       double* T = pp.tsd + base;
       double* W = pp.weight + base;
       const int gx = px * TSD_TILE + xp;
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
     {
       // K3: increaseEmptiness on an initialised partition, all 33x33 cells
       const uint32_t p = pp.emptied[item - nActive];
-      const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+      const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
       double* T = pp.tsd + base;
       double* W = pp.weight + base;
 #pragma unroll
@@ -501,7 +505,7 @@ __device__ __forceinline__ void refresh_borders_of(const PushParams& pp, int px,
 {
   // cur = (px,py) must be initialised and owned
   const int p = py * pp.parts_x + px;
-  const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+  const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
   double* T = pp.tsd + base;
   double* W = pp.weight + base;
   if(px < pp.parts_x - 1 && pp.flags[p + 1])
@@ -510,13 +514,13 @@ __device__ __forceinline__ void refresh_borders_of(const PushParams& pp, int px,
     T[TSD_BORDER_OFF + lane] = pp.tsd[nb + lane * TSD_TILE];
     W[TSD_BORDER_OFF + lane] = pp.weight[nb + lane * TSD_TILE];
   }
-  if(py < pp.parts_y - 1 && py + 1 < pp.row_end && pp.flags[p + pp.parts_x])
+  if(py < pp.parts_y - 1 && py + 1 < pp.alloc_end && pp.flags[p + pp.parts_x])
   {
     const size_t nb = base + (size_t)pp.parts_x * TSD_TILE_STRIDE;
     T[TSD_BORDER_OFF + 32 + lane] = pp.tsd[nb + lane];
     W[TSD_BORDER_OFF + 32 + lane] = pp.weight[nb + lane];
   }
-  if(lane == 0 && px < pp.parts_x - 1 && py < pp.parts_y - 1 && py + 1 < pp.row_end && pp.flags[p + pp.parts_x + 1])
+  if(lane == 0 && px < pp.parts_x - 1 && py < pp.parts_y - 1 && py + 1 < pp.alloc_end && pp.flags[p + pp.parts_x + 1])
   {
     const size_t nb = base + (size_t)(pp.parts_x + 1) * TSD_TILE_STRIDE;
     T[TSD_BORDER_OFF + 64] = pp.tsd[nb];
@@ -534,6 +538,12 @@ __global__ void __launch_bounds__(256) k_borders(PushParams pp, int all)
     for(int p = pp.row_begin * pp.parts_x + warp; p < pp.row_end * pp.parts_x; p += nwarps)
       if(pp.flags[p]) refresh_borders_of(pp, p % pp.parts_x, p / pp.parts_x, lane);
     return;
+  }
+  if(pp.band && pp.row_end < pp.parts_y)
+  {
+    // the partitions above the band's top row belong to another GPU and may have changed: refresh the row
+    for(int px = warp; px < pp.parts_x; px += nwarps)
+      if(pp.flags[(pp.row_end - 1) * pp.parts_x + px]) refresh_borders_of(pp, px, pp.row_end - 1, lane);
   }
   const uint32_t nA = pp.counters[0], nE = pp.counters[1], nP = pp.counters[2];
   for(uint32_t item = warp; item < nA + nE + nP; item += nwarps)
@@ -565,7 +575,7 @@ __global__ void k_footprint_init(PushParams pp, int pxMin, int pxMax, int pyMin,
   {
     const double initW = pp.initw[p];
     const double initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
-    const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+    const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
     for(int i = threadIdx.x; i < TSD_BORDER_OFF + 65; i += blockDim.x)
     {
       pp.tsd[base + i] = initT;
@@ -587,7 +597,7 @@ __global__ void k_footprint_set(PushParams pp, unsigned minX, unsigned maxX, uns
   const int py = rows >> 5, px = cols >> 5;
   if(py < pp.row_begin || py >= pp.row_end) return;
   const int p = py * pp.parts_x + px;
-  const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+  const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
   pp.tsd[base + (rows & 31) * TSD_TILE + (cols & 31)] = 1.0;
 }
 
@@ -602,7 +612,7 @@ __global__ void k_fill(PushParams pp, double tsd, double weight, int only_uninit
     const int py = p / pp.parts_x;
     if(py >= pp.row_begin && py < pp.row_end)
     {
-      const size_t base = (size_t)(p - pp.row_begin * pp.parts_x) * TSD_TILE_STRIDE;
+      const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
       for(int i = threadIdx.x; i < TSD_BORDER_OFF + 65; i += blockDim.x)
       {
         pp.tsd[base + i] = tsd;
@@ -650,6 +660,9 @@ static PushParams make_params(const tsd_grid* g)
   pp.n_parts = g->n_parts;
   pp.row_begin = g->row_begin;
   pp.row_end = g->row_end;
+  pp.alloc_begin = g->alloc_begin;
+  pp.alloc_end = g->alloc_end;
+  pp.band = g->band ? 1 : 0;
   pp.tsd = g->d_tsd;
   pp.weight = g->d_weight;
   pp.flags = g->d_flags;
@@ -869,6 +882,10 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   g->row_begin = part_row_begin;
   g->row_end = part_row_end;
   g->n_owned = (part_row_end - part_row_begin) * g->parts_x;
+  g->band = (part_row_begin > 0 || part_row_end < g->parts_y);
+  g->alloc_begin = g->band && part_row_begin > 0 ? part_row_begin - 1 : part_row_begin;
+  g->alloc_end = g->band && part_row_end < g->parts_y ? part_row_end + 1 : part_row_end;
+  g->n_alloc = (g->alloc_end - g->alloc_begin) * g->parts_x;
   g->max_truncation = 2.0 * cell_size;  // TsdGrid.cpp:136
   g->min_x = 0.0;
   g->max_x = ((double)g->cells_x + 0.5) * cell_size;  // TsdGrid.cpp:141-144
@@ -879,7 +896,7 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaGetDeviceProperties(&prop, device));
   g->sm_count = prop.multiProcessorCount;
   TSD_CUDA(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-  const size_t cellBytes = sizeof(double) * (size_t)g->n_owned * TSD_TILE_STRIDE;
+  const size_t cellBytes = sizeof(double) * (size_t)g->n_alloc * TSD_TILE_STRIDE;
   e = cudaMalloc(&g->d_tsd, cellBytes);
   if(e == cudaSuccess) e = cudaMalloc(&g->d_weight, cellBytes);
   if(e != cudaSuccess)
@@ -986,6 +1003,8 @@ int tsdg_free_footprint(tsd_grid_t* g, double cx, double cy, double width, doubl
   return TSD_OK;
 }
 
+static int push_finish(tsd_grid* g, const PushParams& pp);
+
 int tsdg_stage_scan(tsd_grid_t* g, const tsd_scan_t* scan)
 {
   if(!g) return TSD_E_INVALID;
@@ -1025,6 +1044,17 @@ int tsdg_push_staged(tsd_grid_t* g)
   k_update<<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[2], g->stream));
+  if(g->band)
+  {
+    // sharded grid: the borders need the neighbour band's fresh first row -> tsdg_band_push_finish()
+    g->band_push_open = true;
+    return TSD_OK;
+  }
+  return push_finish(g, pp);
+}
+
+static int push_finish(tsd_grid* g, const PushParams& pp)
+{
   int bctas = g->sm_count * 4;
   k_borders<<<bctas, 256, 0, g->stream>>>(pp, 0);
   TSD_LAUNCHED();
@@ -1045,6 +1075,38 @@ int tsdg_push_async(tsd_grid_t* g, const tsd_scan_t* scan)
 }
 
 void* tsdg_stream(tsd_grid_t* g) { return g ? (void*)g->stream : nullptr; }
+
+int tsdg_band_push_finish(tsd_grid_t* g)
+{
+  if(!g || !g->band || !g->band_push_open) { set_error("no sharded push in flight"); return TSD_E_INVALID; }
+  TSD_CUDA(cudaSetDevice(g->device));
+  PushParams pp = make_params(g);
+  pp.scan = g->staged;
+  pp.dirs = g->d_dirs;
+  g->band_push_open = false;
+  return push_finish(g, pp);
+}
+
+// which: 0 = my lowest partition row (the band below wants it), 1 = my highest row (the band above wants it),
+//        2 = halo slot below my band (filled from the lower neighbour's highest row),
+//        3 = halo slot above my band (filled from the upper neighbour's lowest row).
+int tsdg_band_row(tsd_grid_t* g, int which, double** tsd, double** weight, uint64_t* count)
+{
+  if(!g || !tsd || !weight || !count || which < 0 || which > 3) return TSD_E_INVALID;
+  int row;
+  if(which == 0) row = g->row_begin;
+  else if(which == 1) row = g->row_end - 1;
+  else if(which == 2) row = g->row_begin - 1;
+  else row = g->row_end;
+  *tsd = *weight = nullptr;
+  *count = 0;
+  if(row < g->alloc_begin || row >= g->alloc_end) return TSD_OK;  // no such neighbour
+  const size_t off = (size_t)(row - g->alloc_begin) * g->parts_x * TSD_TILE_STRIDE;
+  *tsd = g->d_tsd + off;
+  *weight = g->d_weight + off;
+  *count = (uint64_t)g->parts_x * TSD_TILE_STRIDE;
+  return TSD_OK;
+}
 
 int tsdg_set_timing(tsd_grid_t* g, int enable)
 {
@@ -1204,7 +1266,7 @@ int tsdg_download_partition(tsd_grid_t* g, int32_t p, double* tsd, double* weigh
   TSD_CUDA(cudaMemcpy(&flag, g->d_flags + p, 1, cudaMemcpyDeviceToHost));
   if(!flag) return TSD_E_INVALID;
   double tile[TSD_TILE_STRIDE];
-  const size_t base = (size_t)(p - g->row_begin * g->parts_x) * TSD_TILE_STRIDE;
+  const size_t base = (size_t)(p - g->alloc_begin * g->parts_x) * TSD_TILE_STRIDE;
   TSD_CUDA(cudaMemcpy(tile, g->d_tsd + base, sizeof(tile), cudaMemcpyDeviceToHost));
   tile_to_33(tile, tsd);
   TSD_CUDA(cudaMemcpy(tile, g->d_weight + base, sizeof(tile), cudaMemcpyDeviceToHost));
@@ -1220,7 +1282,7 @@ int tsdg_upload_partition(tsd_grid_t* g, int32_t p, const double* tsd, const dou
   TSD_CUDA(cudaSetDevice(g->device));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   double tile[TSD_TILE_STRIDE];
-  const size_t base = (size_t)(p - g->row_begin * g->parts_x) * TSD_TILE_STRIDE;
+  const size_t base = (size_t)(p - g->alloc_begin * g->parts_x) * TSD_TILE_STRIDE;
   tile_from_33(tsd, tile);
   TSD_CUDA(cudaMemcpy(g->d_tsd + base, tile, sizeof(tile), cudaMemcpyHostToDevice));
   tile_from_33(weight, tile);

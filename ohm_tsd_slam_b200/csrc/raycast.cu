@@ -21,7 +21,8 @@ struct RayParams
   ScanDev scan;
   const double* rays;  // 2 x n, world frame, length = cellSize
   double* out;         // 4 x n : cx cy nx ny (sensor frame)
-  unsigned long long* keys;   // per beam: 2*step (+1: abort) of the first event, ~0 = none
+  unsigned long long* keys;   // per beam: 4*step + code of the first event (code 0: hit, 1: hit whose normal
+                              // failed, 2: abort), ~0 = none.  A sharded grid min-reduces these over the bands.
   unsigned long long* steps;  // [0] fine [1] coarse
   double xmin, ymin, xmax, ymax;  // RayCastPolar2D.cpp:128-146
   double idxMin, idxMax;          // :148-149
@@ -29,7 +30,7 @@ struct RayParams
 };
 
 #define RC_WARPS 4
-#define NO_EVENT 0xffffffffffffffffULL
+#define NO_EVENT 0x7fffffffffffffffULL  // INT64_MAX: the largest key under a signed or unsigned min-reduction
 
 __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
 {
@@ -167,8 +168,10 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
       if(valid && rv == TSD_INTERPOLATE_SUCCESS) v = t;
       double prev = __shfl_up_sync(0xffffffffu, v, 1);
       if(lane == 0) prev = carry;
-      const bool hit = valid && (prev > 0) && (v < 0);
-      const bool abortEv = valid && (prev < 0) && (v > 0);
+      // a step belongs to the band that owns its sample's partition (everything, for an unsharded grid)
+      const bool mine = valid && (sl.py >= g.row_begin) && (sl.py < g.row_end);
+      const bool hit = mine && (prev > 0) && (v < 0);
+      const bool abortEv = mine && (prev < 0) && (v > 0);
       const unsigned mHit = __ballot_sync(0xffffffffu, hit);
       const unsigned mEv = mHit | __ballot_sync(0xffffffffu, abortEv);
       const unsigned mInval = __ballot_sync(0xffffffffu, !valid);
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
         const int f = __ffs(mEv) - 1;
         nFine += (unsigned)(f + 1);
         const bool isHit = (mHit >> f) & 1u;
-        key = 2ULL * (base + (unsigned)f) + (isHit ? 0ULL : 1ULL);
+        key = 4ULL * (base + (unsigned)f) + (isHit ? 1ULL : 2ULL);
         if(isHit)
         {
           // :259, :277-280 on the lane that owns the step
@@ -195,6 +198,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
           nx = __shfl_sync(0xffffffffu, nx, f);
           ny = __shfl_sync(0xffffffffu, ny, f);
           found = ok != 0;
+          if(found) key &= ~3ULL;
         }
         break;
       }
@@ -223,18 +227,23 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
       rp.out[4 * beam + 1] = m1;
       rp.out[4 * beam + 2] = n0;
       rp.out[4 * beam + 3] = n1;
-      rp.keys[beam] = key;
     }
     else
     {
-      rp.keys[beam] = NO_EVENT;
+      rp.out[4 * beam + 0] = 0.0;
+      rp.out[4 * beam + 1] = 0.0;
+      rp.out[4 * beam + 2] = 0.0;
+      rp.out[4 * beam + 3] = 0.0;
     }
+    rp.keys[beam] = key;
     atomicAdd(&rp.steps[0], nFine);
     atomicAdd(&rp.steps[1], nCoarse);
   }
 }
 
-static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world)
+#define RC_IS_HIT(k) ((k) != NO_EVENT && ((k) & 3ULL) == 0ULL)
+
+static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, bool download = true)
 {
   if(!g || !scan || !rays_world) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
@@ -264,7 +273,7 @@ static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* r
   rp.idxMax = scan->max_range / g->cell_size;
   k_raycast<<<(n + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, g->stream>>>(rp);
   TSD_LAUNCHED();
-  TSD_CUDA(cudaMemcpyAsync(g->h_rc, g->d_rc, g->rc_bytes, cudaMemcpyDeviceToHost, g->stream));
+  if(download) TSD_CUDA(cudaMemcpyAsync(g->h_rc, g->d_rc, g->rc_bytes, cudaMemcpyDeviceToHost, g->stream));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   return TSD_OK;
 }
@@ -280,7 +289,7 @@ int tsdg_raycast_mask(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_
   uint32_t cnt = 0;
   for(int b = 0; b < scan->n; b++)
   {
-    if(g->h_rc_keys[b] != NO_EVENT)
+    if(RC_IS_HIT(g->h_rc_keys[b]))
     {
       coords[2 * b] = g->h_rc_out[4 * b];
       coords[2 * b + 1] = g->h_rc_out[4 * b + 1];
@@ -306,7 +315,7 @@ int tsdg_raycast(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world
   uint32_t cnt = 0;
   for(int b = 0; b < scan->n; b++)
   {
-    if(g->h_rc_keys[b] != NO_EVENT)
+    if(RC_IS_HIT(g->h_rc_keys[b]))
     {
       coords[cnt] = g->h_rc_out[4 * b];
       normals[cnt++] = g->h_rc_out[4 * b + 2];
@@ -330,9 +339,12 @@ int tsdg_last_raycast_steps(tsd_grid_t* g, uint64_t* fine_steps, uint64_t* coars
 int tsdg_raycast_band_keys(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, uint64_t** dev_keys,
                            double** dev_payload)
 {
-  (void)g; (void)scan; (void)rays_world; (void)dev_keys; (void)dev_payload;
-  tsd::set_error("tsdg_raycast_band_keys: not implemented yet");
-  return TSD_E_INVALID;
+  if(!dev_keys || !dev_payload) return TSD_E_INVALID;
+  int rc = raycast_launch(g, scan, rays_world, false);
+  if(rc) return rc;
+  *dev_keys = reinterpret_cast<uint64_t*>(g->d_rc_keys);
+  *dev_payload = g->d_rc_out;
+  return TSD_OK;
 }
 
 }  // extern "C"

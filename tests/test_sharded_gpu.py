@@ -1,0 +1,44 @@
+"""A grid sharded in bands must equal the unsharded grid bit for bit (SURVEY.md 7 hard part 7): several bands
+on one device, boundary rows exchanged by device copies, ray crossings merged by min over the bands."""
+import numpy as np
+import pytest
+
+from ohm_tsd_slam_b200 import capi, synth
+from ohm_tsd_slam_b200.scan import HostSensor
+from ohm_tsd_slam_b200.sharded import LocalBands
+from tests.harness import compare_grids, same
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,bands", [("tiny", 2), ("tiny", 3), ("C1", 2), ("C1", 5)])
+def test_banded_grid_equals_single_grid(name, bands):
+    cfg = synth.config(name)
+    whole = capi.Grid(cfg.cell_size, 5, cfg.layout_grid)
+    parts = LocalBands(cfg.cell_size, cfg.layout_grid, bands)
+    whole.set_max_truncation(cfg.max_truncation)
+    parts.set_max_truncation(cfg.max_truncation)
+    hs = HostSensor(cfg.sensor, capi.invert3x3)
+    scans = list(cfg.scans(7))
+    (x, y, th), r0 = scans[0]
+    # a trajectory that crosses a band boundary: start next to it
+    hs.set_scan(r0)
+    hs.transform(synth.pose_matrix(x, y, th))
+    assert whole.free_footprint(x, y, 0.6, 0.6) and parts.free_footprint(x, y, 0.6, 0.6)
+    for k, (pose, r) in enumerate(scans):
+        hs.set_scan(r)
+        hs.T = synth.pose_matrix(*pose)
+        sc = hs.scan()
+        if k > 0:
+            rays = hs.normalized_rays(cfg.cell_size).copy()
+            c1, n1, m1, k1 = whole.raycast_mask(sc, rays)
+            c2, n2, m2, k2 = parts.raycast_mask(sc, rays)
+            assert same(m1, m2), (k, int((m1 != m2).sum()))
+            assert same(c1[m1 > 0], c2[m2 > 0]) and same(n1[m1 > 0], n2[m2 > 0])
+            assert k1 == k2 and k1 > 0
+        whole.push(sc)
+        parts.push(sc)
+        a, b = whole.last_push_stats(), parts.last_push_stats()
+        assert a["cell_updates"] == b["cell_updates"] and a["active_tiles"] == b["active_tiles"]
+        ok, lines = compare_grids(whole, parts)
+        assert ok, (k, lines)
