@@ -89,11 +89,30 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    wl = DoubleLaserWorkload(args.workload, invert=capi.invert3x3, seed_offset=rank)
+    wl = DoubleLaserWorkload(args.workload, invert=capi.invert3x3)
     cfg = wl.cfg
-    grid = capi.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid, device=local)
+    if world == 1:
+        grid = capi.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid, device=local)
+        band = None
+    else:
+        # the same workload, the grid sharded in `world` bands of partition rows (strong scaling): every rank
+        # integrates the replicated scan into its own rows; boundary rows travel over NCCL
+        from ohm_tsd_slam_b200.sharded import DistBand
+        band = DistBand(cfg.cell_size, cfg.layout_grid, local)
+        grid = band.grid
     grid.set_max_truncation(cfg.max_truncation)
-    wl.build_map(grid)
+
+    def push_host(sc):
+        band.push(sc) if band else grid.push(sc)
+
+    def push_resident():
+        band.push_staged() if band else grid.push_staged()
+
+    for sc in wl.map_scans:
+        push_host(sc)
+    grid.fill(1.0, 1.0, only_uninitialized=True)
+    if band:
+        band.exchange()
     grid.set_timing(True)
     launches0 = capi.kernel_launches()
     stream = torch.cuda.ExternalStream(grid.stream_ptr, device=torch.device("cuda", local))
@@ -109,7 +128,7 @@ def run_cuda(args):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            grid.push_staged()
+            push_resident()
             e1.record(stream)
             acc.append((e0, e1))
 
@@ -138,20 +157,20 @@ def run_cuda(args):
     # exact update count per step: measure each laser's push once
     upd_per_step = 0
     for sc in wl.step_scans[0]:
-        grid.push(sc)
+        push_host(sc)
         upd_per_step += grid.last_push_stats()["cell_updates"]
     upd_avg_per_push = upd_per_step / 2.0
 
     # ---------------- end-to-end leg: host buffers through tsdg_push (blocking; H2D + stats D2H inside)
     for i in range(args.warmup):
         for sc in wl.step_scans[i % n_steps]:
-            grid.push(sc)
+            push_host(sc)
     barrier()
     e2e_updates = 0
     t0 = time.perf_counter()
     for i in range(args.steps):
         for sc in wl.step_scans[i % n_steps]:
-            grid.push(sc)
+            push_host(sc)
             e2e_updates += grid.last_push_stats()["cell_updates"]
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -165,11 +184,15 @@ def run_cuda(args):
     scene = None
     rc_ms = icp_ms = None
     reps = max(3, min(args.steps, 20))
+    def raycast():
+        return band.raycast_mask(sc0, rays0) if band else grid.raycast_mask(sc0, rays0)
+
     for _ in range(2):
-        c, nrm, m, cnt = grid.raycast_mask(sc0, rays0)
+        c, nrm, m, cnt = raycast()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
-        c, nrm, m, cnt = grid.raycast_mask(sc0, rays0)
+        c, nrm, m, cnt = raycast()
     rc_ms = (time.perf_counter() - t0) / reps * 1e3
     valid = (~np.isinf(sc0.ranges)) & (sc0.mask != 0)
     scene = np.stack([hs.rays_local[0, valid] * sc0.ranges[valid], hs.rays_local[1, valid] * sc0.ranges[valid]], axis=1)
@@ -202,9 +225,11 @@ def run_cuda(args):
         n = sc0.n
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "cuda",
-            "config": dict(wl.describe(), parallelism=f"replicas x{world}" if world > 1 else "single GPU",
+            "config": dict(wl.describe(), parallelism=(f"grid sharded in {world} bands of partition rows, scan replicated, boundary rows over NCCL"
+                                        if world > 1 else "single GPU"),
                            cell_updates_per_step=upd_per_step),
             "hbm_gbs_algorithmic": value * ALG_BYTES_PER_UPDATE,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * (n * 8 + n + 8 * 25), "d2h_bytes_per_step": 2 * (16 * 4 + 4 * 8),

@@ -130,6 +130,9 @@ int tsdg_stage_scan(tsd_grid_t* grid, const tsd_scan_t* scan);
 int tsdg_push_staged(tsd_grid_t* grid);
 /* The handle's cudaStream_t, for callers that time or order work with CUDA events. */
 void* tsdg_stream(tsd_grid_t* grid);
+/* Orders the handle's stream against a caller's stream without blocking the host: direction 0 = `other`
+ * waits for the handle's queued work, 1 = the handle waits for `other` (used around NCCL exchanges). */
+int tsdg_stream_order(tsd_grid_t* grid, void* other_stream, int direction);
 /* Measurement aid: with timing enabled every push records CUDA events around its kernels on the handle's
  * stream; ms = {tables + classify, update (K2+K3), borders (K4), whole push} of the last completed push. */
 int tsdg_set_timing(tsd_grid_t* grid, int enable);
@@ -200,6 +203,11 @@ typedef struct tsd_icp tsd_icp_t;
 int icp_create(uint32_t max_iterations, double dist_max, double dist_min, uint32_t dist_iterations,
                const double bounds[4], int device, tsd_icp_t** out);
 int icp_destroy(tsd_icp_t* icp);
+/* Icp::setMaxRMS / setConvergenceCounter (Icp.cpp:341-369).  icp_create sets 0.0 and max_iterations, the
+ * node's values (ThreadLocalize.cpp:223-225). */
+int icp_set_termination(tsd_icp_t* icp, double max_rms, uint32_t convergence_counter);
+/* Icp::setMaxIterations (Icp.cpp:351-354); at most the value given to icp_create. */
+int icp_set_max_iterations(tsd_icp_t* icp, uint32_t max_iterations);
 /* Icp::reset + OutOfBoundsFilter2D::setPose + setModel + setScene + iterate + getFinalTransformation.
  * model/normals: n_model x 2, scene: n_scene x 2 (already compacted to valid points); t_init: 4x4 or NULL.
  * t_out 3x3; *mse is what the reference calls rms (mean squared pair distance, ClosedFormEstimator2D.cpp:59-62). */

@@ -24,10 +24,10 @@ EXPORTS = [
     "tsd_last_error", "tsd_device_count", "tsd_kernel_launches", "tsd_invert3x3",
     "tsdg_create", "tsdg_create_band", "tsdg_band_push_finish", "tsdg_band_row", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
     "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged",
-    "tsdg_stream", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
+    "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
-    "icp_create", "icp_destroy", "icp_run", "icp_set_trace", "icp_get_trace",
+    "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
 
@@ -67,6 +67,7 @@ def lib():
     L.tsdg_sync.argtypes = [C.c_void_p]
     L.tsdg_stream.restype = C.c_void_p
     L.tsdg_stream.argtypes = [C.c_void_p]
+    L.tsdg_stream_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.tsdg_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.tsdg_last_push_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tsdg_last_push_stats.argtypes = [C.c_void_p, C.POINTER(PushStats)]
@@ -83,6 +84,8 @@ def lib():
     L.icp_create.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_uint32, _dp, C.c_int, _vpp]
     L.icp_destroy.argtypes = [C.c_void_p]
     L.icp_run.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _up, _up, _ip]
+    L.icp_set_termination.argtypes = [C.c_void_p, C.c_double, C.c_uint32]
+    L.icp_set_max_iterations.argtypes = [C.c_void_p, C.c_uint32]
     L.icp_set_trace.argtypes = [C.c_void_p, C.c_int]
     L.icp_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _up, _up, _ip, _dp, _dp, _ip]
     L.match_create.argtypes = [C.c_int, _vpp]
@@ -188,6 +191,9 @@ class Grid:
     @property
     def stream_ptr(self) -> int:
         return int(lib().tsdg_stream(self.h) or 0)
+
+    def stream_order(self, other_stream_ptr: int, direction: int):
+        check(lib().tsdg_stream_order(self.h, C.c_void_p(other_stream_ptr), direction))
 
     def last_push_stats(self):
         st = PushStats()

@@ -274,6 +274,7 @@ struct tsd_grid
   bool has_staged;
   bool timing;          // record CUDA events around the push kernels (bench.py's live roofline)
   cudaEvent_t ev[4];
+  cudaEvent_t ev_order;
 };
 
 namespace tsd

@@ -944,6 +944,7 @@ int tsdg_destroy(tsd_grid_t* g)
   cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters);
   cudaFreeHost(g->h_stats64);
   for(int i = 0; i < 4; i++) if(g->ev[i]) cudaEventDestroy(g->ev[i]);
+  if(g->ev_order) cudaEventDestroy(g->ev_order);
   if(g->stream) cudaStreamDestroy(g->stream);
   cudaGetLastError();
   delete g;
@@ -1075,6 +1076,28 @@ int tsdg_push_async(tsd_grid_t* g, const tsd_scan_t* scan)
 }
 
 void* tsdg_stream(tsd_grid_t* g) { return g ? (void*)g->stream : nullptr; }
+
+// Stream-ordered hand-over between the handle's stream and a caller's stream (the one its collectives run on),
+// without blocking the host: direction 0 makes `other` wait for everything queued on the handle's stream,
+// direction 1 makes the handle's stream wait for everything queued on `other`.
+int tsdg_stream_order(tsd_grid_t* g, void* other, int direction)
+{
+  if(!g) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  if(!g->ev_order) TSD_CUDA(cudaEventCreateWithFlags(&g->ev_order, cudaEventDisableTiming));
+  cudaStream_t o = (cudaStream_t)other;
+  if(direction == 0)
+  {
+    TSD_CUDA(cudaEventRecord(g->ev_order, g->stream));
+    TSD_CUDA(cudaStreamWaitEvent(o, g->ev_order, 0));
+  }
+  else
+  {
+    TSD_CUDA(cudaEventRecord(g->ev_order, o));
+    TSD_CUDA(cudaStreamWaitEvent(g->stream, g->ev_order, 0));
+  }
+  return TSD_OK;
+}
 
 int tsdg_band_push_finish(tsd_grid_t* g)
 {

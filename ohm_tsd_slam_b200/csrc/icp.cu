@@ -77,6 +77,7 @@ struct tsd_icp
   double* h_result;  // pinned
   int last_nM, last_nS;
   int trace;
+  int trace_cap_it;
 };
 
 // cell coordinate of a point; clamped so that the hash input stays small and rings never overflow
@@ -584,6 +585,7 @@ int icp_create(uint32_t max_iterations, double dist_max, double dist_min, uint32
   TSD_CUDA(cudaMalloc(&h->d_scene, sizeof(double) * 2 * h->cap));
   TSD_CUDA(cudaMalloc(&h->d_result, sizeof(double) * 16));
   const size_t mi = max_iterations > 0 ? max_iterations : 1;
+  h->trace_cap_it = (int)mi;
   TSD_CUDA(cudaMalloc(&h->d_tr_model, sizeof(unsigned) * mi * h->cap));
   TSD_CUDA(cudaMalloc(&h->d_tr_scene, sizeof(unsigned) * mi * h->cap));
   TSD_CUDA(cudaMalloc(&h->d_tr_count, sizeof(int) * mi));
@@ -662,6 +664,21 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   *state = (int32_t)h->h_result[12];
   h->last_nM = n_model;
   h->last_nS = n_scene;
+  return TSD_OK;
+}
+
+int icp_set_termination(tsd_icp_t* h, double max_rms, uint32_t convergence_counter)
+{
+  if(!h) return TSD_E_INVALID;
+  h->p.max_rms = max_rms;
+  h->p.conv_cnt = convergence_counter;
+  return TSD_OK;
+}
+
+int icp_set_max_iterations(tsd_icp_t* h, uint32_t max_iterations)
+{
+  if(!h || max_iterations > (uint32_t)h->trace_cap_it) { set_error("icp_set_max_iterations: beyond the capacity given to icp_create"); return TSD_E_INVALID; }
+  h->p.max_iterations = (int)max_iterations;
   return TSD_OK;
 }
 

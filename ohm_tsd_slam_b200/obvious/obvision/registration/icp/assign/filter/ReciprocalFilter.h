@@ -1,0 +1,3 @@
+// Forwarding header: same include path as the reference (src/obvision/registration/icp/assign/filter/ReciprocalFilter.h); the classes live in obvious_b200.h.
+#pragma once
+#include "../../../../../obvious_b200.h"

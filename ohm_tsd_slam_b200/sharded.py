@@ -196,9 +196,12 @@ class DistBand:
         return self._views
 
     def exchange(self):
+        """Boundary rows to the neighbouring bands, stream-ordered (no host synchronisation): the collective
+        stream waits for the library's stream, the library's stream waits for the collective."""
         dist = self.dist
         v = self._row_views()
-        self.grid.sync()
+        cur = torch.cuda.current_stream(self.device)
+        self.grid.stream_order(cur.cuda_stream, 0)
         ops = []
         if self.rank > 0:  # lowest row down, lower halo from below
             for k in (0, 1):
@@ -210,24 +213,30 @@ class DistBand:
                 ops.append(dist.P2POp(dist.irecv, v[3][k], self.rank + 1))
         if ops:
             for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        torch.cuda.synchronize(self.device)
+                r.wait()  # NCCL: orders the current stream after the transfer, does not block the host
+        self.grid.stream_order(cur.cuda_stream, 1)
+        self.halo_dirty = False
+
+    def _push_tail(self):
+        # phase 2 needs the upper neighbour's fresh first row; the refreshed borders reach the neighbours'
+        # halos lazily, before the next ray cast (nothing else reads a halo's border cells)
+        self.exchange()
+        self.grid.band_push_finish()
+        self.halo_dirty = True
 
     def push(self, scan: Scan):
         self.grid.push_async(scan)
-        self.exchange()
-        self.grid.band_push_finish()
-        self.exchange()
+        self._push_tail()
 
     def push_staged(self):
         self.grid.push_staged()
-        self.exchange()
-        self.grid.band_push_finish()
-        self.exchange()
+        self._push_tail()
 
     def raycast_mask(self, scan: Scan, rays_world):
         dist = self.dist
         n = scan.n
+        if getattr(self, "halo_dirty", False):
+            self.exchange()
         kp, pp = self.grid.raycast_band_keys(scan, rays_world)
         keys = device_tensor(kp, n, "<i8", self.device)
         payload = device_tensor(pp, 4 * n, "<f8", self.device).view(n, 4)

@@ -1,0 +1,70 @@
+"""The header-compatible C++ mirror of the obvious:: interface (ohm_tsd_slam_b200/obvious/): tests/cpp/slam_loop.cpp
+replays ThreadLocalize / ThreadMapping against it.  The same source compiled against the reference's own headers
+produced tests/golden/slam_loop_*_mode0.txt (see the header of slam_loop.cpp)."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ohm_tsd_slam_b200 import _build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "slam_loop_b200")
+PHI_MIN = repr(-135.0 * math.pi / 180.0)
+ARGS = {
+    "tiny": ["8", "0.025", "3", "361", repr(math.pi / 240.0), PHI_MIN, "8.0", "0.001", "2.0"],
+    "C1": ["10", "0.025", "3", "1081", repr(math.pi / 720.0), PHI_MIN, "30.0", "0.001", "2.0"],
+}
+
+
+def build_exe():
+    _build.build()
+    src = os.path.join(ROOT, "tests", "cpp", "slam_loop.cpp")
+    hdr = os.path.join(ROOT, "ohm_tsd_slam_b200", "obvious", "obvious_b200.h")
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(_build.LIB)):
+        return EXE
+    libdir = os.path.join(ROOT, "ohm_tsd_slam_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I" + os.path.join(libdir, "obvious"), src, "-o", EXE,
+                    "-L" + libdir, "-ltsdslam_b200", "-Wl,-rpath," + libdir], check=True)
+    return EXE
+
+
+def run(name, mode):
+    out = subprocess.run([build_exe(), os.path.join(ROOT, "tests", "golden", f"scans_{name}.bin")] + ARGS[name] + [str(mode)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    return np.array([[float(v) for v in line.split()] for line in out.stdout.strip().splitlines()])
+
+
+def test_node_code_compiles_against_adapter_headers():
+    assert os.path.exists(build_exe())
+
+
+def test_adapter_fails_loudly_without_gpu():
+    from ohm_tsd_slam_b200 import capi
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    out = subprocess.run([build_exe(), os.path.join(ROOT, "tests", "golden", "scans_tiny.bin")] + ARGS["tiny"] + ["0"],
+                         capture_output=True, text=True)
+    assert out.returncode != 0 and "no CPU path" in out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny", "C1"])
+def test_slam_loop_tracks_reference_poses(name):
+    got = run(name, 0)
+    ref = np.loadtxt(os.path.join(ROOT, "tests", "golden", f"slam_loop_{name}_mode0.txt"))
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, [0, 4, 6]], ref[:, [0, 4, 6]])       # scan index, model points, iterations
+    assert np.max(np.abs(got[:, 1:4] - ref[:, 1:4])) < 1e-8             # x, y, theta after every scan
+    assert np.max(np.abs(got[:, 5] - ref[:, 5])) <= 2                   # ICP pairs (ulp-level pose differences)
+
+
+@pytest.mark.gpu
+def test_slam_loop_with_tsd_matcher():
+    """registration_mode 3 (TSD_PDFMatching pre-registration, random control set): poses stay with the ICP-only run."""
+    a = run("tiny", 0)
+    b = run("tiny", 3)
+    assert a.shape == b.shape and np.max(np.abs(a[:, 1:3] - b[:, 1:3])) < 0.05 and np.max(np.abs(a[:, 3] - b[:, 3])) < 0.02
