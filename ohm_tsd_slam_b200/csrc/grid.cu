@@ -117,10 +117,9 @@ struct PushParams
 
 // Per grid column X = ((double)ix + 0.5) * cellSize (TsdGridPartition.cpp:127): the two products of
 // SensorPolar2D.cpp:125 that depend on X only, with gslcblas' accumulation order (temp = 0; temp += a*b ...),
-// and the squared offset of TsdGrid.cpp:262.  Same per grid row.
-__global__ void k_tables(PushParams pp, double* coltab, double* rowtab)
+// and the squared offset of TsdGrid.cpp:262.  Same per grid row.  Runs inside k_classify (first threads).
+__device__ __forceinline__ void fill_tables(const PushParams& pp, double* coltab, double* rowtab, int i)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double* Pi = pp.scan.Pi;
   if(i < pp.cells_x)
   {
@@ -169,16 +168,24 @@ __device__ __forceinline__ int back_project_edge(const ScanDev& s, const double2
   return k;
 }
 
-#define CLASSIFY_WARPS 8
+#define CLASSIFY_THREADS 256
 
-// K1: TsdGridComponent::isInRange (TsdGridComponent.cpp:43-124) for every partition, one warp each.
-__global__ void __launch_bounds__(CLASSIFY_WARPS * 32) k_classify(PushParams pp)
+// K1: TsdGridComponent::isInRange (TsdGridComponent.cpp:43-124) for every partition.  Four lanes per partition
+// (one per edge point), eight partitions per warp; the beam interval [minIdx, maxIdx] is scanned by the four
+// lanes.  The first cells_x / cells_y threads of the grid also fill the column / row tables of this push.
+__global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, double* coltab, double* rowtab)
 {
+  const int gtid = blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
+  fill_tables(pp, coltab, rowtab, gtid);
   const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * CLASSIFY_WARPS + (threadIdx.x >> 5);
-  if(p >= pp.n_parts) return;
+  const int sub = lane & 3;
+  const int gshift = lane & ~3;
+  const unsigned gmask = 0xfu << gshift;
+  const int p = gtid >> 2;
+  // no lane leaves before the warp-wide part below: `alive` carries the reference's early returns
+  bool alive = p < pp.n_parts;
   const ScanDev& s = pp.scan;
-  const int px = p % pp.parts_x, py = p / pp.parts_x;
+  const int px = alive ? p % pp.parts_x : 0, py = alive ? p / pp.parts_x : 0;
   const unsigned int x0 = px * TSD_TILE, y0 = py * TSD_TILE;
   const double cs = pp.cell_size;
 
@@ -203,24 +210,24 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS * 32) k_classify(PushParams pp)
   }
   const double distance = sqrt(sqr);
   const double closest = distance - circumradius - pp.max_trunc;
-  if(closest > s.max_range) return;
+  if(closest > s.max_range) alive = false;
   const double farthest = distance + circumradius + pp.max_trunc;
-  if(farthest < s.min_range) return;
+  if(farthest < s.min_range) alive = false;
 
-  // lanes 0..3: the four edge points
+  // one edge point per lane
   int idxEdge = 0;
-  if(lane < 4)
+  if(alive)
   {
-    const double X = (lane & 1) ? e1x : e0x;
-    const double Y = (lane & 2) ? e2y : e0y;
+    const double X = (sub & 1) ? e1x : e0x;
+    const double Y = (sub & 2) ? e2y : e0y;
     idxEdge = back_project_edge(s, pp.dirs, X, Y);
   }
   bool visibleEdge = true;
   if(idxEdge == -1) { idxEdge = s.n - 1; visibleEdge = false; }
   else if(idxEdge == -2) { idxEdge = 0; visibleEdge = false; }
   if(idxEdge > s.n - 1) idxEdge = s.n - 1;  // the reference would read past the scan here
-  const unsigned vis4 = __ballot_sync(0xffffffffu, visibleEdge) & 0xfu;
-  if(vis4 == 0u) return;  // !isAnyEdgeVisible
+  const unsigned vis4 = (__ballot_sync(0xffffffffu, visibleEdge) >> gshift) & 0xfu;
+  if(vis4 == 0u) alive = false;  // !isAnyEdgeVisible
   const bool allVisible = (vis4 == 0xfu);
   int minIdx = idxEdge, maxIdx = idxEdge;
 #pragma unroll
@@ -231,25 +238,54 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS * 32) k_classify(PushParams pp)
     minIdx = min(minIdx, a);
     maxIdx = max(maxIdx, b);
   }
-  minIdx = __shfl_sync(0xffffffffu, minIdx, 0);
-  maxIdx = __shfl_sync(0xffffffffu, maxIdx, 0);
 
+  // TsdGridComponent.cpp:96-118: the beams between the outermost edge beams.  Narrow intervals are scanned by
+  // the partition's four lanes, wide ones (partitions next to the sensor) by the whole warp.
   bool vis = false, empty = true;
-  for(int j = minIdx + lane; j <= maxIdx; j += 32)
+  const bool wide = alive && (maxIdx - minIdx > 96);
+  if(alive && !wide)
   {
-    const double d = s.ranges[j];
-    const bool m = s.mask[j] != 0;
-    vis = vis || ((d > closest) && m);
-    if(isinf(d)) empty = empty && (distance < s.low_refl);
-    else empty = empty && (d > farthest) && m;
+    for(int j = minIdx + sub; j <= maxIdx; j += 4)
+    {
+      const double d = s.ranges[j];
+      const bool m = s.mask[j] != 0;
+      vis = vis || ((d > closest) && m);
+      if(isinf(d)) empty = empty && (distance < s.low_refl);
+      else empty = empty && (d > farthest) && m;
+    }
   }
-  if(!__any_sync(0xffffffffu, vis)) return;
+  unsigned wideLeaders = __ballot_sync(0xffffffffu, wide && sub == 0);
+  while(wideLeaders)
+  {
+    const int gl = __ffs(wideLeaders) - 1;
+    wideLeaders &= wideLeaders - 1;
+    const int lo = __shfl_sync(0xffffffffu, minIdx, gl), hi = __shfl_sync(0xffffffffu, maxIdx, gl);
+    const double cl = __shfl_sync(0xffffffffu, closest, gl), fa = __shfl_sync(0xffffffffu, farthest, gl);
+    const double di = __shfl_sync(0xffffffffu, distance, gl);
+    bool v = false, e = true;
+    for(int j = lo + lane; j <= hi; j += 32)
+    {
+      const double d = s.ranges[j];
+      const bool m = s.mask[j] != 0;
+      v = v || ((d > cl) && m);
+      if(isinf(d)) e = e && (di < s.low_refl);
+      else e = e && (d > fa) && m;
+    }
+    const bool anyV = __any_sync(0xffffffffu, v);
+    const bool allE = __all_sync(0xffffffffu, e);
+    if((lane >> 2) == (gl >> 2)) { vis = anyV; empty = allE; }
+  }
+  const unsigned mVis = __ballot_sync(0xffffffffu, vis);
+  const unsigned mEmpty = __ballot_sync(0xffffffffu, empty);
+  if(!alive) return;
+  if((mVis & gmask) == 0u) return;
+  const bool allEmpty = (mEmpty & gmask) == gmask;
   const bool owned = (py >= pp.row_begin && py < pp.row_end);
   const bool wasInit = pp.flags[p] != 0;
-  if(allVisible && __all_sync(0xffffffffu, empty))
+  if(allVisible && allEmpty)
   {
     // increaseEmptiness (TsdGridPartition.cpp:136-164)
-    if(lane == 0)
+    if(sub == 0)
     {
       if(wasInit)
       {
@@ -267,7 +303,7 @@ __global__ void __launch_bounds__(CLASSIFY_WARPS * 32) k_classify(PushParams pp)
     return;
   }
   // active: TsdGrid.cpp:237-243
-  if(lane == 0)
+  if(sub == 0)
   {
     double distCentroid = sqrt((cenx - trx) * (cenx - trx) + (ceny - try_) * (ceny - try_));
     if(distCentroid > s.max_range) distCentroid = s.max_range;
@@ -307,8 +343,8 @@ __device__ __forceinline__ bool update_cell(const PushParams& pp, const double* 
   slowCount += slow ? 1u : 0u;
   if(index < 0) return false;
   const int idx = min(index, s.n - 1);
-  if(!s_mask[idx]) return false;
-  const double r = s_ranges[idx];
+  if(!__ldg(s_mask + idx)) return false;
+  const double r = __ldg(s_ranges + idx);
   const double dist = sqrt(colD + rowD);
   double sd;
   if(!isinf(r)) sd = r - dist;
@@ -318,7 +354,7 @@ __device__ __forceinline__ bool update_cell(const PushParams& pp, const double* 
     sd = pp.max_trunc;
   }
   if(!(sd >= -pp.max_trunc)) return false;
-  const double tsdNew = ob_min(sd * pp.inv_max_trunc, 1.0);
+  const double tsdNew = fmin(sd * pp.inv_max_trunc, 1.0);  // == obvious::min(a, 1.0): the constant is never NaN
   if(isnan(tsd))
   {
     tsd = tsdNew;
@@ -327,7 +363,7 @@ __device__ __forceinline__ bool update_cell(const PushParams& pp, const double* 
   else
   {
     tsd = (tsd * weight + tsdNew * wTile) / (weight + wTile);
-    weight = ob_min(weight + wTile, TSD_MAXWEIGHT);
+    weight = fmin(weight + wTile, TSD_MAXWEIGHT);
   }
   return true;
 }
@@ -342,7 +378,7 @@ __device__ __forceinline__ void empty_cell(double& tsd, double& weight)
   }
   else
   {
-    weight = ob_min(weight + 1, TSD_MAXWEIGHT);
+    weight = fmin(weight + 1, TSD_MAXWEIGHT);
     tsd = (tsd * (weight - 1.0) + 1.0) / weight;
   }
 }
@@ -352,19 +388,12 @@ __device__ __forceinline__ void empty_cell(double& tsd, double& weight)
 // adjacent 256-B rows (512 contiguous bytes) per 16-byte vector load.
 __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
+  // the scan (8.6 KB + 1 KB) and the beam-boundary table (17 KB) are read through L1 (read-only path): they
+  // stay resident per SM for the whole launch, with no per-CTA staging pass
   const ScanDev& s = pp.scan;
-  const int n = s.n;
-  double2* s_dirs = reinterpret_cast<double2*>(smem);
-  double* s_ranges = reinterpret_cast<double*>(s_dirs + (n + 1));
-  uint8_t* s_mask = reinterpret_cast<uint8_t*>(s_ranges + n);
-  for(int i = threadIdx.x; i <= n; i += blockDim.x) s_dirs[i] = pp.dirs[i];
-  for(int i = threadIdx.x; i < n; i += blockDim.x)
-  {
-    s_ranges[i] = s.ranges[i];
-    s_mask[i] = s.mask[i];
-  }
-  __syncthreads();
+  const double2* s_dirs = pp.dirs;
+  const double* s_ranges = s.ranges;
+  const uint8_t* s_mask = s.mask;
 
   const uint32_t nActive = pp.counters[0];
   const uint32_t nEmptied = pp.counters[1];
@@ -528,6 +557,46 @@ __device__ __forceinline__ void refresh_borders_of(const PushParams& pp, int px,
   }
 }
 
+// The six border strips that depend on one touched partition T: T's own right / top / corner (from its +x, +y,
+// +xy neighbours) and the strips of its -x, -y, -xy neighbours that mirror T's first column / row / cell.  All
+// loads are issued before the first store: one memory round trip per touched partition.
+__device__ __forceinline__ void refresh_strips_around(const PushParams& pp, int px, int py, int lane)
+{
+  const int p = py * pp.parts_x + px;
+  const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
+  const size_t rowStride = (size_t)pp.parts_x * TSD_TILE_STRIDE;
+  const bool hasR = px < pp.parts_x - 1 && pp.flags[p + 1];
+  const bool hasU = py < pp.parts_y - 1 && py + 1 < pp.alloc_end && pp.flags[p + pp.parts_x];
+  const bool hasUR = px < pp.parts_x - 1 && py < pp.parts_y - 1 && py + 1 < pp.alloc_end && pp.flags[p + pp.parts_x + 1];
+  const bool hasL = px > 0 && pp.flags[p - 1];
+  const bool hasD = py > pp.row_begin && pp.flags[p - pp.parts_x];
+  const bool hasDL = px > 0 && py > pp.row_begin && pp.flags[p - pp.parts_x - 1];
+  double tR = 0, wR = 0, tU = 0, wU = 0, tC = 0, wC = 0, tc0 = 0, wc0 = 0, tr0 = 0, wr0 = 0;
+  if(hasR) { tR = pp.tsd[base + TSD_TILE_STRIDE + lane * TSD_TILE]; wR = pp.weight[base + TSD_TILE_STRIDE + lane * TSD_TILE]; }
+  if(hasU) { tU = pp.tsd[base + rowStride + lane]; wU = pp.weight[base + rowStride + lane]; }
+  if(hasUR && lane == 0) { tC = pp.tsd[base + rowStride + TSD_TILE_STRIDE]; wC = pp.weight[base + rowStride + TSD_TILE_STRIDE]; }
+  if(hasL) { tc0 = pp.tsd[base + lane * TSD_TILE]; wc0 = pp.weight[base + lane * TSD_TILE]; }
+  if(hasD || hasDL) { tr0 = pp.tsd[base + lane]; wr0 = pp.weight[base + lane]; }
+  if(hasR) { pp.tsd[base + TSD_BORDER_OFF + lane] = tR; pp.weight[base + TSD_BORDER_OFF + lane] = wR; }
+  if(hasU) { pp.tsd[base + TSD_BORDER_OFF + 32 + lane] = tU; pp.weight[base + TSD_BORDER_OFF + 32 + lane] = wU; }
+  if(hasUR && lane == 0) { pp.tsd[base + TSD_BORDER_OFF + 64] = tC; pp.weight[base + TSD_BORDER_OFF + 64] = wC; }
+  if(hasL)
+  {
+    pp.tsd[base - TSD_TILE_STRIDE + TSD_BORDER_OFF + lane] = tc0;
+    pp.weight[base - TSD_TILE_STRIDE + TSD_BORDER_OFF + lane] = wc0;
+  }
+  if(hasD)
+  {
+    pp.tsd[base - rowStride + TSD_BORDER_OFF + 32 + lane] = tr0;
+    pp.weight[base - rowStride + TSD_BORDER_OFF + 32 + lane] = wr0;
+  }
+  if(hasDL && lane == 0)
+  {
+    pp.tsd[base - rowStride - TSD_TILE_STRIDE + TSD_BORDER_OFF + 64] = tr0;
+    pp.weight[base - rowStride - TSD_TILE_STRIDE + TSD_BORDER_OFF + 64] = wr0;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_borders(PushParams pp, int all)
 {
   const int lane = threadIdx.x & 31;
@@ -552,14 +621,20 @@ __global__ void __launch_bounds__(256) k_borders(PushParams pp, int all)
     if(item < nA) p = pp.active[item] & 0x7fffffffu;
     else if(item < nA + nE) p = pp.emptied[item - nA];
     else p = pp.pending[item - nA - nE];
-    const int px = p % pp.parts_x, py = p / pp.parts_x;
     if(!pp.flags[p]) continue;
-    refresh_borders_of(pp, px, py, lane);
-    // neighbours whose border mirrors this partition
-    if(px > 0 && pp.flags[p - 1]) refresh_borders_of(pp, px - 1, py, lane);
-    if(py > pp.row_begin && pp.flags[p - pp.parts_x]) refresh_borders_of(pp, px, py - 1, lane);
-    if(px > 0 && py > pp.row_begin && pp.flags[p - pp.parts_x - 1]) refresh_borders_of(pp, px - 1, py - 1, lane);
+    refresh_strips_around(pp, p % pp.parts_x, p / pp.parts_x, lane);
   }
+}
+
+// after K4: snapshot the per-push statistics (so that a later push does not clobber them before they are read)
+// and consume the pending list / refresh-all flag
+__global__ void k_push_tail(PushParams pp)
+{
+  if(threadIdx.x < 8) pp.counters[8 + threadIdx.x] = pp.counters[threadIdx.x];
+  if(threadIdx.x == 8) pp.stats64[1] = pp.stats64[0];
+  __syncwarp();
+  if(threadIdx.x < 8) pp.counters[threadIdx.x] = 0;  // next push starts from zero (incl. pending / refresh-all)
+  if(threadIdx.x == 8) pp.stats64[0] = 0;
 }
 
 // TsdGrid::freeFootprint (TsdGrid.cpp:609-638), phase 1: initialise the partitions under the footprint
@@ -1025,21 +1100,17 @@ int tsdg_push_staged(tsd_grid_t* g)
   pp.dirs = g->d_dirs;
   const tsd::ScanDev* scan = &g->staged;
   // counters [0] active [1] emptied are per push; [2] pending and [3] refresh-all persist until consumed below
-  TSD_CUDA(cudaMemsetAsync(g->d_counters, 0, sizeof(uint32_t) * 2, g->stream));
-  TSD_CUDA(cudaMemsetAsync(g->d_counters + 4, 0, sizeof(uint32_t) * 4, g->stream));
-  TSD_CUDA(cudaMemsetAsync(g->d_stats64, 0, sizeof(unsigned long long) * 4, g->stream));
+  // (pending [2] and refresh-all [3] were zeroed by the previous push's tail; [0..1], [4..7] and the 64-bit
+  //  statistics are zeroed by k_tables' first thread)
+  if(g->band && g->band_push_open) { set_error("the previous sharded push was not finished (tsdg_band_push_finish)"); return TSD_E_INVALID; }
   const int nmax = g->cells_x > g->cells_y ? g->cells_x : g->cells_y;
+  const int nthreads = (4 * g->n_parts > nmax) ? 4 * g->n_parts : nmax;
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[0], g->stream));
-  k_tables<<<(nmax + 255) / 256, 256, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
-  TSD_LAUNCHED();
-  k_classify<<<(g->n_parts + CLASSIFY_WARPS - 1) / CLASSIFY_WARPS, CLASSIFY_WARPS * 32, 0, g->stream>>>(pp);
+  k_classify<<<(nthreads + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[1], g->stream));
-  const size_t smem = sizeof(double2) * (scan->n + 1) + sizeof(double) * scan->n + scan->n + 16;
-  if(smem > 48 * 1024)
-  {
-    TSD_CUDA(cudaFuncSetAttribute(k_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  const size_t smem = 0;
+  (void)scan;
   int ctas = g->sm_count * 4;
   if(ctas > g->n_owned) ctas = g->n_owned;
   k_update<<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
@@ -1060,10 +1131,9 @@ static int push_finish(tsd_grid* g, const PushParams& pp)
   k_borders<<<bctas, 256, 0, g->stream>>>(pp, 0);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[3], g->stream));
-  TSD_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, g->stream));
-  TSD_CUDA(cudaMemcpyAsync(g->h_stats64, g->d_stats64, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, g->stream));
-  // pending list and refresh-all flag are consumed
-  TSD_CUDA(cudaMemsetAsync(g->d_counters + 2, 0, sizeof(uint32_t) * 2, g->stream));
+  // pending list and refresh-all flag are consumed (k_borders' tail); statistics are fetched on demand
+  k_push_tail<<<1, 32, 0, g->stream>>>(pp);
+  TSD_LAUNCHED();
   g->pushed_once = true;
   return TSD_OK;
 }
@@ -1172,13 +1242,15 @@ int tsdg_last_push_stats(tsd_grid_t* g, tsd_push_stats_t* out)
 {
   if(!g || !out) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, g->stream));
+  TSD_CUDA(cudaMemcpyAsync(g->h_stats64, g->d_stats64, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, g->stream));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
-  out->cell_updates = g->h_stats64[0];
-  out->active_tiles = g->h_counters[7];
-  out->cell_visits = (uint64_t)g->h_counters[0] * TSD_TILE_CELLS;
-  out->emptied_tiles = g->h_counters[6];
-  out->newly_initialized = g->h_counters[4];
-  out->fallback_cells = g->h_counters[5];
+  out->cell_updates = g->h_stats64[1];
+  out->active_tiles = g->h_counters[8 + 7];
+  out->cell_visits = (uint64_t)g->h_counters[8 + 0] * TSD_TILE_CELLS;
+  out->emptied_tiles = g->h_counters[8 + 6];
+  out->newly_initialized = g->h_counters[8 + 4];
+  out->fallback_cells = g->h_counters[8 + 5];
   return TSD_OK;
 }
 
