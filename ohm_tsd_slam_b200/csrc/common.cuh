@@ -219,6 +219,7 @@ struct tsd_grid
   int alloc_begin, alloc_end, n_alloc;  // allocated rows: owned + halo rows (bands only)
   bool band;                        // sharded grid: push runs in two phases around the halo exchange
   bool band_push_open;
+  bool refresh_all_pending;        // an upload / fill asked for a full border refresh at the next push
   double cell_size, inv_cell_size, max_truncation;
   double min_x, max_x, min_y, max_y;
   bool pushed_once;
@@ -231,6 +232,7 @@ struct tsd_grid
   uint32_t* d_active;  // bit 31: partition was initialised before this push
   double* d_active_w;  // 0.01 * partWeight per active item
   uint32_t* d_emptied;
+  uint32_t* d_newly;   // partitions allocated by the current push
   uint32_t* d_pending; // partitions initialised/modified outside push: borders refreshed by the next push
   uint32_t* d_counters;   // [0] active [1] emptied [2] pending [3] refresh-all flag [4] newly initialised [5] slow cells
   unsigned long long* d_stats64;  // [0] cell updates

@@ -100,6 +100,7 @@ struct PushParams
   int row_begin, row_end;
   int alloc_begin, alloc_end;
   int band;
+  int fused_tail;  // 1: k_update's last CTA runs the pull pass and the push tail (no k_borders launch)
   double* tsd;
   double* weight;
   uint8_t* flags;
@@ -107,6 +108,7 @@ struct PushParams
   uint32_t* active;
   double* active_w;
   uint32_t* emptied;
+  uint32_t* newly;    // partitions allocated by this push (count: counters[4], owned ones only in the list)
   uint32_t* pending;
   uint32_t* counters;
   unsigned long long* stats64;
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
     {
       pp.flags[p] = 1;
       atomicAdd(&pp.counters[4], 1u);
+      if(owned) pp.newly[atomicAdd(&pp.counters[18], 1u)] = (uint32_t)p;
     }
     atomicAdd(&pp.counters[7], 1u);
   }
@@ -383,7 +386,48 @@ __device__ __forceinline__ void empty_cell(double& tsd, double& weight)
   }
 }
 
-// K2 + K3.  Persistent CTAs; the scan and the beam-boundary table are staged in shared memory once per CTA.
+// Border bookkeeping inside k_update (replaces most of the reference's propagateBorders pass, TsdGrid.cpp:372-427).
+// Invariant after every push: a border strip whose source neighbour (+x, +y, +xy) is initialised equals that
+// neighbour's first column / row / cell.  So (a) a partition never needs to update such a strip itself
+// (increaseEmptiness, init) -- whoever owns the source keeps it current -- and (b) every partition that k_update
+// rewrites stores its own first column / row / cell into the strips of its -x, -y, -xy neighbours that mirror
+// them.  What is left for k_borders is to *pull* the strips of partitions that became initialised outside this
+// mechanism (allocated by this push, by freeFootprint or by an upload).
+__device__ __forceinline__ bool strip_has_source(const PushParams& pp, int p, int px, int py, int b)
+{
+  if(b < 32) return px < pp.parts_x - 1 && pp.flags[p + 1];
+  if(b < 64) return py < pp.parts_y - 1 && pp.flags[p + pp.parts_x];
+  return px < pp.parts_x - 1 && py < pp.parts_y - 1 && pp.flags[p + pp.parts_x + 1];
+}
+
+// thread (xp, y) holds the final values of cells (y, xp) and (y, xp + 1) of partition p
+__device__ __forceinline__ void mirror_to_neighbours(const PushParams& pp, int p, int px, int py, size_t base, int xp, int y,
+                                                     const double2& tv, const double2& wv)
+{
+  const size_t rowStride = (size_t)pp.parts_x * TSD_TILE_STRIDE;
+  if(xp == 0 && px > 0 && pp.flags[p - 1])
+  {
+    // first column -> right border of the -x neighbour
+    pp.tsd[base - TSD_TILE_STRIDE + TSD_BORDER_OFF + y] = tv.x;
+    pp.weight[base - TSD_TILE_STRIDE + TSD_BORDER_OFF + y] = wv.x;
+  }
+  if(y == 0 && py > pp.row_begin && pp.flags[p - pp.parts_x])
+  {
+    // first row -> top border of the -y neighbour
+    *reinterpret_cast<double2*>(pp.tsd + base - rowStride + TSD_BORDER_OFF + 32 + xp) = tv;
+    *reinterpret_cast<double2*>(pp.weight + base - rowStride + TSD_BORDER_OFF + 32 + xp) = wv;
+  }
+  if(y == 0 && xp == 0 && px > 0 && py > pp.row_begin && pp.flags[p - pp.parts_x - 1])
+  {
+    pp.tsd[base - rowStride - TSD_TILE_STRIDE + TSD_BORDER_OFF + 64] = tv.x;
+    pp.weight[base - rowStride - TSD_TILE_STRIDE + TSD_BORDER_OFF + 64] = wv.x;
+  }
+}
+
+__device__ __forceinline__ void pull_pass(const PushParams& pp, int warp, int nwarps, int lane);
+__device__ __forceinline__ void push_tail(const PushParams& pp);
+
+// K2 + K3.  Persistent CTAs with a two-stage cp.async pipeline over their partitions.
 // Thread t of 256 owns the cell pair x = 2*(t%16), 2*(t%16)+1 in rows t/16 and t/16 + 16: a warp reads two
 // adjacent 256-B rows (512 contiguous bytes) per 16-byte vector load.
 __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
@@ -397,28 +441,45 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
 
   const uint32_t nActive = pp.counters[0];
   const uint32_t nEmptied = pp.counters[1];
+  const uint32_t nItems = nActive + nEmptied;
   const int t = threadIdx.x;
   const int xp = (t & 15) * 2;
   const int yb = t >> 4;
   unsigned long long updates = 0;
   unsigned slowCount = 0;
 
-  for(uint32_t item = blockIdx.x; item < nActive + nEmptied; item += gridDim.x)
+  // Two-stage pipeline over the CTA's partitions: the 16 KB of cell state of partition i+1 are copied into
+  // shared memory with cp.async (LDGSTS, L1 bypass) while partition i is computed.  Every thread copies exactly
+  // the four 16-byte pieces it will read itself, so the only synchronisation is its own cp.async.wait_group.
+  __shared__ __align__(16) double2 s_cells[2][2][2 * UPDATE_THREADS];  // [stage][tsd|weight][row j * 256 + t]
+  auto stage_in = [&](uint32_t it, int stage)
   {
+    if(it < nItems)
     {
-      // pull the next partition of this CTA towards L2 while this one is being computed
-      const uint32_t nxt = item + gridDim.x;
-      if(nxt < nActive + nEmptied)
+      const uint32_t e = (it < nActive) ? pp.active[it] : (pp.emptied[it - nActive] | 0x80000000u);
+      if(e & 0x80000000u)  // allocated before this push: its cells are read
       {
-        const uint32_t e = (nxt < nActive) ? pp.active[nxt] : (pp.emptied[nxt - nActive] | 0x80000000u);
-        if(e & 0x80000000u)
+        const size_t nb = (size_t)((e & 0x7fffffffu) - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
+#pragma unroll
+        for(int j = 0; j < 2; j++)
         {
-          const size_t nb = (size_t)((e & 0x7fffffffu) - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE + (size_t)t * 4;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp.tsd + nb));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp.weight + nb));
+          const int ci = (yb + 16 * j) * TSD_TILE + xp;
+          const unsigned dT = (unsigned)__cvta_generic_to_shared(&s_cells[stage][0][j * UPDATE_THREADS + t]);
+          const unsigned dW = (unsigned)__cvta_generic_to_shared(&s_cells[stage][1][j * UPDATE_THREADS + t]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dT), "l"(pp.tsd + nb + ci));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dW), "l"(pp.weight + nb + ci));
         }
       }
     }
+    asm volatile("cp.async.commit_group;" ::);
+  };
+
+  stage_in(blockIdx.x, 0);
+  int stage = 0;
+  for(uint32_t item = blockIdx.x; item < nItems; item += gridDim.x, stage ^= 1)
+  {
+    stage_in(item + gridDim.x, stage ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     if(item < nActive)
     {
       const uint32_t e = pp.active[item];
@@ -452,8 +513,8 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
         double2 tv, wv;
         if(wasInit)
         {
-          tv = *reinterpret_cast<const double2*>(T + ci);
-          wv = *reinterpret_cast<const double2*>(W + ci);
+          tv = s_cells[stage][0][j * UPDATE_THREADS + t];
+          wv = s_cells[stage][1][j * UPDATE_THREADS + t];
         }
         else
         {
@@ -468,8 +529,9 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
           *reinterpret_cast<double2*>(T + ci) = tv;
           *reinterpret_cast<double2*>(W + ci) = wv;
         }
+        if(y == 0 || xp == 0) mirror_to_neighbours(pp, (int)p, px, py, base, xp, y, tv, wv);
       }
-      if(!wasInit && t < 65)
+      if(!wasInit && t < 65 && !strip_has_source(pp, (int)p, px, py, t))
       {
         T[TSD_BORDER_OFF + t] = initT;
         W[TSD_BORDER_OFF + t] = initW;
@@ -479,21 +541,24 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
     {
       // K3: increaseEmptiness on an initialised partition, all 33x33 cells
       const uint32_t p = pp.emptied[item - nActive];
+      const int px = p % pp.parts_x, py = p / pp.parts_x;
       const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
       double* T = pp.tsd + base;
       double* W = pp.weight + base;
 #pragma unroll
       for(int j = 0; j < 2; j++)
       {
-        const int ci = (yb + 16 * j) * TSD_TILE + xp;
-        double2 tv = *reinterpret_cast<const double2*>(T + ci);
-        double2 wv = *reinterpret_cast<const double2*>(W + ci);
+        const int y = yb + 16 * j;
+        const int ci = y * TSD_TILE + xp;
+        double2 tv = s_cells[stage][0][j * UPDATE_THREADS + t];
+        double2 wv = s_cells[stage][1][j * UPDATE_THREADS + t];
         empty_cell(tv.x, wv.x);
         empty_cell(tv.y, wv.y);
         *reinterpret_cast<double2*>(T + ci) = tv;
         *reinterpret_cast<double2*>(W + ci) = wv;
+        if(y == 0 || xp == 0) mirror_to_neighbours(pp, (int)p, px, py, base, xp, y, tv, wv);
       }
-      if(t < 65)
+      if(t < 65 && !strip_has_source(pp, (int)p, px, py, t))
       {
         double tv = T[TSD_BORDER_OFF + t], wv = W[TSD_BORDER_OFF + t];
         empty_cell(tv, wv);
@@ -503,6 +568,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
       if(t == 0) updates += 33 * 33;
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 
   // one atomic per CTA
   __shared__ unsigned long long s_upd[UPDATE_THREADS / 32];
@@ -522,6 +588,30 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
     for(int i = 0; i < UPDATE_THREADS / 32; i++) { u += s_upd[i]; sl += s_slow[i]; }
     if(u) atomicAdd(&pp.stats64[0], u);
     if(sl) atomicAdd(&pp.counters[5], sl);
+  }
+  if(pp.fused_tail)
+  {
+    // the last CTA to get here has seen every partition of this push written: it pulls the borders of the
+    // partitions this push allocated (usually none) and closes the push
+    __shared__ unsigned s_last;
+    if(t == 0)
+    {
+      __threadfence();
+      s_last = (atomicAdd(&pp.counters[17], 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if(s_last)
+    {
+      __threadfence();
+      pull_pass(pp, t >> 5, UPDATE_THREADS / 32, t & 31);
+      __syncthreads();
+      if(t == 0)
+      {
+        __threadfence();
+        push_tail(pp);
+        pp.counters[17] = 0;
+      }
+    }
   }
 }
 
@@ -597,44 +687,60 @@ __device__ __forceinline__ void refresh_strips_around(const PushParams& pp, int 
   }
 }
 
-__global__ void __launch_bounds__(256) k_borders(PushParams pp, int all)
+// pull pass: partitions allocated by this push (their strips were not maintained before) and partitions
+// allocated / modified outside push since the last one
+__device__ __forceinline__ void pull_pass(const PushParams& pp, int warp, int nwarps, int lane)
 {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  if(all || pp.counters[3])
+  const uint32_t nN = pp.counters[18], nP = pp.counters[2];
+  for(uint32_t item = warp; item < nN + nP; item += nwarps)
   {
-    for(int p = pp.row_begin * pp.parts_x + warp; p < pp.row_end * pp.parts_x; p += nwarps)
-      if(pp.flags[p]) refresh_borders_of(pp, p % pp.parts_x, p / pp.parts_x, lane);
-    return;
-  }
-  if(pp.band && pp.row_end < pp.parts_y)
-  {
-    // the partitions above the band's top row belong to another GPU and may have changed: refresh the row
-    for(int px = warp; px < pp.parts_x; px += nwarps)
-      if(pp.flags[(pp.row_end - 1) * pp.parts_x + px]) refresh_borders_of(pp, px, pp.row_end - 1, lane);
-  }
-  const uint32_t nA = pp.counters[0], nE = pp.counters[1], nP = pp.counters[2];
-  for(uint32_t item = warp; item < nA + nE + nP; item += nwarps)
-  {
-    uint32_t p;
-    if(item < nA) p = pp.active[item] & 0x7fffffffu;
-    else if(item < nA + nE) p = pp.emptied[item - nA];
-    else p = pp.pending[item - nA - nE];
+    const uint32_t p = (item < nN) ? pp.newly[item] : pp.pending[item - nN];
     if(!pp.flags[p]) continue;
     refresh_strips_around(pp, p % pp.parts_x, p / pp.parts_x, lane);
   }
 }
 
-// after K4: snapshot the per-push statistics (so that a later push does not clobber them before they are read)
-// and consume the pending list / refresh-all flag
-__global__ void k_push_tail(PushParams pp)
+// snapshot the per-push statistics (so that a later push does not clobber them before they are read) and zero
+// the per-push counters, the pending list and the refresh-all flag
+__device__ __forceinline__ void push_tail(const PushParams& pp)
 {
-  if(threadIdx.x < 8) pp.counters[8 + threadIdx.x] = pp.counters[threadIdx.x];
-  if(threadIdx.x == 8) pp.stats64[1] = pp.stats64[0];
-  __syncwarp();
-  if(threadIdx.x < 8) pp.counters[threadIdx.x] = 0;  // next push starts from zero (incl. pending / refresh-all)
-  if(threadIdx.x == 8) pp.stats64[0] = 0;
+  for(int i = 0; i < 8; i++) pp.counters[8 + i] = pp.counters[i];
+  pp.stats64[1] = pp.stats64[0];
+  for(int i = 0; i < 8; i++) pp.counters[i] = 0;
+  pp.counters[18] = 0;
+  pp.stats64[0] = 0;
+}
+
+// K4 as a kernel of its own: sharded grids (after the halo exchange) and "refresh everything" requests.
+__global__ void __launch_bounds__(256) k_borders(PushParams pp, int all)
+{
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool refreshAll = all || pp.counters[3];
+  if(refreshAll)
+  {
+    for(int p = pp.row_begin * pp.parts_x + warp; p < pp.row_end * pp.parts_x; p += nwarps)
+      if(pp.flags[p]) refresh_borders_of(pp, p % pp.parts_x, p / pp.parts_x, lane);
+  }
+  if(!refreshAll && pp.band && pp.row_end < pp.parts_y)
+  {
+    // the partitions above the band's top row belong to another GPU and may have changed: refresh the row
+    for(int px = warp; px < pp.parts_x; px += nwarps)
+      if(pp.flags[(pp.row_end - 1) * pp.parts_x + px]) refresh_borders_of(pp, px, pp.row_end - 1, lane);
+  }
+  if(!refreshAll) pull_pass(pp, warp, nwarps, lane);
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    __threadfence();
+    const unsigned ticket = atomicAdd(&pp.counters[16], 1u);
+    if(ticket == gridDim.x - 1)
+    {
+      push_tail(pp);
+      pp.counters[16] = 0;
+    }
+  }
 }
 
 // TsdGrid::freeFootprint (TsdGrid.cpp:609-638), phase 1: initialise the partitions under the footprint
@@ -745,6 +851,7 @@ static PushParams make_params(const tsd_grid* g)
   pp.active = g->d_active;
   pp.active_w = g->d_active_w;
   pp.emptied = g->d_emptied;
+  pp.newly = g->d_newly;
   pp.pending = g->d_pending;
   pp.counters = g->d_counters;
   pp.stats64 = g->d_stats64;
@@ -986,8 +1093,9 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMalloc(&g->d_active, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_active_w, sizeof(double) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_emptied, sizeof(uint32_t) * g->n_owned));
+  TSD_CUDA(cudaMalloc(&g->d_newly, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_pending, sizeof(uint32_t) * g->n_owned));
-  TSD_CUDA(cudaMalloc(&g->d_counters, sizeof(uint32_t) * 16));
+  TSD_CUDA(cudaMalloc(&g->d_counters, sizeof(uint32_t) * 32));
   TSD_CUDA(cudaMalloc(&g->d_stats64, sizeof(unsigned long long) * 4));
   TSD_CUDA(cudaMalloc(&g->d_coltab, sizeof(double) * 3 * g->cells_x));
   TSD_CUDA(cudaMalloc(&g->d_rowtab, sizeof(double) * 3 * g->cells_y));
@@ -995,7 +1103,7 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMallocHost(&g->h_stats64, sizeof(unsigned long long) * 4));
   TSD_CUDA(cudaMemsetAsync(g->d_flags, 0, g->n_parts, g->stream));
   TSD_CUDA(cudaMemsetAsync(g->d_initw, 0, sizeof(double) * g->n_parts, g->stream));
-  TSD_CUDA(cudaMemsetAsync(g->d_counters, 0, sizeof(uint32_t) * 16, g->stream));
+  TSD_CUDA(cudaMemsetAsync(g->d_counters, 0, sizeof(uint32_t) * 32, g->stream));
   TSD_CUDA(cudaMemsetAsync(g->d_stats64, 0, sizeof(unsigned long long) * 4, g->stream));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   *out = g;
@@ -1013,7 +1121,7 @@ int tsdg_destroy(tsd_grid_t* g)
   cudaSetDevice(g->device);
   if(g->stream) cudaStreamSynchronize(g->stream);
   cudaFree(g->d_tsd); cudaFree(g->d_weight); cudaFree(g->d_flags); cudaFree(g->d_initw); cudaFree(g->d_active);
-  cudaFree(g->d_active_w); cudaFree(g->d_emptied); cudaFree(g->d_pending); cudaFree(g->d_counters);
+  cudaFree(g->d_active_w); cudaFree(g->d_emptied); cudaFree(g->d_newly); cudaFree(g->d_pending); cudaFree(g->d_counters);
   cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_dirs); cudaFree(g->d_in);
   cudaFree(g->d_rc); cudaFree(g->d_scratch);
   cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters);
@@ -1113,9 +1221,17 @@ int tsdg_push_staged(tsd_grid_t* g)
   (void)scan;
   int ctas = g->sm_count * 4;
   if(ctas > g->n_owned) ctas = g->n_owned;
+  // unsharded grid, nothing asked for a full border refresh: K4's remainder runs in k_update's last CTA
+  pp.fused_tail = (!g->band && !g->refresh_all_pending) ? 1 : 0;
   k_update<<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[2], g->stream));
+  if(pp.fused_tail)
+  {
+    if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[3], g->stream));
+    g->pushed_once = true;
+    return TSD_OK;
+  }
   if(g->band)
   {
     // sharded grid: the borders need the neighbour band's fresh first row -> tsdg_band_push_finish()
@@ -1127,13 +1243,13 @@ int tsdg_push_staged(tsd_grid_t* g)
 
 static int push_finish(tsd_grid* g, const PushParams& pp)
 {
-  int bctas = g->sm_count * 4;
+  g->refresh_all_pending = false;
+  int bctas = g->sm_count;
   k_borders<<<bctas, 256, 0, g->stream>>>(pp, 0);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[3], g->stream));
-  // pending list and refresh-all flag are consumed (k_borders' tail); statistics are fetched on demand
-  k_push_tail<<<1, 32, 0, g->stream>>>(pp);
-  TSD_LAUNCHED();
+  // (pending list, refresh-all flag and per-push counters are consumed by k_borders' last CTA; statistics
+  //  are fetched on demand)
   g->pushed_once = true;
   return TSD_OK;
 }
@@ -1386,6 +1502,7 @@ int tsdg_upload_partition(tsd_grid_t* g, int32_t p, const double* tsd, const dou
   TSD_CUDA(cudaMemcpy(g->d_flags + p, &one, 1, cudaMemcpyHostToDevice));
   const uint32_t all = 1;  // the next push refreshes every border, like the reference's full propagateBorders
   TSD_CUDA(cudaMemcpy(g->d_counters + 3, &all, sizeof(all), cudaMemcpyHostToDevice));
+  g->refresh_all_pending = true;
   return TSD_OK;
 }
 
@@ -1399,6 +1516,7 @@ int tsdg_fill(tsd_grid_t* g, double tsd, double weight, int only_uninitialized)
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   const uint32_t all = 1;
   TSD_CUDA(cudaMemcpy(g->d_counters + 3, &all, sizeof(all), cudaMemcpyHostToDevice));
+  g->refresh_all_pending = true;
   return TSD_OK;
 }
 
