@@ -89,46 +89,56 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    wl = DoubleLaserWorkload(args.workload, invert=capi.invert3x3)
-    cfg = wl.cfg
     if world == 1:
+        wl = DoubleLaserWorkload(args.workload, invert=capi.invert3x3)
+        cfg = wl.cfg
         grid = capi.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid, device=local)
         band = None
     else:
-        # the same workload, the grid sharded in `world` bands of partition rows (strong scaling): every rank
-        # integrates the replicated scan into its own rows; boundary rows travel over NCCL
+        # N robots of the same kind on one grid sharded in N bands of partition rows, one band per GPU (weak
+        # scaling; BASELINE.json configs[4]).  Every rank sees every scan, integrates those that can reach its band
+        # (tsdg_scan_box) into its own rows -- no communication -- and synchronises the boundary rows with its
+        # neighbours once per step (P2P over NCCL), as a SLAM cycle that ray-casts after pushing would.
         from ohm_tsd_slam_b200.sharded import DistBand
-        band = DistBand(cfg.cell_size, cfg.layout_grid, local)
+        from ohm_tsd_slam_b200.workload import MultiRobotWorkload
+        wl = MultiRobotWorkload(world, args.workload, invert=capi.invert3x3)
+        cfg = wl.cfg
+        band = DistBand(wl.cell_size, wl.layout_grid, local)
         grid = band.grid
     grid.set_max_truncation(cfg.max_truncation)
 
-    def push_host(sc):
-        band.push(sc) if band else grid.push(sc)
-
-    def push_resident():
-        band.push_staged() if band else grid.push_staged()
-
     for sc in wl.map_scans:
-        push_host(sc)
+        band.push(sc) if band else grid.push(sc)
     grid.fill(1.0, 1.0, only_uninitialized=True)
     if band:
-        band.exchange()
+        band.sync_halos(full=True)
     grid.set_timing(True)
     launches0 = capi.kernel_launches()
     stream = torch.cuda.ExternalStream(grid.stream_ptr, device=torch.device("cuda", local))
     n_steps = len(wl.step_scans)
 
-    # ---------------- device-resident leg: scans staged in HBM, one staged handle per laser and step
-    # (staging buffers are per grid handle: re-stage outside the timed region is not possible for 2 lasers x n
-    #  steps, so the two lasers' scans of step i are staged right before their pushes from PINNED host memory by
-    #  tsdg_stage_scan; to keep H2D out of `value`, value times push_staged only, via CUDA events per push).
+    def ev_pair():
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---------------- device-resident leg: `value` times the pushes (and the halo synchronisation of a sharded grid)
+    # with CUDA events on the library's stream; the H2D staging of each scan (tsdg_stage_scan, from pinned host
+    # memory) sits between the event pairs, outside them.
     def resident_step(i, acc):
         for sc in wl.step_scans[i % n_steps]:
-            grid.stage_scan(sc)      # H2D (not timed in `value`)
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
+            if band:
+                if not band.stage_and_note(sc):
+                    continue
+            else:
+                grid.stage_scan(sc)
+            e0, e1 = ev_pair()
             e0.record(stream)
-            push_resident()
+            grid.push_staged()
+            e1.record(stream)
+            acc.append((e0, e1))
+        if band:
+            e0, e1 = ev_pair()
+            e0.record(stream)
+            band.sync_halos()
             e1.record(stream)
             acc.append((e0, e1))
 
@@ -139,39 +149,55 @@ def run_cuda(args):
     sampler = ClockSampler(local)
     sampler.start()
     evs = []
-    upd_total = 0
     kms = []
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         resident_step(i, evs)
-        # per-push statistics are read back outside the event brackets
-        st = grid.last_push_stats()
-        km = grid.last_push_kernel_ms()
-        upd_total += 2 * st["cell_updates"]  # both lasers of a step see the same map: counted from the second, doubled below exactly
-        kms.append(km)
+        if i % 8 == 0:  # (synchronises: sampled, not every step) kernel times and update count of the SAME push
+            kms.append((grid.last_push_kernel_ms(), grid.last_push_stats()["cell_updates"]))
     grid.sync()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
 
-    # exact update count per step: measure each laser's push once
-    upd_per_step = 0
-    for sc in wl.step_scans[0]:
-        push_host(sc)
-        upd_per_step += grid.last_push_stats()["cell_updates"]
-    upd_avg_per_push = upd_per_step / 2.0
-
-    # ---------------- end-to-end leg: host buffers through tsdg_push (blocking; H2D + stats D2H inside)
-    for i in range(args.warmup):
+    # exact update count of one step on this rank, and of its heaviest push (the roofline launch)
+    def host_step(i, count=None):
         for sc in wl.step_scans[i % n_steps]:
-            push_host(sc)
+            if band:
+                mine = band.note_scan(grid.scan_box(sc))
+                band.flags_dirty = True
+                if not mine:
+                    continue
+            grid.push(sc)  # blocking: H2D of the scan, kernels, synchronise
+            if count is not None:
+                count.append(grid.last_push_stats()["cell_updates"])  # D2H of the statistics
+        if band:
+            band.sync_halos()
+            grid.sync()
+
+    upd_steps = []
+    for i in range(n_steps):
+        c = []
+        host_step(i, c)
+        upd_steps.append(c)
+    pushes_per_step = len(upd_steps[0])
+    upd_per_step = float(np.mean([sum(c) for c in upd_steps]))
+    upd_total_dev = sum(sum(upd_steps[i % n_steps]) for i in range(args.steps))
+    # roofline samples: full-size pushes only (on a sharded grid a rank also sees the tail of its neighbour's scans)
+    big = [(k, u) for k, u in kms if u > 0.25 * max(u2 for _, u2 in kms)]
+    upd_avg_per_push = float(np.mean([u for _, u in big]))
+    kms = [k for k, _ in big]
+
+    # ---------------- end-to-end leg: host buffers through tsdg_push (blocking; H2D + statistics D2H inside)
+    for i in range(args.warmup):
+        host_step(i)
     barrier()
     e2e_updates = 0
     t0 = time.perf_counter()
     for i in range(args.steps):
-        for sc in wl.step_scans[i % n_steps]:
-            push_host(sc)
-            e2e_updates += grid.last_push_stats()["cell_updates"]
+        c = []
+        host_step(i, c)
+        e2e_updates += sum(c)
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag.set()
@@ -209,15 +235,16 @@ def run_cuda(args):
 
     # max over ranks of the timed durations, sum of the work
     dev_ms_t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    work_t = torch.tensor([float(upd_per_step * args.steps), float(e2e_updates)], dtype=torch.float64, device="cuda")
+    work_t = torch.tensor([float(upd_total_dev), float(e2e_updates), upd_per_step], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(dev_ms_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(work_t, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_ms_max = dev_ms_t.tolist()
-    work_dev, work_e2e = work_t.tolist()
+    work_dev, work_e2e, upd_per_step_all = work_t.tolist()
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic, traffic_src = profiled_traffic("k_update")
         upd_ms = float(np.mean([k["update"] for k in kms]))
         achieved = ALG_BYTES_PER_UPDATE * upd_avg_per_push / (upd_ms * 1e-3) / 1e9
         value = work_dev / (dev_ms_max * 1e-3) / 1e9
@@ -225,23 +252,24 @@ def run_cuda(args):
         n = sc0.n
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "cuda",
-            "config": dict(wl.describe(), parallelism=(f"grid sharded in {world} bands of partition rows, scan replicated, boundary rows over NCCL"
-                                        if world > 1 else "single GPU"),
-                           cell_updates_per_step=upd_per_step),
+            "config": dict(wl.describe(), parallelism=(f"one band of partition rows per GPU ({world} bands), scans replicated, pushes without "
+                                                       f"communication, boundary rows to the neighbours once per step (NCCL P2P)"
+                                                       if world > 1 else "single GPU"),
+                           cell_updates_per_step=upd_per_step_all, pushes_per_step_rank0=pushes_per_step),
             "hbm_gbs_algorithmic": value * ALG_BYTES_PER_UPDATE,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * (n * 8 + n + 8 * 25), "d2h_bytes_per_step": 2 * (16 * 4 + 4 * 8),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pushes_per_step * (n * 8 + n + 8 * 25), "d2h_bytes_per_step": pushes_per_step * (16 * 4 + 4 * 8),
                     "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_update (TsdGrid::push cell update, K2+K3)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel_ms": upd_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE * upd_avg_per_push},
             "push_kernel_ms": {k: float(np.mean([x[k] for x in kms])) for k in kms[0]},
             "raycast_icp": {"raycast_ms": rc_ms, "icp_ms": icp_ms, "raycast_hits": int(cnt),
                             "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
-                            "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / 2) if icp_ms else None,
+                            "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(pushes_per_step, 1)) if icp_ms else None,
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall,
@@ -251,6 +279,21 @@ def run_cuda(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def profiled_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed
+    `ncu --set full` summary (profiles/rNN_metrics.json, written by profiles/summarize.py); (None, None) if absent."""
+    import glob
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_metrics.json")))
+    for f in reversed(files):
+        try:
+            m = json.load(open(f)).get(kernel)
+            if m:
+                return m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"], os.path.join("profiles", os.path.basename(f))
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, None
 
 
 def cpu_baseline(workload: str, steps: int, warmup: int, threads):
@@ -333,7 +376,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="C2")

@@ -99,12 +99,26 @@ int tsdg_create(double cell_size, int layout_partition, int layout_grid, int dev
  * one halo partition row above the band is kept for the replicated borders. */
 int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, int device, int part_row_begin,
                      int part_row_end, tsd_grid_t** out);
-/* On a band, tsdg_push / tsdg_push_async / tsdg_push_staged stop after the cell update.  The caller then
- * exchanges boundary partition rows with the neighbouring bands (tsdg_band_row: which 0/1 = my lowest /
- * highest row to send, 2/3 = the halo slots below / above to receive into; count doubles each of tsd and
- * weight; NULL when there is no such neighbour), calls tsdg_band_push_finish (replicated borders, K4) and
- * exchanges the rows once more so that the halos carry the refreshed borders (ray casting reads them). */
+/* On a band, a push integrates the scan into the band's own rows and maintains every border strip that does
+ * not depend on another band.  Pushes need no communication.  Before anything READS the map across a band
+ * boundary (ray casting, interpolation, download), the caller brings the halos up to date:
+ *   1. exchange boundary partition rows with the neighbouring bands (tsdg_band_row: which 0/1 = my lowest /
+ *      highest row to send, 2/3 = the halo slots below / above to receive into; count doubles each of tsd and
+ *      weight; NULL when there is no such neighbour),
+ *   2. tsdg_band_push_finish: the band's top row takes its top / corner border strips from the halo above
+ *      (TsdGrid::propagateBorders, TsdGrid.cpp:401-424, across the band boundary),
+ *   3. exchange the rows once more so that the halos carry the refreshed borders.
+ * Any number of pushes may precede one such synchronisation; the result equals the unsharded grid's. */
 int tsdg_band_push_finish(tsd_grid_t* grid);
+/* Allocation flags of ALL partitions of the grid (device memory, one byte each, 1 = allocated; row-major).  A band
+ * keeps the flags of its own rows and of the row on either side current; ray casting walks rays through other
+ * bands' rows too (the partition-skipping loop of RayCastPolar2D.cpp:223-235), so before a ray cast the caller
+ * merges the bands' flags with an element-wise MAX (flags only ever go 0 -> 1). */
+int tsdg_band_flags(tsd_grid_t* grid, uint8_t** flags, uint64_t* count);
+/* Partition box {px0, py0, px1, py1} (inclusive) a scan can touch: every partition outside fails the range cull
+ * of TsdGridComponent::isInRange (TsdGridComponent.cpp:50-58).  The classifier of a push looks at this box only;
+ * a sharded caller uses it to skip scans that cannot reach its band and to bound the halo columns to exchange. */
+int tsdg_scan_box(const tsd_grid_t* grid, const tsd_scan_t* scan, int32_t box[4]);
 int tsdg_band_row(tsd_grid_t* grid, int which, double** tsd, double** weight, uint64_t* count);
 int tsdg_destroy(tsd_grid_t* grid);
 

@@ -20,9 +20,11 @@ _sp = C.POINTER(ScanStruct)
 _hp = C.POINTER(Hypothesis)
 _vpp = C.POINTER(C.c_void_p)
 
+TILE_STRIDE = 1104  # doubles per partition and array (csrc/common.cuh TSD_TILE_STRIDE)
+
 EXPORTS = [
     "tsd_last_error", "tsd_device_count", "tsd_kernel_launches", "tsd_invert3x3",
-    "tsdg_create", "tsdg_create_band", "tsdg_band_push_finish", "tsdg_band_row", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
+    "tsdg_create", "tsdg_create_band", "tsdg_band_push_finish", "tsdg_band_flags", "tsdg_scan_box", "tsdg_band_row", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
     "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged",
     "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
@@ -55,6 +57,8 @@ def lib():
     L.tsdg_create_band.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vpp]
     L.tsdg_destroy.argtypes = [C.c_void_p]
     L.tsdg_band_push_finish.argtypes = [C.c_void_p]
+    L.tsdg_scan_box.argtypes = [C.c_void_p, _sp, C.POINTER(C.c_int32)]
+    L.tsdg_band_flags.argtypes = [C.c_void_p, _vpp, C.POINTER(C.c_uint64)]
     L.tsdg_band_row.argtypes = [C.c_void_p, C.c_int, _vpp, _vpp, C.POINTER(C.c_uint64)]
     L.tsdg_raycast_band_keys.argtypes = [C.c_void_p, _sp, _dp, _vpp, _vpp]
     L.tsdg_set_max_truncation.argtypes = [C.c_void_p, C.c_double]
@@ -266,6 +270,18 @@ class Grid:
 
     def band_push_finish(self):
         check(lib().tsdg_band_push_finish(self.h))
+
+    def band_flags(self):
+        """(device pointer, count) of the allocation flags of all partitions."""
+        f, n = C.c_void_p(), C.c_uint64()
+        check(lib().tsdg_band_flags(self.h, C.byref(f), C.byref(n)))
+        return int(f.value or 0), int(n.value)
+
+    def scan_box(self, scan: Scan):
+        """Inclusive partition box (px0, py0, px1, py1) the scan can touch (tsdg_scan_box)."""
+        box = (C.c_int32 * 4)()
+        check(lib().tsdg_scan_box(self.h, scan.byref(), box))
+        return tuple(int(v) for v in box)
 
     def band_row(self, which: int):
         """(tsd_ptr, weight_ptr, count_doubles) of a boundary / halo partition row; (0, 0, 0) if absent."""

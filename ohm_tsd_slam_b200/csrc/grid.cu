@@ -17,6 +17,7 @@
 //   k_borders   warp per touched partition: TsdGrid::propagateBorders restricted to what changed (K4)
 #include <stdarg.h>
 #include <string.h>
+#include <cmath>
 
 #include <mutex>
 #include <vector>
@@ -97,6 +98,8 @@ struct PushParams
   double max_trunc;
   double inv_max_trunc;  // 1.0 / maxTruncation (TsdGridPartition.cpp:94)
   int cells_x, cells_y, parts_x, parts_y, n_parts;
+  int parts_shift;  // parts_x == 1 << parts_shift
+  int cl_px0, cl_py0, cl_w, cl_h;  // partitions k_classify looks at: the scan's range box (scan_partition_box)
   int row_begin, row_end;
   int alloc_begin, alloc_end;
   int band;
@@ -123,8 +126,10 @@ struct PushParams
 __device__ __forceinline__ void fill_tables(const PushParams& pp, double* coltab, double* rowtab, int i)
 {
   const double* Pi = pp.scan.Pi;
-  if(i < pp.cells_x)
+  const int i0 = i;
+  if(i0 < pp.cl_w * TSD_TILE)
   {
+    const int i = pp.cl_px0 * TSD_TILE + i0;
     const double X = ((double)i + 0.5) * pp.cell_size;
     double a = 0.0;
     a += Pi[0] * X;
@@ -135,8 +140,9 @@ __device__ __forceinline__ void fill_tables(const PushParams& pp, double* coltab
     coltab[pp.cells_x + i] = b;
     coltab[2 * pp.cells_x + i] = d * d;
   }
-  if(i < pp.cells_y)
+  if(i0 < pp.cl_h * TSD_TILE)
   {
+    const int i = pp.cl_py0 * TSD_TILE + i0;
     const double Y = ((double)i + 0.5) * pp.cell_size;
     const double d = Y - pp.scan.P[5];
     rowtab[i] = Pi[1] * Y;
@@ -178,16 +184,17 @@ __device__ __forceinline__ int back_project_edge(const ScanDev& s, const double2
 __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, double* coltab, double* rowtab)
 {
   const int gtid = blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
-  fill_tables(pp, coltab, rowtab, gtid);
+  fill_tables(pp, coltab, rowtab, gtid);  // (columns / rows of the range box only)
   const int lane = threadIdx.x & 31;
   const int sub = lane & 3;
   const int gshift = lane & ~3;
   const unsigned gmask = 0xfu << gshift;
-  const int p = gtid >> 2;
+  const int q = gtid >> 2;  // index inside the range box; everything outside fails the range cull below anyway
   // no lane leaves before the warp-wide part below: `alive` carries the reference's early returns
-  bool alive = p < pp.n_parts;
+  bool alive = q < pp.cl_w * pp.cl_h;
   const ScanDev& s = pp.scan;
-  const int px = alive ? p % pp.parts_x : 0, py = alive ? p / pp.parts_x : 0;
+  const int px = alive ? pp.cl_px0 + q % pp.cl_w : 0, py = alive ? pp.cl_py0 + q / pp.cl_w : 0;
+  const int p = py * pp.parts_x + px;
   const unsigned int x0 = px * TSD_TILE, y0 = py * TSD_TILE;
   const double cs = pp.cell_size;
 
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
         w = ob_min(w, TSD_MAXWEIGHT);
         pp.initw[p] = w;
       }
-      atomicAdd(&pp.counters[6], 1u);
+      if(owned) atomicAdd(&pp.counters[6], 1u);  // statistics count a band's own partitions
     }
     return;
   }
@@ -322,68 +329,153 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
     if(!wasInit)
     {
       pp.flags[p] = 1;
-      atomicAdd(&pp.counters[4], 1u);
+      if(owned) atomicAdd(&pp.counters[4], 1u);
       if(owned) pp.newly[atomicAdd(&pp.counters[18], 1u)] = (uint32_t)p;
     }
-    atomicAdd(&pp.counters[7], 1u);
+    if(owned) atomicAdd(&pp.counters[7], 1u);
   }
 }
 
 #define UPDATE_THREADS 256
+#ifndef UPDATE_CTAS_PER_SM
+#define UPDATE_CTAS_PER_SM 3
+#endif
+#define BEAM_UNDECIDED (-3)
 
-// One cell of TsdGrid.cpp:250-274 + TsdGridPartition::addTsd (TsdGridPartition.h:170-212).
-// Returns true when the cell was rewritten.
-__device__ __forceinline__ bool update_cell(const PushParams& pp, const double* s_ranges, const uint8_t* s_mask,
-                                            const double2* s_dirs, double colA, double colB, double colD, double rowA,
-                                            double rowB, double rowD, double wTile, double& tsd, double& weight,
-                                            unsigned& slowCount)
+// Beam index of the slow path (the reference formula verbatim), kept out of line: ~0.1 % of the cells.
+__device__ __noinline__ int beam_index_slow(uint32_t* counter, double phi_min, double res_inv, double phi_lower, double phi_upper,
+                                            double x, double y)
 {
-  const ScanDev& s = pp.scan;
-  const double xs = (colA + rowA) + s.Pi[2] * 1.0;
-  const double ys = (colB + rowB) + s.Pi[5] * 1.0;
-  bool slow;
-  const int index = beam_index(s.bm, s_dirs, xs, ys, &slow);
-  slowCount += slow ? 1u : 0u;
-  if(index < 0) return false;
-  const int idx = min(index, s.n - 1);
-  if(!__ldg(s_mask + idx)) return false;
-  const double r = __ldg(s_ranges + idx);
-  const double dist = sqrt(colD + rowD);
-  double sd;
-  if(!isinf(r)) sd = r - dist;
-  else
-  {
-    if(!(dist < s.low_refl)) return false;
-    sd = pp.max_trunc;
-  }
-  if(!(sd >= -pp.max_trunc)) return false;
-  const double tsdNew = fmin(sd * pp.inv_max_trunc, 1.0);  // == obvious::min(a, 1.0): the constant is never NaN
-  if(isnan(tsd))
-  {
-    tsd = tsdNew;
-    weight += wTile;
-  }
-  else
-  {
-    tsd = (tsd * weight + tsdNew * wTile) / (weight + wTile);
-    weight = fmin(weight + wTile, TSD_MAXWEIGHT);
-  }
-  return true;
+  atomicAdd(counter, 1u);
+  const double phi = atan2(y, x);  // SensorPolar2D.cpp:126-134
+  if(phi <= phi_lower) return -2;
+  if(phi >= phi_upper) return -1;
+  return (int)round((phi - phi_min) * res_inv);
 }
 
-// increaseEmptiness for one cell (TsdGridPartition.cpp:140-157)
+// Branch-free front half of beam_index() (beam_index.cuh): candidate + double-precision confirmation.
+// Returns the beam, -2 / -1 for points clearly outside the field of view, BEAM_UNDECIDED otherwise.
+__device__ __forceinline__ int beam_index_fast(const BeamModel& bm, const double2* __restrict__ dirs, double x, double y)
+{
+  const float xf = (float)x, yf = (float)y;
+  const float ax = fabsf(xf), ay = fabsf(yf);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));  // mx == 0 -> NaN candidate -> undecided
+  const float t = mn * rc;
+  const float s = t * t;
+  float p = -0.011719098314642906f;
+  p = __fmaf_rn(p, s, 0.05264726281166077f);
+  p = __fmaf_rn(p, s, -0.11642640829086304f);
+  p = __fmaf_rn(p, s, 0.19354034960269928f);
+  p = __fmaf_rn(p, s, -0.33262282609939575f);
+  p = __fmaf_rn(p, s, 0.9999772310256958f);
+  float r = p * t;
+  r = (ay > ax) ? 1.57079632679489662f - r : r;
+  r = (xf < 0.0f) ? 3.14159265358979324f - r : r;
+  const float phif = copysignf(r, yf);
+  const int k = __float2int_rn((phif - bm.phi_min_f) * bm.res_inv_f);
+  const bool inside = (unsigned)k < (unsigned)bm.n;
+  const int kc = inside ? k : 0;
+  const double2 lo = __ldg(dirs + kc);
+  const double2 hi = __ldg(dirs + kc + 1);
+  const double m = TSD_BEAM_MARGIN * (fabs(x) + fabs(y));
+  const double s_lo = lo.x * y - lo.y * x;
+  const double s_hi = hi.x * y - hi.y * x;
+  const bool confirmed = inside && (s_lo > m) && (s_hi < -m);
+  // clearly outside the field of view: 1e-3 rad of slack on a candidate good to 2e-6 rad (lower bound first)
+  const bool below = !inside && (phif < bm.phi_lower_f - 1e-3f);
+  const bool above = !inside && (phif > bm.phi_upper_f + 1e-3f);
+  return confirmed ? k : (below ? -2 : (above ? -1 : BEAM_UNDECIDED));
+}
+
+// Two horizontally adjacent cells of TsdGrid.cpp:250-274 + TsdGridPartition::addTsd (TsdGridPartition.h:170-212),
+// written straight-line so that the two dependency chains interleave; only the division is skipped when neither
+// cell is rewritten.  Returns the number of cells rewritten (0..2).
+__device__ __forceinline__ unsigned update_pair(const PushParams& pp, const double2 cA, const double2 cB, const double2 cD,
+                                                double rA, double rB, double rD, double wTile, double2& tv, double2& wv)
+{
+  const ScanDev& s = pp.scan;
+  const double x0 = (cA.x + rA) + s.Pi[2] * 1.0;
+  const double y0 = (cB.x + rB) + s.Pi[5] * 1.0;
+  const double x1 = (cA.y + rA) + s.Pi[2] * 1.0;
+  const double y1 = (cB.y + rB) + s.Pi[5] * 1.0;
+  int i0, i1;
+  if(s.bm.fast_ok)
+  {
+    i0 = beam_index_fast(s.bm, pp.dirs, x0, y0);
+    i1 = beam_index_fast(s.bm, pp.dirs, x1, y1);
+  }
+  else i0 = i1 = BEAM_UNDECIDED;
+  if(i0 == BEAM_UNDECIDED) i0 = beam_index_slow(pp.counters + 5, s.bm.phi_min, s.bm.res_inv, s.bm.phi_lower, s.bm.phi_upper, x0, y0);
+  if(i1 == BEAM_UNDECIDED) i1 = beam_index_slow(pp.counters + 5, s.bm.phi_min, s.bm.res_inv, s.bm.phi_lower, s.bm.phi_upper, x1, y1);
+  const int last = s.n - 1;
+  const int j0 = min(max(i0, 0), last), j1 = min(max(i1, 0), last);
+  const unsigned m0 = __ldg(s.mask + j0), m1 = __ldg(s.mask + j1);
+  const double r0 = __ldg(s.ranges + j0), r1 = __ldg(s.ranges + j1);
+  const double dist0 = sqrt(cD.x + rD), dist1 = sqrt(cD.y + rD);
+  const bool inf0 = isinf(r0), inf1 = isinf(r1);
+  const double sd0 = inf0 ? pp.max_trunc : r0 - dist0;
+  const double sd1 = inf1 ? pp.max_trunc : r1 - dist1;
+  const bool ok0 = (i0 >= 0) && (m0 != 0) && (!inf0 || dist0 < s.low_refl) && (sd0 >= -pp.max_trunc);
+  const bool ok1 = (i1 >= 0) && (m1 != 0) && (!inf1 || dist1 < s.low_refl) && (sd1 >= -pp.max_trunc);
+  if(ok0 || ok1)
+  {
+    const double n0 = fmin(sd0 * pp.inv_max_trunc, 1.0);  // == obvious::min(a, 1.0): the constant is never NaN
+    const double n1 = fmin(sd1 * pp.inv_max_trunc, 1.0);
+    const double den0 = wv.x + wTile, den1 = wv.y + wTile;
+    const double q0 = (tv.x * wv.x + n0 * wTile) / den0;
+    const double q1 = (tv.y * wv.y + n1 * wTile) / den1;
+    const bool f0 = isnan(tv.x), f1 = isnan(tv.y);  // first measurement of the cell
+    if(ok0)
+    {
+      tv.x = f0 ? n0 : q0;
+      wv.x = f0 ? den0 : fmin(den0, TSD_MAXWEIGHT);
+    }
+    if(ok1)
+    {
+      tv.y = f1 ? n1 : q1;
+      wv.y = f1 ? den1 : fmin(den1, TSD_MAXWEIGHT);
+    }
+  }
+  return (ok0 ? 1u : 0u) + (ok1 ? 1u : 0u);
+}
+
+// increaseEmptiness for one cell (TsdGridPartition.cpp:140-157), branch-free
 __device__ __forceinline__ void empty_cell(double& tsd, double& weight)
 {
-  if(isnan(tsd))
+  const bool first = isnan(tsd);
+  const double w1 = weight + 1.0;
+  const double wn = fmin(w1, TSD_MAXWEIGHT);
+  const double q = (tsd * (wn - 1.0) + 1.0) / wn;
+  tsd = first ? 1.0 : q;
+  weight = first ? w1 : wn;
+}
+
+// The same for two cells.  Free space that has been seen for a while sits at the weight cap: the divisor is then
+// the power of two TSD_MAXWEIGHT = 32 and the IEEE quotient equals the product with 1/32 exactly (no subnormal
+// results are reachable: |tsd * 31 + 1| is 0 or >= 2^-53), which spares the division in the steady state.
+__device__ __forceinline__ void empty_pair(double2& tv, double2& wv)
+{
+  const bool f0 = isnan(tv.x), f1 = isnan(tv.y);
+  const double a0 = wv.x + 1.0, a1 = wv.y + 1.0;
+  const double w0 = fmin(a0, TSD_MAXWEIGHT), w1 = fmin(a1, TSD_MAXWEIGHT);
+  const double n0 = tv.x * (w0 - 1.0) + 1.0, n1 = tv.y * (w1 - 1.0) + 1.0;
+  double q0, q1;
+  if(w0 == TSD_MAXWEIGHT && w1 == TSD_MAXWEIGHT)
   {
-    weight += 1.0;
-    tsd = 1.0;
+    q0 = n0 * (1.0 / TSD_MAXWEIGHT);
+    q1 = n1 * (1.0 / TSD_MAXWEIGHT);
   }
   else
   {
-    weight = fmin(weight + 1, TSD_MAXWEIGHT);
-    tsd = (tsd * (weight - 1.0) + 1.0) / weight;
+    q0 = n0 / w0;
+    q1 = n1 / w1;
   }
+  tv.x = f0 ? 1.0 : q0;
+  tv.y = f1 ? 1.0 : q1;
+  wv.x = f0 ? a0 : w0;
+  wv.y = f1 ? a1 : w1;
 }
 
 // Border bookkeeping inside k_update (replaces most of the reference's propagateBorders pass, TsdGrid.cpp:372-427).
@@ -400,24 +492,43 @@ __device__ __forceinline__ bool strip_has_source(const PushParams& pp, int p, in
   return px < pp.parts_x - 1 && py < pp.parts_y - 1 && pp.flags[p + pp.parts_x + 1];
 }
 
-// thread (xp, y) holds the final values of cells (y, xp) and (y, xp + 1) of partition p
-__device__ __forceinline__ void mirror_to_neighbours(const PushParams& pp, int p, int px, int py, size_t base, int xp, int y,
+// Allocation flags of the -x / -y / -xy neighbours of partition e (0 where the neighbour is outside this grid /
+// band).  Loaded one item ahead of their use (mirror_to_neighbours), only by the threads that own a first-column
+// or first-row cell.
+struct MirrorFlags { unsigned x, y, xy; };
+__device__ __forceinline__ MirrorFlags load_mirror_flags(const PushParams& pp, uint32_t e, bool edge)
+{
+  MirrorFlags f = {0u, 0u, 0u};
+  if(edge && e != 0xffffffffu)
+  {
+    const int p = (int)(e & 0x7fffffffu);
+    const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
+    const bool hasX = px > 0, hasY = py > pp.row_begin;
+    if(hasX) f.x = pp.flags[p - 1];
+    if(hasY) f.y = pp.flags[p - pp.parts_x];
+    if(hasX && hasY) f.xy = pp.flags[p - pp.parts_x - 1];
+  }
+  return f;
+}
+
+// thread (xp, y) holds the final values of cells (y, xp) and (y, xp + 1) of the partition at `base`
+__device__ __forceinline__ void mirror_to_neighbours(const PushParams& pp, unsigned nb, size_t base, int xp, int y,
                                                      const double2& tv, const double2& wv)
 {
   const size_t rowStride = (size_t)pp.parts_x * TSD_TILE_STRIDE;
-  if(xp == 0 && px > 0 && pp.flags[p - 1])
+  if(xp == 0 && (nb & 1u))
   {
     // first column -> right border of the -x neighbour
     pp.tsd[base - TSD_TILE_STRIDE + TSD_BORDER_OFF + y] = tv.x;
     pp.weight[base - TSD_TILE_STRIDE + TSD_BORDER_OFF + y] = wv.x;
   }
-  if(y == 0 && py > pp.row_begin && pp.flags[p - pp.parts_x])
+  if(y == 0 && (nb & 2u))
   {
     // first row -> top border of the -y neighbour
     *reinterpret_cast<double2*>(pp.tsd + base - rowStride + TSD_BORDER_OFF + 32 + xp) = tv;
     *reinterpret_cast<double2*>(pp.weight + base - rowStride + TSD_BORDER_OFF + 32 + xp) = wv;
   }
-  if(y == 0 && xp == 0 && px > 0 && py > pp.row_begin && pp.flags[p - pp.parts_x - 1])
+  if(y == 0 && xp == 0 && (nb & 4u))
   {
     pp.tsd[base - rowStride - TSD_TILE_STRIDE + TSD_BORDER_OFF + 64] = tv.x;
     pp.weight[base - rowStride - TSD_TILE_STRIDE + TSD_BORDER_OFF + 64] = wv.x;
@@ -430,70 +541,86 @@ __device__ __forceinline__ void push_tail(const PushParams& pp);
 // K2 + K3.  Persistent CTAs with a two-stage cp.async pipeline over their partitions.
 // Thread t of 256 owns the cell pair x = 2*(t%16), 2*(t%16)+1 in rows t/16 and t/16 + 16: a warp reads two
 // adjacent 256-B rows (512 contiguous bytes) per 16-byte vector load.
-__global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
+template <int CTAS_PER_SM>
+__global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushParams pp)
 {
   // the scan (8.6 KB + 1 KB) and the beam-boundary table (17 KB) are read through L1 (read-only path): they
   // stay resident per SM for the whole launch, with no per-CTA staging pass
-  const ScanDev& s = pp.scan;
-  const double2* s_dirs = pp.dirs;
-  const double* s_ranges = s.ranges;
-  const uint8_t* s_mask = s.mask;
-
   const uint32_t nActive = pp.counters[0];
-  const uint32_t nEmptied = pp.counters[1];
-  const uint32_t nItems = nActive + nEmptied;
+  const uint32_t nItems = nActive + pp.counters[1];
   const int t = threadIdx.x;
   const int xp = (t & 15) * 2;
   const int yb = t >> 4;
-  unsigned long long updates = 0;
-  unsigned slowCount = 0;
+  const bool edge = (xp == 0) || (yb == 0);
+  unsigned updates = 0;
+  unsigned long long updatesWide = 0;
+
+  // list entry of item `it`: partition index, bit 31 = its cells existed before this push (so they are read)
+  auto entry = [&](uint32_t it) -> uint32_t
+  {
+    if(it >= nItems) return 0xffffffffu;
+    return (it < nActive) ? pp.active[it] : (pp.emptied[it - nActive] | 0x80000000u);
+  };
 
   // Two-stage pipeline over the CTA's partitions: the 16 KB of cell state of partition i+1 are copied into
   // shared memory with cp.async (LDGSTS, L1 bypass) while partition i is computed.  Every thread copies exactly
   // the four 16-byte pieces it will read itself, so the only synchronisation is its own cp.async.wait_group.
+  // The list entries themselves are fetched two items ahead, so no address waits on a load.
   __shared__ __align__(16) double2 s_cells[2][2][2 * UPDATE_THREADS];  // [stage][tsd|weight][row j * 256 + t]
-  auto stage_in = [&](uint32_t it, int stage)
+  auto stage_in = [&](uint32_t e, int stage)
   {
-    if(it < nItems)
+    if(e != 0xffffffffu && (e & 0x80000000u))
     {
-      const uint32_t e = (it < nActive) ? pp.active[it] : (pp.emptied[it - nActive] | 0x80000000u);
-      if(e & 0x80000000u)  // allocated before this push: its cells are read
-      {
-        const size_t nb = (size_t)((e & 0x7fffffffu) - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
+      const size_t nb = (size_t)((e & 0x7fffffffu) - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
 #pragma unroll
-        for(int j = 0; j < 2; j++)
-        {
-          const int ci = (yb + 16 * j) * TSD_TILE + xp;
-          const unsigned dT = (unsigned)__cvta_generic_to_shared(&s_cells[stage][0][j * UPDATE_THREADS + t]);
-          const unsigned dW = (unsigned)__cvta_generic_to_shared(&s_cells[stage][1][j * UPDATE_THREADS + t]);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dT), "l"(pp.tsd + nb + ci));
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dW), "l"(pp.weight + nb + ci));
-        }
+      for(int j = 0; j < 2; j++)
+      {
+        const int ci = (yb + 16 * j) * TSD_TILE + xp;
+        const unsigned dT = (unsigned)__cvta_generic_to_shared(&s_cells[stage][0][j * UPDATE_THREADS + t]);
+        const unsigned dW = (unsigned)__cvta_generic_to_shared(&s_cells[stage][1][j * UPDATE_THREADS + t]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dT), "l"(pp.tsd + nb + ci));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dW), "l"(pp.weight + nb + ci));
       }
     }
     asm volatile("cp.async.commit_group;" ::);
   };
 
-  stage_in(blockIdx.x, 0);
+  // Static striding over the item list (a ticket counter with one __syncthreads per item was measured slower:
+  // 55 us vs 48 us on C2).  The list entries are fetched two items ahead, the neighbour flags one item ahead.
+  const uint32_t G = gridDim.x;
+  uint32_t eCur = entry(blockIdx.x);
+  uint32_t eNext = entry(blockIdx.x + G);
+  MirrorFlags mfCur = load_mirror_flags(pp, eCur, edge);
+  stage_in(eCur, 0);
   int stage = 0;
-  for(uint32_t item = blockIdx.x; item < nItems; item += gridDim.x, stage ^= 1)
+  for(uint32_t item = blockIdx.x; item < nItems; item += G, stage ^= 1)
   {
-    stage_in(item + gridDim.x, stage ^ 1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    const uint32_t eNext2 = entry(item + 2 * G);
+    const MirrorFlags mfNext = load_mirror_flags(pp, eNext, edge);
+    stage_in(eNext, stage ^ 1);
+    const uint32_t p = eCur & 0x7fffffffu;
+    const bool wasInit = (eCur & 0x80000000u) != 0;
+    const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
+    const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
+    double* T = pp.tsd + base;
+    double* W = pp.weight + base;
+    const unsigned nb = (mfCur.x ? 1u : 0u) | (mfCur.y ? 2u : 0u) | (mfCur.xy ? 4u : 0u);
     if(item < nActive)
     {
-      const uint32_t e = pp.active[item];
-      const uint32_t p = e & 0x7fffffffu;
-      const bool wasInit = (e & 0x80000000u) != 0;
       const double wTile = pp.active_w[item];
-      const int px = p % pp.parts_x, py = p / pp.parts_x;
-      const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
-      double* T = pp.tsd + base;
-      double* W = pp.weight + base;
       const int gx = px * TSD_TILE + xp;
+      const int gy = py * TSD_TILE + yb;
       const double2 cA = *reinterpret_cast<const double2*>(pp.coltab + gx);
       const double2 cB = *reinterpret_cast<const double2*>(pp.coltab + pp.cells_x + gx);
       const double2 cD = *reinterpret_cast<const double2*>(pp.coltab + 2 * pp.cells_x + gx);
+      double rA[2], rB[2], rD[2];
+#pragma unroll
+      for(int j = 0; j < 2; j++)
+      {
+        rA[j] = pp.rowtab[gy + 16 * j];
+        rB[j] = pp.rowtab[pp.cells_y + gy + 16 * j];
+        rD[j] = pp.rowtab[2 * pp.cells_y + gy + 16 * j];
+      }
       double initT = 0.0, initW = 0.0;
       if(!wasInit)
       {
@@ -501,14 +628,11 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
         initW = pp.initw[p];
         initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
       }
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
 #pragma unroll
       for(int j = 0; j < 2; j++)
       {
         const int y = yb + 16 * j;
-        const int gy = py * TSD_TILE + y;
-        const double rA = pp.rowtab[gy];
-        const double rB = pp.rowtab[pp.cells_y + gy];
-        const double rD = pp.rowtab[2 * pp.cells_y + gy];
         const int ci = y * TSD_TILE + xp;
         double2 tv, wv;
         if(wasInit)
@@ -521,15 +645,14 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
           tv = make_double2(initT, initT);
           wv = make_double2(initW, initW);
         }
-        const bool u0 = update_cell(pp, s_ranges, s_mask, s_dirs, cA.x, cB.x, cD.x, rA, rB, rD, wTile, tv.x, wv.x, slowCount);
-        const bool u1 = update_cell(pp, s_ranges, s_mask, s_dirs, cA.y, cB.y, cD.y, rA, rB, rD, wTile, tv.y, wv.y, slowCount);
-        updates += (u0 ? 1 : 0) + (u1 ? 1 : 0);
-        if(!wasInit || u0 || u1)
+        const unsigned u = update_pair(pp, cA, cB, cD, rA[j], rB[j], rD[j], wTile, tv, wv);
+        updates += u;
+        if(!wasInit || u)
         {
           *reinterpret_cast<double2*>(T + ci) = tv;
           *reinterpret_cast<double2*>(W + ci) = wv;
         }
-        if(y == 0 || xp == 0) mirror_to_neighbours(pp, (int)p, px, py, base, xp, y, tv, wv);
+        if(nb) mirror_to_neighbours(pp, nb, base, xp, y, tv, wv);
       }
       if(!wasInit && t < 65 && !strip_has_source(pp, (int)p, px, py, t))
       {
@@ -540,11 +663,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
     else
     {
       // K3: increaseEmptiness on an initialised partition, all 33x33 cells
-      const uint32_t p = pp.emptied[item - nActive];
-      const int px = p % pp.parts_x, py = p / pp.parts_x;
-      const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
-      double* T = pp.tsd + base;
-      double* W = pp.weight + base;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
 #pragma unroll
       for(int j = 0; j < 2; j++)
       {
@@ -552,11 +671,10 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
         const int ci = y * TSD_TILE + xp;
         double2 tv = s_cells[stage][0][j * UPDATE_THREADS + t];
         double2 wv = s_cells[stage][1][j * UPDATE_THREADS + t];
-        empty_cell(tv.x, wv.x);
-        empty_cell(tv.y, wv.y);
+        empty_pair(tv, wv);
         *reinterpret_cast<double2*>(T + ci) = tv;
         *reinterpret_cast<double2*>(W + ci) = wv;
-        if(y == 0 || xp == 0) mirror_to_neighbours(pp, (int)p, px, py, base, xp, y, tv, wv);
+        if(nb) mirror_to_neighbours(pp, nb, base, xp, y, tv, wv);
       }
       if(t < 65 && !strip_has_source(pp, (int)p, px, py, t))
       {
@@ -565,29 +683,25 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 4) k_update(PushParams pp)
         T[TSD_BORDER_OFF + t] = tv;
         W[TSD_BORDER_OFF + t] = wv;
       }
-      if(t == 0) updates += 33 * 33;
+      if(t == 0) updatesWide += 33 * 33;
     }
+    eCur = eNext;
+    eNext = eNext2;
+    mfCur = mfNext;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 
   // one atomic per CTA
   __shared__ unsigned long long s_upd[UPDATE_THREADS / 32];
-  __shared__ unsigned s_slow[UPDATE_THREADS / 32];
 #pragma unroll
-  for(int o = 16; o > 0; o >>= 1)
-  {
-    updates += __shfl_xor_sync(0xffffffffu, updates, o);
-    slowCount += __shfl_xor_sync(0xffffffffu, slowCount, o);
-  }
-  if((t & 31) == 0) { s_upd[t >> 5] = updates; s_slow[t >> 5] = slowCount; }
+  for(int o = 16; o > 0; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
+  if((t & 31) == 0) s_upd[t >> 5] = (unsigned long long)updates + updatesWide;
   __syncthreads();
   if(t == 0)
   {
     unsigned long long u = 0;
-    unsigned sl = 0;
-    for(int i = 0; i < UPDATE_THREADS / 32; i++) { u += s_upd[i]; sl += s_slow[i]; }
+    for(int i = 0; i < UPDATE_THREADS / 32; i++) u += s_upd[i];
     if(u) atomicAdd(&pp.stats64[0], u);
-    if(sl) atomicAdd(&pp.counters[5], sl);
   }
   if(pp.fused_tail)
   {
@@ -711,23 +825,28 @@ __device__ __forceinline__ void push_tail(const PushParams& pp)
   pp.stats64[0] = 0;
 }
 
-// K4 as a kernel of its own: sharded grids (after the halo exchange) and "refresh everything" requests.
-__global__ void __launch_bounds__(256) k_borders(PushParams pp, int all)
+// K4 as a kernel of its own.  mode 0: end of a push that was asked to refresh every border (after a fill / upload /
+// free-footprint), with the push tail; mode 1: refresh everything, no push involved; mode 2: sharded grid, after
+// the halo exchange: the band's top row takes its top / corner strips from the halo row above (the partitions
+// there belong to another GPU and may have changed).
+__global__ void __launch_bounds__(256) k_borders(PushParams pp, int mode)
 {
+  const int all = (mode == 1);
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const bool refreshAll = all || pp.counters[3];
+  const bool refreshAll = (mode != 2) && (all || pp.counters[3]);
   if(refreshAll)
   {
     for(int p = pp.row_begin * pp.parts_x + warp; p < pp.row_end * pp.parts_x; p += nwarps)
       if(pp.flags[p]) refresh_borders_of(pp, p % pp.parts_x, p / pp.parts_x, lane);
   }
-  if(!refreshAll && pp.band && pp.row_end < pp.parts_y)
+  if(mode == 2)
   {
-    // the partitions above the band's top row belong to another GPU and may have changed: refresh the row
-    for(int px = warp; px < pp.parts_x; px += nwarps)
-      if(pp.flags[(pp.row_end - 1) * pp.parts_x + px]) refresh_borders_of(pp, px, pp.row_end - 1, lane);
+    if(pp.band && pp.row_end < pp.parts_y)
+      for(int px = warp; px < pp.parts_x; px += nwarps)
+        if(pp.flags[(pp.row_end - 1) * pp.parts_x + px]) refresh_borders_of(pp, px, pp.row_end - 1, lane);
+    return;
   }
   if(!refreshAll) pull_pass(pp, warp, nwarps, lane);
   __syncthreads();
@@ -837,6 +956,8 @@ static PushParams make_params(const tsd_grid* g)
   pp.cells_x = g->cells_x;
   pp.cells_y = g->cells_y;
   pp.parts_x = g->parts_x;
+  pp.parts_shift = 0;
+  while((1 << pp.parts_shift) < g->parts_x) pp.parts_shift++;
   pp.parts_y = g->parts_y;
   pp.n_parts = g->n_parts;
   pp.row_begin = g->row_begin;
@@ -1189,6 +1310,29 @@ int tsdg_free_footprint(tsd_grid_t* g, double cx, double cy, double width, doubl
 
 static int push_finish(tsd_grid* g, const PushParams& pp);
 
+// Partitions a scan taken at (tx, ty) can touch: everything else fails the range cull of isInRange
+// (TsdGridComponent.cpp:50-58: centroid distance - circumradius - maxTruncation > maxRange).  One partition of
+// slack on every side covers the half-cell offsets and the rounding of the cull itself.  box = {px0, py0, px1, py1},
+// inclusive, clipped to the grid; a non-finite pose or range selects the whole grid.
+static void scan_partition_box(const tsd_grid* g, double tx, double ty, double max_range, int box[4])
+{
+  box[0] = 0; box[1] = 0; box[2] = g->parts_x - 1; box[3] = g->parts_y - 1;
+  const double part = TSD_TILE * g->cell_size;
+  const double reach = max_range + g->max_truncation + part;  // circumradius < one partition edge
+  if(!(std::isfinite(tx) && std::isfinite(ty) && std::isfinite(reach)) || !(reach >= 0.0)) return;
+  const double lo[2] = {std::floor((tx - reach) / part) - 1.0, std::floor((ty - reach) / part) - 1.0};
+  const double hi[2] = {std::floor((tx + reach) / part) + 1.0, std::floor((ty + reach) / part) + 1.0};
+  const int n[2] = {g->parts_x, g->parts_y};
+  for(int a = 0; a < 2; a++)
+  {
+    // a box entirely outside the grid degenerates to one row / column of partitions, all of which are culled
+    const double l = lo[a] < 0.0 ? 0.0 : (lo[a] > n[a] - 1 ? n[a] - 1 : lo[a]);
+    const double h = hi[a] < 0.0 ? 0.0 : (hi[a] > n[a] - 1 ? n[a] - 1 : hi[a]);
+    box[a] = (int)l;
+    box[2 + a] = (int)h;
+  }
+}
+
 int tsdg_stage_scan(tsd_grid_t* g, const tsd_scan_t* scan)
 {
   if(!g) return TSD_E_INVALID;
@@ -1210,32 +1354,44 @@ int tsdg_push_staged(tsd_grid_t* g)
   // counters [0] active [1] emptied are per push; [2] pending and [3] refresh-all persist until consumed below
   // (pending [2] and refresh-all [3] were zeroed by the previous push's tail; [0..1], [4..7] and the 64-bit
   //  statistics are zeroed by k_tables' first thread)
-  if(g->band && g->band_push_open) { set_error("the previous sharded push was not finished (tsdg_band_push_finish)"); return TSD_E_INVALID; }
-  const int nmax = g->cells_x > g->cells_y ? g->cells_x : g->cells_y;
-  const int nthreads = (4 * g->n_parts > nmax) ? 4 * g->n_parts : nmax;
+  int box[4];
+  scan_partition_box(g, pp.scan.P[2], pp.scan.P[5], pp.scan.max_range, box);
+  if(g->band)
+  {
+    // a band keeps allocation flags / emptiness weights of its own rows and of the two rows next to them
+    if(box[1] < g->row_begin - 1) box[1] = g->row_begin - 1;
+    if(box[3] > g->row_end) box[3] = g->row_end;
+    if(box[1] < 0) box[1] = 0;
+    if(box[3] > g->parts_y - 1) box[3] = g->parts_y - 1;
+    if(box[3] < box[1]) return TSD_OK;  // the scan cannot reach this band
+  }
+  pp.cl_px0 = box[0];
+  pp.cl_py0 = box[1];
+  pp.cl_w = box[2] - box[0] + 1;
+  pp.cl_h = box[3] - box[1] + 1;
+  const int nmax = TSD_TILE * (pp.cl_w > pp.cl_h ? pp.cl_w : pp.cl_h);
+  const int nthreads = (4 * pp.cl_w * pp.cl_h > nmax) ? 4 * pp.cl_w * pp.cl_h : nmax;
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[0], g->stream));
   k_classify<<<(nthreads + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[1], g->stream));
   const size_t smem = 0;
   (void)scan;
-  int ctas = g->sm_count * 4;
+  static const int ctasPerSm = []{ const char* e = getenv("TSD_UPDATE_CTAS"); const int v = e ? atoi(e) : UPDATE_CTAS_PER_SM; return (v == 3 || v == 4) ? v : UPDATE_CTAS_PER_SM; }();
+  int ctas = g->sm_count * ctasPerSm;
   if(ctas > g->n_owned) ctas = g->n_owned;
-  // unsharded grid, nothing asked for a full border refresh: K4's remainder runs in k_update's last CTA
-  pp.fused_tail = (!g->band && !g->refresh_all_pending) ? 1 : 0;
-  k_update<<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+  // nothing asked for a full border refresh: K4's remainder runs in k_update's last CTA.  (Sharded grids too: the
+  // strips that depend on the halo row above the band are refreshed after the exchange, tsdg_band_push_finish.)
+  pp.fused_tail = g->refresh_all_pending ? 0 : 1;
+  if(g->band) g->band_push_open = true;
+  if(ctasPerSm == 3) k_update<3><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+  else k_update<4><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[2], g->stream));
   if(pp.fused_tail)
   {
     if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[3], g->stream));
     g->pushed_once = true;
-    return TSD_OK;
-  }
-  if(g->band)
-  {
-    // sharded grid: the borders need the neighbour band's fresh first row -> tsdg_band_push_finish()
-    g->band_push_open = true;
     return TSD_OK;
   }
   return push_finish(g, pp);
@@ -1287,13 +1443,33 @@ int tsdg_stream_order(tsd_grid_t* g, void* other, int direction)
 
 int tsdg_band_push_finish(tsd_grid_t* g)
 {
-  if(!g || !g->band || !g->band_push_open) { set_error("no sharded push in flight"); return TSD_E_INVALID; }
+  if(!g || !g->band) { set_error("not a sharded grid"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));
   PushParams pp = make_params(g);
-  pp.scan = g->staged;
-  pp.dirs = g->d_dirs;
   g->band_push_open = false;
-  return push_finish(g, pp);
+  if(g->row_end < g->parts_y)
+  {
+    k_borders<<<g->sm_count, 256, 0, g->stream>>>(pp, 2);
+    TSD_LAUNCHED();
+  }
+  return TSD_OK;
+}
+
+int tsdg_band_flags(tsd_grid_t* g, uint8_t** flags, uint64_t* count)
+{
+  if(!g || !flags || !count) return TSD_E_INVALID;
+  *flags = g->d_flags;
+  *count = (uint64_t)g->n_parts;
+  return TSD_OK;
+}
+
+int tsdg_scan_box(const tsd_grid_t* g, const tsd_scan_t* scan, int32_t box[4])
+{
+  if(!g || !scan || !box) return TSD_E_INVALID;
+  int b[4];
+  scan_partition_box(g, scan->pose[2], scan->pose[5], scan->max_range, b);
+  for(int i = 0; i < 4; i++) box[i] = b[i];
+  return TSD_OK;
 }
 
 // which: 0 = my lowest partition row (the band below wants it), 1 = my highest row (the band above wants it),

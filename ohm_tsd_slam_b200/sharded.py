@@ -4,10 +4,13 @@ Plumbing only: the kernels live in libtsdslam_b200 (tsdg_create_band & co.); thi
 between bands and merges per-beam first events, with torch.distributed (NCCL over NVLink, or gloo in the CPU
 tests of the merge logic) or, for several bands on ONE device, with plain device copies.
 
-  push      every band integrates the (replicated) scan into its own rows            -> tsdg_push_async
+  push      every band a scan can reach (tsdg_scan_box) integrates it into its own rows -> tsdg_push_async
+            no communication: any number of pushes, from any number of sensors
+  sync      before the map is READ across a band boundary (ray casting):
             boundary partition rows go to the neighbouring bands (halo)              -> exchange
-            replicated borders of the band's top row are refreshed from the halo     -> tsdg_band_push_finish
-            boundary rows once more, now with refreshed borders (ray casting reads them)
+            the band's top row takes its top/corner border strips from the halo      -> tsdg_band_push_finish
+            boundary rows once more, now with refreshed borders
+            (only the partition columns pushed to since the last sync are sent)
   raycast   every band marches all beams, evaluates only the steps whose sample it owns -> tsdg_raycast_band_keys
             keys: all-reduce MIN; payload of the winner: mask + all-reduce SUM
 """
@@ -42,6 +45,38 @@ def split_rows(parts_y: int, world: int):
         out.append((b, e))
         b = e
     return out
+
+
+def band_reached(box, row_begin: int, row_end: int) -> bool:
+    """Does a scan with partition box (px0, py0, px1, py1) reach the band [row_begin, row_end)?  The band keeps a
+    replica of the allocation state of the rows next to it (halo), so those count as reached too."""
+    return box[1] <= row_end and box[3] >= row_begin - 1
+
+
+def touched_boundaries(box, row_begin: int, row_end: int, rank: int, world: int):
+    """(lower, upper): does a scan with this partition box dirty the boundary below / above the band?  A boundary
+    between rows e-1 | e is dirty when the box contains either row; both neighbours evaluate the same test."""
+    lower = rank > 0 and box[1] <= row_begin and box[3] >= row_begin - 1
+    upper = rank + 1 < world and box[1] <= row_end and box[3] >= row_end - 1
+    return lower, upper
+
+
+class DirtyColumns:
+    """Partition columns of a band boundary that were pushed to since the last halo synchronisation.  Every rank
+    sees every scan, so both sides of a boundary compute the same range without talking to each other."""
+
+    def __init__(self):
+        self.lo, self.hi = None, None
+
+    def add(self, px0: int, px1: int):
+        self.lo = px0 if self.lo is None else min(self.lo, px0)
+        self.hi = px1 if self.hi is None else max(self.hi, px1)
+
+    def clear(self):
+        self.lo, self.hi = None, None
+
+    def __bool__(self):
+        return self.lo is not None
 
 
 def merge_first_events(keys: torch.Tensor, payload: torch.Tensor, allreduce_min, allreduce_sum):
@@ -111,23 +146,54 @@ class LocalBands:
                 device_tensor(dw, n, "<f8", self.device).copy_(device_tensor(sw, n, "<f8", self.device))
         torch.cuda.synchronize(self.device)
 
-    def push(self, scan: Scan):
-        for g in self.grids:
-            g.push_async(scan)
+    def push(self, scan: Scan, sync: bool = True):
+        box = self.grids[0].scan_box(scan)
+        self.pushed = [band_reached(box, b, e) for (b, e) in self.rows]
+        for g, mine in zip(self.grids, self.pushed):
+            if mine:
+                g.push_async(scan)
+        self.dirty = True
+        if sync:
+            self.sync_halos()
+
+    def sync_halos(self):
+        if not getattr(self, "dirty", False):
+            return
         self._exchange()
         for g in self.grids:
             g.band_push_finish()
         self._exchange()
+        self.dirty = False
+
+    def sync_flags(self):
+        """Element-wise MAX of the bands' allocation flags (what DistBand does with an all-reduce)."""
+        views = []
+        for g in self.grids:
+            g.sync()
+            ptr, n = g.band_flags()
+            views.append(device_tensor(ptr, n, "|u1", self.device))
+        merged = torch.stack(views).max(dim=0).values
+        for v in views:
+            v.copy_(merged)
+        torch.cuda.synchronize(self.device)
 
     def last_push_stats(self):
-        sts = [g.last_push_stats() for g in self.grids]
+        sts = [g.last_push_stats() for g, mine in zip(self.grids, self.pushed) if mine]
         out = dict(sts[0])
-        for k in ("cell_updates", "cell_visits", "fallback_cells"):
+        for k in ("cell_updates", "cell_visits", "fallback_cells", "active_tiles", "emptied_tiles", "newly_initialized"):
             out[k] = sum(s[k] for s in sts)
         return out
 
     def partition_states(self):
-        return self.grids[0].partition_states()  # replicated
+        """State and init weight of every partition, each taken from the band that owns it."""
+        out = None
+        for (b, e), g in zip(self.rows, self.grids):
+            st, iw = g.partition_states()
+            if out is None:
+                out = (st.copy(), iw.copy())
+            out[0][b * self.parts_x:e * self.parts_x] = st[b * self.parts_x:e * self.parts_x]
+            out[1][b * self.parts_x:e * self.parts_x] = iw[b * self.parts_x:e * self.parts_x]
+        return out
 
     def download_partition(self, p: int):
         py = p // self.parts_x
@@ -137,6 +203,8 @@ class LocalBands:
         return None
 
     def raycast_mask(self, scan: Scan, rays_world, coords=None, normals=None):
+        self.sync_halos()
+        self.sync_flags()
         n = scan.n
         ks, ps = [], []
         for g in self.grids:
@@ -184,6 +252,10 @@ class DistBand:
         parts_y = (1 << layout_grid) // 32
         self.rows = split_rows(parts_y, self.world)
         self.grid = capi.Grid(cell_size, 5, layout_grid, device=device, band=self.rows[self.rank])
+        self.parts_x = parts_y
+        self.dirty_lo, self.dirty_hi = DirtyColumns(), DirtyColumns()
+        self.flags_dirty = False
+        self._flags = None
         self._views = None
 
     def _row_views(self):
@@ -195,48 +267,98 @@ class DistBand:
             self._views = v
         return self._views
 
-    def exchange(self):
+    def note_scan(self, box) -> bool:
+        """Book-keeping for one scan that EVERY rank calls with the same box: which boundaries it dirties.
+        Returns whether this rank has to push it."""
+        b, e = self.rows[self.rank]
+        lower, upper = touched_boundaries(box, b, e, self.rank, self.world)
+        if lower:
+            self.dirty_lo.add(box[0], box[2])
+        if upper:
+            self.dirty_hi.add(box[0], box[2])
+        return band_reached(box, b, e)
+
+    def exchange(self, full: bool = False):
         """Boundary rows to the neighbouring bands, stream-ordered (no host synchronisation): the collective
-        stream waits for the library's stream, the library's stream waits for the collective."""
+        stream waits for the library's stream, the library's stream waits for the collective.  Only the dirty
+        partition columns of each boundary travel (all of them with full=True)."""
         dist = self.dist
         v = self._row_views()
         cur = torch.cuda.current_stream(self.device)
         self.grid.stream_order(cur.cuda_stream, 0)
         ops = []
-        if self.rank > 0:  # lowest row down, lower halo from below
+        stride = capi.TILE_STRIDE
+
+        def cols(d):
+            return (0, self.parts_x - 1) if full else (d.lo, d.hi)
+
+        if self.rank > 0 and (full or self.dirty_lo):  # lowest row down, lower halo from below
+            lo, hi = cols(self.dirty_lo)
+            sl = slice(lo * stride, (hi + 1) * stride)
             for k in (0, 1):
-                ops.append(dist.P2POp(dist.isend, v[0][k], self.rank - 1))
-                ops.append(dist.P2POp(dist.irecv, v[2][k], self.rank - 1))
-        if self.rank + 1 < self.world:
+                ops.append(dist.P2POp(dist.isend, v[0][k][sl], self.rank - 1))
+                ops.append(dist.P2POp(dist.irecv, v[2][k][sl], self.rank - 1))
+        if self.rank + 1 < self.world and (full or self.dirty_hi):
+            lo, hi = cols(self.dirty_hi)
+            sl = slice(lo * stride, (hi + 1) * stride)
             for k in (0, 1):
-                ops.append(dist.P2POp(dist.isend, v[1][k], self.rank + 1))
-                ops.append(dist.P2POp(dist.irecv, v[3][k], self.rank + 1))
+                ops.append(dist.P2POp(dist.isend, v[1][k][sl], self.rank + 1))
+                ops.append(dist.P2POp(dist.irecv, v[3][k][sl], self.rank + 1))
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()  # NCCL: orders the current stream after the transfer, does not block the host
         self.grid.stream_order(cur.cuda_stream, 1)
-        self.halo_dirty = False
+        return len(ops)
 
-    def _push_tail(self):
-        # phase 2 needs the upper neighbour's fresh first row; the refreshed borders reach the neighbours'
-        # halos lazily, before the next ray cast (nothing else reads a halo's border cells)
-        self.exchange()
+    def sync_halos(self, full: bool = False):
+        """Bring the halos up to date (see the module docstring).  Collective: every rank calls it."""
+        if not (full or self.dirty_lo or self.dirty_hi):
+            return 0
+        n = self.exchange(full)
         self.grid.band_push_finish()
-        self.halo_dirty = True
+        n += self.exchange(full)
+        self.dirty_lo.clear()
+        self.dirty_hi.clear()
+        return n
 
-    def push(self, scan: Scan):
-        self.grid.push_async(scan)
-        self._push_tail()
+    def sync_flags(self):
+        """Merge the bands' allocation flags (all-reduce MAX over the byte array) if a push happened since the last
+        merge.  Collective: every rank calls it (ray casting does)."""
+        if not self.flags_dirty:
+            return
+        if self._flags is None:
+            ptr, n = self.grid.band_flags()
+            self._flags = device_tensor(ptr, n, "|u1", self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self.grid.stream_order(cur.cuda_stream, 0)
+        self.dist.all_reduce(self._flags, op=self.dist.ReduceOp.MAX)
+        self.grid.stream_order(cur.cuda_stream, 1)
+        self.flags_dirty = False
+
+    def push(self, scan: Scan, sync: bool = False):
+        """Every rank calls this with the same scan; ranks the scan cannot reach skip it."""
+        self.flags_dirty = True
+        if self.note_scan(self.grid.scan_box(scan)):
+            self.grid.push_async(scan)
+        if sync:
+            self.sync_halos()
+
+    def stage_and_note(self, scan: Scan) -> bool:
+        """Staged variant: H2D of the scan if this rank has to push it; follow with push_staged()."""
+        self.flags_dirty = True
+        mine = self.note_scan(self.grid.scan_box(scan))
+        if mine:
+            self.grid.stage_scan(scan)
+        return mine
 
     def push_staged(self):
         self.grid.push_staged()
-        self._push_tail()
 
     def raycast_mask(self, scan: Scan, rays_world):
         dist = self.dist
         n = scan.n
-        if getattr(self, "halo_dirty", False):
-            self.exchange()
+        self.sync_halos()
+        self.sync_flags()
         kp, pp = self.grid.raycast_band_keys(scan, rays_world)
         keys = device_tensor(kp, n, "<i8", self.device)
         payload = device_tensor(pp, 4 * n, "<f8", self.device).view(n, 4)

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ohm_tsd_slam_b200.sharded import NO_EVENT, merge_best_hypothesis, merge_first_events, split_rows
+from ohm_tsd_slam_b200.sharded import (NO_EVENT, DirtyColumns, band_reached, merge_best_hypothesis, merge_first_events, split_rows,
+                                       touched_boundaries)
 
 
 def _free_port():
@@ -82,3 +83,33 @@ def test_split_rows():
     rows = split_rows(32, 5)
     assert rows[0][0] == 0 and rows[-1][1] == 32 and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
     assert max(e - b for b, e in rows) - min(e - b for b, e in rows) <= 1
+
+
+def test_boundary_bookkeeping_is_symmetric():
+    """Both sides of a band boundary must derive the same dirty partition columns from the (replicated) scans,
+    because the halo exchange is a matched send / receive of exactly that slice."""
+    rng = np.random.default_rng(11)
+    parts = 128
+    for world in (2, 3, 8):
+        rows = split_rows(parts, world)
+        lo = [DirtyColumns() for _ in range(world)]
+        hi = [DirtyColumns() for _ in range(world)]
+        for _ in range(200):
+            x0, y0 = rng.integers(0, parts, 2)
+            box = (int(x0), int(y0), int(min(parts - 1, x0 + rng.integers(0, 40))), int(min(parts - 1, y0 + rng.integers(0, 40))))
+            reached = [band_reached(box, b, e) for b, e in rows]
+            assert any(reached)
+            for r, (b, e) in enumerate(rows):
+                l, u = touched_boundaries(box, b, e, r, world)
+                if l:
+                    lo[r].add(box[0], box[2])
+                    assert reached[r] and reached[r - 1]
+                if u:
+                    hi[r].add(box[0], box[2])
+                    assert reached[r] and reached[r + 1]
+                # a rank that owns rows inside the box is always reached
+                if box[1] < e and box[3] >= b:
+                    assert reached[r]
+        for r in range(world - 1):
+            assert (hi[r].lo, hi[r].hi) == (lo[r + 1].lo, lo[r + 1].hi)
+        assert not lo[0] and not hi[world - 1]

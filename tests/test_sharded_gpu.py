@@ -42,3 +42,51 @@ def test_banded_grid_equals_single_grid(name, bands):
         assert a["cell_updates"] == b["cell_updates"] and a["active_tiles"] == b["active_tiles"]
         ok, lines = compare_grids(whole, parts)
         assert ok, (k, lines)
+
+
+def test_pushes_need_no_communication():
+    """Several pushes from two sensor poses, ONE halo synchronisation at the end: same grid as unsharded."""
+    cfg = synth.config("C1")
+    whole = capi.Grid(cfg.cell_size, 5, cfg.layout_grid)
+    parts = LocalBands(cfg.cell_size, cfg.layout_grid, 4)
+    whole.set_max_truncation(cfg.max_truncation)
+    parts.set_max_truncation(cfg.max_truncation)
+    hs = HostSensor(cfg.sensor, capi.invert3x3)
+    scans = list(cfg.scans(6))
+    for k, (pose, r) in enumerate(scans):
+        hs.set_scan(r)
+        hs.T = synth.pose_matrix(*pose)
+        sc = hs.scan()
+        whole.push(sc)
+        parts.push(sc, sync=False)
+    parts.sync_halos()
+    ok, lines = compare_grids(whole, parts)
+    assert ok, lines
+    hs.set_scan(scans[-1][1])
+    hs.T = synth.pose_matrix(*scans[-1][0])
+    sc = hs.scan()
+    rays = hs.normalized_rays(cfg.cell_size).copy()
+    c1, n1, m1, k1 = whole.raycast_mask(sc, rays)
+    c2, n2, m2, k2 = parts.raycast_mask(sc, rays)
+    assert same(m1, m2) and k1 == k2 and k1 > 0
+    assert same(c1[m1 > 0], c2[m2 > 0]) and same(n1[m1 > 0], n2[m2 > 0])
+
+
+def test_scan_box_contains_every_touched_partition():
+    cfg = synth.config("C1")
+    g = capi.Grid(cfg.cell_size, 5, cfg.layout_grid)
+    g.set_max_truncation(cfg.max_truncation)
+    hs = HostSensor(cfg.sensor, capi.invert3x3)
+    pose, r = next(iter(cfg.scans(1)))
+    hs.set_scan(r)
+    hs.T = synth.pose_matrix(*pose)
+    sc = hs.scan()
+    before = g.partition_states()[0].copy()
+    g.push(sc)
+    st, iw = g.partition_states()
+    px0, py0, px1, py1 = g.scan_box(sc)
+    parts_x = (1 << cfg.layout_grid) // 32
+    touched = np.nonzero(st != before)[0]
+    assert len(touched) > 0
+    assert (touched % parts_x >= px0).all() and (touched % parts_x <= px1).all()
+    assert (touched // parts_x >= py0).all() and (touched // parts_x <= py1).all()
