@@ -123,7 +123,7 @@ def run_cuda(args):
     # ---------------- device-resident leg: `value` times the pushes (and the halo synchronisation of a sharded grid)
     # with CUDA events on the library's stream; the H2D staging of each scan (tsdg_stage_scan, from pinned host
     # memory) sits between the event pairs, outside them.
-    def resident_step(i, acc):
+    def resident_step(i, acc, samples=None):
         for sc in wl.step_scans[i % n_steps]:
             if band:
                 if not band.stage_and_note(sc):
@@ -135,6 +135,8 @@ def run_cuda(args):
             grid.push_staged()
             e1.record(stream)
             acc.append((e0, e1))
+            if samples is not None:  # (synchronises, between the event pairs) kernel times + update count of this push
+                samples.append((grid.last_push_kernel_ms(), grid.last_push_stats()["cell_updates"]))
         if band:
             e0, e1 = ev_pair()
             e0.record(stream)
@@ -152,9 +154,7 @@ def run_cuda(args):
     kms = []
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        resident_step(i, evs)
-        if i % 8 == 0:  # (synchronises: sampled, not every step) kernel times and update count of the SAME push
-            kms.append((grid.last_push_kernel_ms(), grid.last_push_stats()["cell_updates"]))
+        resident_step(i, evs, kms if i % 8 == 0 else None)  # per-kernel times: sampled, not every step
     grid.sync()
     barrier()
     t_wall = time.perf_counter() - t_wall0

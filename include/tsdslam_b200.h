@@ -107,9 +107,22 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
  *      weight; NULL when there is no such neighbour),
  *   2. tsdg_band_push_finish: the band's top row takes its top / corner border strips from the halo above
  *      (TsdGrid::propagateBorders, TsdGrid.cpp:401-424, across the band boundary),
- *   3. exchange the rows once more so that the halos carry the refreshed borders.
+ *      and the halo row below the band gets the top / corner strips that mirror this band's first row.
  * Any number of pushes may precede one such synchronisation; the result equals the unsharded grid's. */
 int tsdg_band_push_finish(tsd_grid_t* grid);
+/* The same synchronisation in ONE kernel over peer memory (NVLink / NVSwitch P2P): each band stores its boundary
+ * rows directly into its neighbours' halo rows, signals them, waits for theirs and completes the borders.
+ * Set-up, once: every process exports its band (tsdg_band_export: CUDA IPC handles of its arrays, an opaque blob of
+ * TSD_BAND_EXPORT_BYTES) and connects the bands below (side 0) and above (side 1) with the blobs it received;
+ * bands living in one process connect with tsdg_band_connect_local.  tsdg_band_halo_sync is a collective among
+ * neighbours: both sides of a boundary call it equally often, with the same dirty partition columns
+ * [px0, px1] for that boundary (px1 < px0: nothing changed there, the boundary is skipped on both sides).  It only
+ * enqueues work on the grid's stream. */
+#define TSD_BAND_EXPORT_BYTES 256
+int tsdg_band_export(tsd_grid_t* grid, void* blob);
+int tsdg_band_connect(tsd_grid_t* grid, int side, const void* blob);
+int tsdg_band_connect_local(tsd_grid_t* grid, int side, tsd_grid_t* neighbour);
+int tsdg_band_halo_sync(tsd_grid_t* grid, int lo_px0, int lo_px1, int hi_px0, int hi_px1);
 /* Allocation flags of ALL partitions of the grid (device memory, one byte each, 1 = allocated; row-major).  A band
  * keeps the flags of its own rows and of the row on either side current; ray casting walks rays through other
  * bands' rows too (the partition-skipping loop of RayCastPolar2D.cpp:223-235), so before a ray cast the caller

@@ -20,11 +20,13 @@ _sp = C.POINTER(ScanStruct)
 _hp = C.POINTER(Hypothesis)
 _vpp = C.POINTER(C.c_void_p)
 
+BAND_EXPORT_BYTES = 256  # include/tsdslam_b200.h TSD_BAND_EXPORT_BYTES
 TILE_STRIDE = 1104  # doubles per partition and array (csrc/common.cuh TSD_TILE_STRIDE)
 
 EXPORTS = [
     "tsd_last_error", "tsd_device_count", "tsd_kernel_launches", "tsd_invert3x3",
-    "tsdg_create", "tsdg_create_band", "tsdg_band_push_finish", "tsdg_band_flags", "tsdg_scan_box", "tsdg_band_row", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
+    "tsdg_create", "tsdg_create_band", "tsdg_band_push_finish", "tsdg_band_export", "tsdg_band_connect", "tsdg_band_connect_local", "tsdg_band_halo_sync",
+    "tsdg_band_flags", "tsdg_scan_box", "tsdg_band_row", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
     "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged",
     "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
@@ -59,6 +61,10 @@ def lib():
     L.tsdg_band_push_finish.argtypes = [C.c_void_p]
     L.tsdg_scan_box.argtypes = [C.c_void_p, _sp, C.POINTER(C.c_int32)]
     L.tsdg_band_flags.argtypes = [C.c_void_p, _vpp, C.POINTER(C.c_uint64)]
+    L.tsdg_band_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.tsdg_band_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.tsdg_band_connect_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.tsdg_band_halo_sync.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.tsdg_band_row.argtypes = [C.c_void_p, C.c_int, _vpp, _vpp, C.POINTER(C.c_uint64)]
     L.tsdg_raycast_band_keys.argtypes = [C.c_void_p, _sp, _dp, _vpp, _vpp]
     L.tsdg_set_max_truncation.argtypes = [C.c_void_p, C.c_double]
@@ -270,6 +276,26 @@ class Grid:
 
     def band_push_finish(self):
         check(lib().tsdg_band_push_finish(self.h))
+
+    def band_export(self) -> bytes:
+        """Opaque description of this band (CUDA IPC handles) for the neighbouring processes."""
+        blob = C.create_string_buffer(BAND_EXPORT_BYTES)
+        check(lib().tsdg_band_export(self.h, blob))
+        return blob.raw
+
+    def band_connect(self, side: int, blob: bytes):
+        """side 0: the band below, 1: the band above (a blob from that band's band_export)."""
+        buf = C.create_string_buffer(blob, BAND_EXPORT_BYTES)
+        check(lib().tsdg_band_connect(self.h, side, buf))
+
+    def band_connect_local(self, side: int, other: "Grid"):
+        check(lib().tsdg_band_connect_local(self.h, side, other.h))
+
+    def band_halo_sync(self, lo=None, hi=None):
+        """lo / hi: (px0, px1) dirty partition columns at the boundary below / above; None = untouched."""
+        l = lo if lo is not None else (0, -1)
+        h = hi if hi is not None else (0, -1)
+        check(lib().tsdg_band_halo_sync(self.h, int(l[0]), int(l[1]), int(h[0]), int(h[1])))
 
     def band_flags(self):
         """(device pointer, count) of the allocation flags of all partitions."""

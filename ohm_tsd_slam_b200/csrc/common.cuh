@@ -273,6 +273,17 @@ struct tsd_grid
   tsd_push_stats_t last_stats;
   int sm_count;
   tsd::ScanDev staged;  // scan staged by tsdg_stage_scan (device pointers + scalars)
+  // halo synchronisation over peer memory (bands only): [0] = the band below, [1] = the band above
+  uint32_t* d_signal;        // [0]/[1] data-ready from below/above, [2]/[3] ack from below/above, [4] CTA ticket
+  struct Peer
+  {
+    bool connected, ipc;
+    double* tsd;             // the neighbour's cell arrays (its allocation base) as seen from this process
+    double* weight;
+    uint32_t* signal;
+    int alloc_begin;         // the neighbour's first allocated partition row
+  } peer[2];
+  uint32_t halo_seq[2];      // synchronisations done per boundary (both sides count alike)
   bool has_staged;
   bool timing;          // record CUDA events around the push kernels (bench.py's live roofline)
   cudaEvent_t ev[4];

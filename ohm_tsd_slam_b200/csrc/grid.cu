@@ -825,6 +825,114 @@ __device__ __forceinline__ void push_tail(const PushParams& pp)
   pp.stats64[0] = 0;
 }
 
+// Sharded grid, after boundary rows were exchanged: (a) the band's top row takes its top / corner strips from the
+// halo row above (those partitions belong to another GPU and may have changed); (b) the halo row BELOW the band
+// arrived with the top / corner strips its owner had before it saw this band's new first row -- they mirror this
+// band's own cells, so they are completed here with exactly the values the owner computes under (a).  With (b) one
+// exchange per synchronisation suffices.  Columns [lo0, hi0] / [lo1, hi1]: what changed at the lower / upper
+// boundary (a corner strip looks one partition to the right, hence the -1).
+__device__ __forceinline__ void band_boundary_refresh(const PushParams& pp, int lo0, int hi0, int lo1, int hi1, int warp,
+                                                      int nwarps, int lane)
+{
+  if(pp.row_end < pp.parts_y && hi1 >= lo1)
+    for(int px = max(lo1 - 1, 0) + warp; px <= hi1; px += nwarps)
+      if(pp.flags[(pp.row_end - 1) * pp.parts_x + px]) refresh_borders_of(pp, px, pp.row_end - 1, lane);
+  if(pp.row_begin > 0 && hi0 >= lo0)
+    for(int px = max(lo0 - 1, 0) + warp; px <= hi0; px += nwarps)
+      if(pp.flags[(pp.row_begin - 1) * pp.parts_x + px]) refresh_borders_of(pp, px, pp.row_begin - 1, lane);
+}
+
+// Halo synchronisation of a sharded grid in ONE kernel over peer memory (NVLink / NVSwitch P2P stores; the
+// neighbours' arrays are mapped with CUDA IPC, or are plain device pointers when both bands live in one process):
+//   A  tell both neighbours "I am done reading the halo rows you gave me last time" (stream order guarantees it),
+//   B  wait for the same message from them,
+//   C  store this band's lowest / highest partition row (the dirty columns) straight into the neighbours' halo rows,
+//   D  fence, then the last CTA raises "data ready" at both neighbours,
+//   E  wait for the neighbours' "data ready",
+//   F  band_boundary_refresh.
+// Signals are sequence numbers (release / acquire at system scope); both sides of a boundary count alike.
+struct HaloParams
+{
+  PushParams pp;
+  int active[2];          // boundary below / above takes part in this synchronisation
+  int px0[2], px1[2];     // dirty partition columns per boundary
+  const double* src_t[2]; // this band's lowest / highest owned row
+  const double* src_w[2];
+  double* dst_t[2];       // the neighbour's halo row above / below ITS band
+  double* dst_w[2];
+  uint32_t* peer_sig[2];
+  uint32_t* my_sig;
+  uint32_t seq[2];
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// sequence numbers wrap: compare as a signed distance
+__device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq)
+{
+  // a neighbour that never calls would hang the GPU: give up (and fail loudly) after a few seconds
+  for(unsigned spins = 0; (int32_t)(ld_acquire_sys(p) - seq) < 0; spins++)
+  {
+    __nanosleep(128);
+    if(spins > (1u << 25)) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_halo_sync(HaloParams hp)
+{
+  const int t = threadIdx.x;
+  // A: my signal slots at the neighbour: [1]/[3] at the band below (I am its upper neighbour), [0]/[2] above
+  if(blockIdx.x == 0 && t < 2 && hp.active[t]) st_release_sys(hp.peer_sig[t] + (t == 0 ? 3 : 2), hp.seq[t]);
+  // B
+  if(t < 2 && hp.active[t]) wait_seq(hp.my_sig + 2 + t, hp.seq[t]);
+  __syncthreads();
+  // C: 16-byte stores; a partition is 8832 B = 552 x 16 B, so every column offset is aligned
+  for(int b = 0; b < 2; b++)
+  {
+    if(!hp.active[b]) continue;
+    const size_t off = (size_t)hp.px0[b] * TSD_TILE_STRIDE;
+    const size_t n2 = (size_t)(hp.px1[b] - hp.px0[b] + 1) * (TSD_TILE_STRIDE / 2);
+    const double2* st = reinterpret_cast<const double2*>(hp.src_t[b] + off);
+    const double2* sw = reinterpret_cast<const double2*>(hp.src_w[b] + off);
+    double2* dt = reinterpret_cast<double2*>(hp.dst_t[b] + off);
+    double2* dw = reinterpret_cast<double2*>(hp.dst_w[b] + off);
+    for(size_t i = (size_t)blockIdx.x * blockDim.x + t; i < n2; i += (size_t)gridDim.x * blockDim.x)
+    {
+      dt[i] = st[i];
+      dw[i] = sw[i];
+    }
+  }
+  // D
+  __threadfence_system();
+  __syncthreads();
+  if(t == 0)
+  {
+    if(atomicAdd(hp.my_sig + 4, 1u) == gridDim.x - 1)
+    {
+      hp.my_sig[4] = 0;
+      __threadfence_system();
+      for(int b = 0; b < 2; b++)
+        if(hp.active[b]) st_release_sys(hp.peer_sig[b] + (b == 0 ? 1 : 0), hp.seq[b]);
+    }
+  }
+  // E
+  if(t < 2 && hp.active[t]) wait_seq(hp.my_sig + t, hp.seq[t]);
+  __syncthreads();
+  // F
+  const int warp = (blockIdx.x * blockDim.x + t) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  band_boundary_refresh(hp.pp, hp.active[0] ? hp.px0[0] : 0, hp.active[0] ? hp.px1[0] : -1, hp.active[1] ? hp.px0[1] : 0,
+                        hp.active[1] ? hp.px1[1] : -1, warp, nwarps, t & 31);
+}
+
 // K4 as a kernel of its own.  mode 0: end of a push that was asked to refresh every border (after a fill / upload /
 // free-footprint), with the push tail; mode 1: refresh everything, no push involved; mode 2: sharded grid, after
 // the halo exchange: the band's top row takes its top / corner strips from the halo row above (the partitions
@@ -843,9 +951,7 @@ __global__ void __launch_bounds__(256) k_borders(PushParams pp, int mode)
   }
   if(mode == 2)
   {
-    if(pp.band && pp.row_end < pp.parts_y)
-      for(int px = warp; px < pp.parts_x; px += nwarps)
-        if(pp.flags[(pp.row_end - 1) * pp.parts_x + px]) refresh_borders_of(pp, px, pp.row_end - 1, lane);
+    band_boundary_refresh(pp, 0, pp.parts_x - 1, 0, pp.parts_x - 1, warp, nwarps, lane);
     return;
   }
   if(!refreshAll) pull_pass(pp, warp, nwarps, lane);
@@ -1215,6 +1321,8 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMalloc(&g->d_active_w, sizeof(double) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_emptied, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_newly, sizeof(uint32_t) * g->n_owned));
+  TSD_CUDA(cudaMalloc(&g->d_signal, sizeof(uint32_t) * 8));
+  TSD_CUDA(cudaMemset(g->d_signal, 0, sizeof(uint32_t) * 8));
   TSD_CUDA(cudaMalloc(&g->d_pending, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_counters, sizeof(uint32_t) * 32));
   TSD_CUDA(cudaMalloc(&g->d_stats64, sizeof(unsigned long long) * 4));
@@ -1242,7 +1350,13 @@ int tsdg_destroy(tsd_grid_t* g)
   cudaSetDevice(g->device);
   if(g->stream) cudaStreamSynchronize(g->stream);
   cudaFree(g->d_tsd); cudaFree(g->d_weight); cudaFree(g->d_flags); cudaFree(g->d_initw); cudaFree(g->d_active);
-  cudaFree(g->d_active_w); cudaFree(g->d_emptied); cudaFree(g->d_newly); cudaFree(g->d_pending); cudaFree(g->d_counters);
+  cudaFree(g->d_active_w); cudaFree(g->d_emptied); cudaFree(g->d_newly); cudaFree(g->d_signal);
+  for(int b = 0; b < 2; b++)
+    if(g->peer[b].connected && g->peer[b].ipc)
+    {
+      cudaIpcCloseMemHandle(g->peer[b].tsd); cudaIpcCloseMemHandle(g->peer[b].weight); cudaIpcCloseMemHandle(g->peer[b].signal);
+    }
+  cudaFree(g->d_pending); cudaFree(g->d_counters);
   cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_dirs); cudaFree(g->d_in);
   cudaFree(g->d_rc); cudaFree(g->d_scratch);
   cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters);
@@ -1447,11 +1561,135 @@ int tsdg_band_push_finish(tsd_grid_t* g)
   TSD_CUDA(cudaSetDevice(g->device));
   PushParams pp = make_params(g);
   g->band_push_open = false;
-  if(g->row_end < g->parts_y)
+  if(g->row_end < g->parts_y || g->row_begin > 0)
   {
     k_borders<<<g->sm_count, 256, 0, g->stream>>>(pp, 2);
     TSD_LAUNCHED();
   }
+  return TSD_OK;
+}
+
+// --- halo synchronisation over peer memory ---------------------------------------------------------------
+struct BandExport
+{
+  cudaIpcMemHandle_t tsd, weight, signal;
+  int32_t alloc_begin, row_begin, row_end, parts_x;
+};
+static_assert(sizeof(BandExport) <= TSD_BAND_EXPORT_BYTES, "tsd_band_export_t too small");
+
+int tsdg_band_export(tsd_grid_t* g, void* blob)
+{
+  if(!g || !blob || !g->band) { set_error("not a sharded grid"); return TSD_E_INVALID; }
+  TSD_CUDA(cudaSetDevice(g->device));
+  BandExport e;
+  memset(&e, 0, sizeof(e));
+  TSD_CUDA(cudaIpcGetMemHandle(&e.tsd, g->d_tsd));
+  TSD_CUDA(cudaIpcGetMemHandle(&e.weight, g->d_weight));
+  TSD_CUDA(cudaIpcGetMemHandle(&e.signal, g->d_signal));
+  e.alloc_begin = g->alloc_begin;
+  e.row_begin = g->row_begin;
+  e.row_end = g->row_end;
+  e.parts_x = g->parts_x;
+  memset(blob, 0, TSD_BAND_EXPORT_BYTES);
+  memcpy(blob, &e, sizeof(e));
+  return TSD_OK;
+}
+
+static int check_neighbour(const tsd_grid* g, int side, int nb_row_begin, int nb_row_end, int nb_parts_x)
+{
+  if(nb_parts_x != g->parts_x) { set_error("neighbouring band has another grid geometry"); return TSD_E_INVALID; }
+  if(side == 0 && nb_row_end != g->row_begin) { set_error("band below does not end where this band begins"); return TSD_E_INVALID; }
+  if(side == 1 && nb_row_begin != g->row_end) { set_error("band above does not begin where this band ends"); return TSD_E_INVALID; }
+  return TSD_OK;
+}
+
+int tsdg_band_connect(tsd_grid_t* g, int side, const void* blob)
+{
+  if(!g || !blob || !g->band || side < 0 || side > 1) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  BandExport e;
+  memcpy(&e, blob, sizeof(e));
+  int rc = check_neighbour(g, side, e.row_begin, e.row_end, e.parts_x);
+  if(rc) return rc;
+  tsd_grid::Peer& pr = g->peer[side];
+  if(pr.connected) { set_error("neighbour already connected"); return TSD_E_INVALID; }
+  void *pt = nullptr, *pw = nullptr, *ps = nullptr;
+  TSD_CUDA(cudaIpcOpenMemHandle(&pt, e.tsd, cudaIpcMemLazyEnablePeerAccess));
+  TSD_CUDA(cudaIpcOpenMemHandle(&pw, e.weight, cudaIpcMemLazyEnablePeerAccess));
+  TSD_CUDA(cudaIpcOpenMemHandle(&ps, e.signal, cudaIpcMemLazyEnablePeerAccess));
+  pr.tsd = static_cast<double*>(pt);
+  pr.weight = static_cast<double*>(pw);
+  pr.signal = static_cast<uint32_t*>(ps);
+  pr.alloc_begin = e.alloc_begin;
+  pr.ipc = true;
+  pr.connected = true;
+  return TSD_OK;
+}
+
+int tsdg_band_connect_local(tsd_grid_t* g, int side, tsd_grid_t* nb)
+{
+  if(!g || !nb || !g->band || !nb->band || side < 0 || side > 1) return TSD_E_INVALID;
+  int rc = check_neighbour(g, side, nb->row_begin, nb->row_end, nb->parts_x);
+  if(rc) return rc;
+  tsd_grid::Peer& pr = g->peer[side];
+  if(pr.connected) { set_error("neighbour already connected"); return TSD_E_INVALID; }
+  if(nb->device != g->device)
+  {
+    TSD_CUDA(cudaSetDevice(g->device));
+    int can = 0;
+    TSD_CUDA(cudaDeviceCanAccessPeer(&can, g->device, nb->device));
+    if(!can) { set_error("no peer access between devices %d and %d", g->device, nb->device); return TSD_E_INVALID; }
+    cudaError_t pe = cudaDeviceEnablePeerAccess(nb->device, 0);
+    if(pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) TSD_CUDA(pe);
+    cudaGetLastError();
+  }
+  pr.tsd = nb->d_tsd;
+  pr.weight = nb->d_weight;
+  pr.signal = nb->d_signal;
+  pr.alloc_begin = nb->alloc_begin;
+  pr.ipc = false;
+  pr.connected = true;
+  return TSD_OK;
+}
+
+int tsdg_band_halo_sync(tsd_grid_t* g, int lo_px0, int lo_px1, int hi_px0, int hi_px1)
+{
+  if(!g || !g->band) { set_error("not a sharded grid"); return TSD_E_INVALID; }
+  TSD_CUDA(cudaSetDevice(g->device));
+  HaloParams hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.pp = make_params(g);
+  const int px0[2] = {lo_px0, hi_px0}, px1[2] = {lo_px1, hi_px1};
+  bool any = false;
+  for(int b = 0; b < 2; b++)
+  {
+    const bool has = (b == 0) ? g->row_begin > 0 : g->row_end < g->parts_y;
+    if(!has || px1[b] < px0[b]) continue;
+    if(px0[b] < 0 || px1[b] >= g->parts_x) { set_error("halo columns out of range"); return TSD_E_RANGE; }
+    if(!g->peer[b].connected) { set_error("neighbouring band not connected (tsdg_band_connect)"); return TSD_E_INVALID; }
+    any = true;
+    hp.active[b] = 1;
+    hp.px0[b] = px0[b];
+    hp.px1[b] = px1[b];
+    const int src_row = (b == 0) ? g->row_begin : g->row_end - 1;
+    const size_t src_off = (size_t)(src_row - g->alloc_begin) * g->parts_x * TSD_TILE_STRIDE;
+    hp.src_t[b] = g->d_tsd + src_off;
+    hp.src_w[b] = g->d_weight + src_off;
+    // the same row in the neighbour's allocation: its halo above (b == 0) / below (b == 1) its band
+    const size_t dst_off = (size_t)(src_row - g->peer[b].alloc_begin) * g->parts_x * TSD_TILE_STRIDE;
+    hp.dst_t[b] = g->peer[b].tsd + dst_off;
+    hp.dst_w[b] = g->peer[b].weight + dst_off;
+    hp.peer_sig[b] = g->peer[b].signal;
+    hp.seq[b] = ++g->halo_seq[b];
+  }
+  g->band_push_open = false;
+  if(!any) return TSD_OK;
+  hp.my_sig = g->d_signal;
+  // all CTAs must be co-resident (they wait on remote flags): at most one per SM
+  int ctas = g->sm_count / 2;
+  if(ctas < 1) ctas = 1;
+  k_halo_sync<<<ctas, 256, 0, g->stream>>>(hp);
+  TSD_LAUNCHED();
   return TSD_OK;
 }
 

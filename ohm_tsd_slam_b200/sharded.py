@@ -108,14 +108,24 @@ def merge_best_hypothesis(score: float, index: int, allreduce_max_i64):
 class LocalBands:
     """All bands of a sharded grid on ONE device (tests, and a way to prove that sharding is exact)."""
 
-    def __init__(self, cell_size: float, layout_grid: int, bands: int, device: int = 0):
+    def __init__(self, cell_size: float, layout_grid: int, bands: int, device: int = 0, peer: bool = False):
+        """peer: synchronise halos with the one-kernel peer-memory path (tsdg_band_halo_sync) instead of device
+        copies + tsdg_band_push_finish."""
         self.device = device
+        self.peer = peer
         parts_y = (1 << layout_grid) // 32
         self.rows = split_rows(parts_y, bands)
         self.grids = [capi.Grid(cell_size, 5, layout_grid, device=device, band=r) for r in self.rows]
         self.n_partitions = self.grids[0].n_partitions
         self.parts_x = parts_y
         self.dim = 32
+        self.dirty_cols = DirtyColumns()
+        if peer:
+            for i, g in enumerate(self.grids):
+                if i > 0:
+                    g.band_connect_local(0, self.grids[i - 1])
+                if i + 1 < len(self.grids):
+                    g.band_connect_local(1, self.grids[i + 1])
 
     def set_max_truncation(self, v):
         for g in self.grids:
@@ -126,6 +136,7 @@ class LocalBands:
         return self.grids[0].bounds
 
     def free_footprint(self, *a):
+        self.dirty = True  # (all columns: dirty_cols stays empty)
         return all([g.free_footprint(*a) for g in self.grids])
 
     def _exchange(self):
@@ -153,17 +164,27 @@ class LocalBands:
             if mine:
                 g.push_async(scan)
         self.dirty = True
+        self.dirty_cols.add(box[0], box[2])
         if sync:
             self.sync_halos()
 
     def sync_halos(self):
         if not getattr(self, "dirty", False):
             return
-        self._exchange()
-        for g in self.grids:
-            g.band_push_finish()
-        self._exchange()
+        if self.peer:
+            # every band's kernel waits for its neighbours': all of them are enqueued (on their own streams) before
+            # anything synchronises
+            cols = (self.dirty_cols.lo, self.dirty_cols.hi) if self.dirty_cols else (0, self.parts_x - 1)
+            for g in self.grids:
+                g.band_halo_sync(cols, cols)
+            for g in self.grids:
+                g.sync()
+        else:
+            self._exchange()
+            for g in self.grids:
+                g.band_push_finish()
         self.dirty = False
+        self.dirty_cols.clear()
 
     def sync_flags(self):
         """Element-wise MAX of the bands' allocation flags (what DistBand does with an all-reduce)."""
@@ -243,7 +264,9 @@ class LocalBands:
 class DistBand:
     """One band per rank over torch.distributed (backend nccl on GPUs)."""
 
-    def __init__(self, cell_size: float, layout_grid: int, device: int):
+    def __init__(self, cell_size: float, layout_grid: int, device: int, transport: str = "peer"):
+        """transport "peer": halo rows are stored straight into the neighbours' memory by one kernel
+        (tsdg_band_halo_sync over CUDA IPC mappings, NVLink P2P); "nccl": batched isend/irecv + tsdg_band_push_finish."""
         import torch.distributed as dist
         self.dist = dist
         self.rank = dist.get_rank()
@@ -257,6 +280,15 @@ class DistBand:
         self.flags_dirty = False
         self._flags = None
         self._views = None
+        self.transport = transport
+        if transport == "peer" and self.world > 1:
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, self.grid.band_export())
+            if self.rank > 0:
+                self.grid.band_connect(0, blobs[self.rank - 1])
+            if self.rank + 1 < self.world:
+                self.grid.band_connect(1, blobs[self.rank + 1])
+            dist.barrier()
 
     def _row_views(self):
         if self._views is None:
@@ -314,9 +346,15 @@ class DistBand:
         """Bring the halos up to date (see the module docstring).  Collective: every rank calls it."""
         if not (full or self.dirty_lo or self.dirty_hi):
             return 0
-        n = self.exchange(full)
-        self.grid.band_push_finish()
-        n += self.exchange(full)
+        if self.transport == "peer":
+            whole = (0, self.parts_x - 1)
+            lo = whole if full else ((self.dirty_lo.lo, self.dirty_lo.hi) if self.dirty_lo else None)
+            hi = whole if full else ((self.dirty_hi.lo, self.dirty_hi.hi) if self.dirty_hi else None)
+            self.grid.band_halo_sync(lo, hi)
+            n = 1
+        else:
+            n = self.exchange(full)
+            self.grid.band_push_finish()
         self.dirty_lo.clear()
         self.dirty_hi.clear()
         return n

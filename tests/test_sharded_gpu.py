@@ -11,11 +11,13 @@ from tests.harness import compare_grids, same
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,bands", [("tiny", 2), ("tiny", 3), ("C1", 2), ("C1", 5)])
-def test_banded_grid_equals_single_grid(name, bands):
+@pytest.mark.parametrize("name,bands,peer", [("tiny", 2, False), ("tiny", 3, True), ("C1", 2, True), ("C1", 5, False), ("C1", 4, True)])
+def test_banded_grid_equals_single_grid(name, bands, peer):
+    """peer=False: halo rows by device copies + tsdg_band_push_finish; peer=True: the one-kernel peer-memory
+    synchronisation (tsdg_band_halo_sync), every band's kernel running concurrently on its own stream."""
     cfg = synth.config(name)
     whole = capi.Grid(cfg.cell_size, 5, cfg.layout_grid)
-    parts = LocalBands(cfg.cell_size, cfg.layout_grid, bands)
+    parts = LocalBands(cfg.cell_size, cfg.layout_grid, bands, peer=peer)
     whole.set_max_truncation(cfg.max_truncation)
     parts.set_max_truncation(cfg.max_truncation)
     hs = HostSensor(cfg.sensor, capi.invert3x3)
@@ -48,7 +50,7 @@ def test_pushes_need_no_communication():
     """Several pushes from two sensor poses, ONE halo synchronisation at the end: same grid as unsharded."""
     cfg = synth.config("C1")
     whole = capi.Grid(cfg.cell_size, 5, cfg.layout_grid)
-    parts = LocalBands(cfg.cell_size, cfg.layout_grid, 4)
+    parts = LocalBands(cfg.cell_size, cfg.layout_grid, 4, peer=True)
     whole.set_max_truncation(cfg.max_truncation)
     parts.set_max_truncation(cfg.max_truncation)
     hs = HostSensor(cfg.sensor, capi.invert3x3)
