@@ -23,6 +23,8 @@
 
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 using namespace tsd;
@@ -30,6 +32,9 @@ using namespace tsd;
 #define ICP_THREADS 1024
 #define ICP_MAX_POINTS 2048
 #define ICP_SLOTS 4096  // hash buckets
+#ifndef ICP_CLUSTER
+#define ICP_CLUSTER 8   // CTAs (SMs) per registration: the portable cluster size
+#endif
 
 struct IcpParams
 {
@@ -118,38 +123,81 @@ __device__ __forceinline__ void block_sum_n(double* v, double* s_red, int tid)
   for(int k = 0; k < NV; k++) v[k] = s_red[192 + k];
 }
 
-__global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
+// Distributed shared memory is only ever READ remotely here (ld.shared::cluster through a mapa address).  Remote
+// 64-bit min atomics are not usable: for a shared::cluster address that is not the CTA's own window, the
+// compiler's atomicMin(unsigned long long) expands to a plain load / compare / store (seen in the SASS, and as
+// lost updates in the pair lists), so every atomic below stays inside the CTA that owns the word.
+__device__ __forceinline__ uint32_t dsmem_addr(const void* own_smem, unsigned rank)
 {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(own_smem);
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ unsigned long long dsmem_ld_u64(uint32_t addr)
+{
+  unsigned long long v;
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned dsmem_ld_u32(uint32_t addr)
+{
+  unsigned v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// One thread-block CLUSTER of ICP_CLUSTER CTAs (one SM each) runs the whole loop.  Every CTA keeps the model, its
+// search structure, the scene and the transformation in its own shared memory and evolves them identically
+// (same code, same data, same reduction trees), so no state is ever broadcast.  What is split is the expensive
+// part, the nearest-neighbour search: query i belongs to CTA i % ICP_CLUSTER, and four lanes share a query (the
+// cells of a ring are dealt round-robin to the lanes, then two shuffles pick the winner).  The reciprocal filter
+// (closest scene point per model point) is reduced in two levels: every CTA filters its own queries with
+// shared-memory atomics, then model point m's host, CTA m % ICP_CLUSTER, reads the ICP_CLUSTER local results
+// through distributed shared memory and keeps the winner.  Two cluster barriers per iteration:
+//      NN search + local reciprocal filter                                   | cluster.sync |
+//      hosts gather (best distance, lowest scene index) of their model points | cluster.sync |
+//      estimator sums over the winners (read from the hosts), pose update, scene transform -- replicated
+__global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
+{
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x;
   const int nM = P.nM, nS = P.nS;
-  // shared memory carve-up
+  const int nQ = (nS + ICP_CLUSTER - 1) / ICP_CLUSTER;  // queries per CTA (upper bound)
+  const int nH = (nM + ICP_CLUSTER - 1) / ICP_CLUSTER;  // model points hosted per CTA (upper bound)
+  // shared memory carve-up (identical in every CTA, so that map_shared_rank offsets agree)
   double* s_mx = reinterpret_cast<double*>(smem);
   double* s_my = s_mx + nM;
   double* s_sx = s_my + nM;
   double* s_sy = s_sx + nS;
-  double* s_d2 = s_sy + nS;                                                        // nS
-  double* s_lb = s_d2 + nS;                                                        // nS: lower bound of the NN distance
-  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_lb + nS);  // nM
+  double* s_d2 = s_sy + nS;                                                        // nQ: own queries
+  double* s_lb = s_d2 + nQ;                                                        // nQ: lower bound of the NN distance
+  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_lb + nQ);  // nM: over this CTA's queries
   double* s_red = reinterpret_cast<double*>(s_best + nM);                          // 208
   double* s_T = s_red + 208;                                                       // Tfinal 16, Tlast 16
-  unsigned* s_win = reinterpret_cast<unsigned*>(s_T + 32);                         // nM
-  int* s_nn = reinterpret_cast<int*>(s_win + nM);                                  // nS
-  unsigned* s_scan = reinterpret_cast<unsigned*>(s_nn + nS);                       // 40
+  unsigned* s_win = reinterpret_cast<unsigned*>(s_T + 32);                         // nM: over this CTA's queries
+  unsigned* s_fin = s_win + nM;                                                    // nH: winners of the hosted model points
+  int* s_nn = reinterpret_cast<int*>(s_fin + nH);                                  // nQ
+  unsigned* s_scan = reinterpret_cast<unsigned*>(s_nn + nQ);                       // 40
   unsigned short* s_bstart = reinterpret_cast<unsigned short*>(s_scan + 40);       // ICP_SLOTS + 2
   unsigned short* s_bcnt = s_bstart + (ICP_SLOTS + 2);                             // ICP_SLOTS
   unsigned short* s_bidx = s_bcnt + ICP_SLOTS;                                     // nM (+1 pad)
   unsigned* s_coarse = reinterpret_cast<unsigned*>(s_bidx + ((nM + 2) & ~1));      // 128 words: coarse occupancy bitmap
   unsigned* s_occ = s_coarse + 128;                                                // 128 words: non-empty hash slots
 
+  const unsigned long long INF64 = 0xffffffffffffffffULL;
   for(int i = tid; i < nM; i += ICP_THREADS) { s_mx[i] = P.model[2 * i]; s_my[i] = P.model[2 * i + 1]; }
-  for(int i = tid; i < nS; i += ICP_THREADS) { s_sx[i] = P.scene[2 * i]; s_sy[i] = P.scene[2 * i + 1]; s_lb[i] = 0.0; }
+  for(int i = tid; i < nS; i += ICP_THREADS) { s_sx[i] = P.scene[2 * i]; s_sy[i] = P.scene[2 * i + 1]; }
+  for(int i = tid; i < nQ; i += ICP_THREADS) s_lb[i] = 0.0;
   for(int i = tid; i < ICP_SLOTS; i += ICP_THREADS) s_bcnt[i] = 0;
   if(tid < 128) { s_coarse[tid] = 0u; s_occ[tid] = 0u; }
   if(tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0 : 0.0; s_T[16 + tid] = s_T[tid]; }
   __syncthreads();
 
-  // ---- spatial hash of the model: counting sort of the points by hash slot ----
+  // ---- spatial hash of the model: counting sort of the points by hash slot (built by every CTA for itself) ----
   const double h = P.hash_h, invh = 1.0 / P.hash_h;
   const double invhc = 1.0 / P.coarse_h;  // coarse cells: edge >= the distance filter's largest threshold
   const double bx0 = s_mx[0], by0 = s_my[0];
@@ -224,6 +272,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
     }
     __syncthreads();
   }
+  cluster.sync();  // every CTA is resident before anybody addresses its shared memory
 
   int eRetval = TSD_ICP_PROCESSING;
   unsigned iter = 0;
@@ -232,32 +281,32 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
   double rms = 0.0;  // the caller passes *rms = 0.0 (ThreadLocalize.cpp:577)
   unsigned pairs = 0;
   double distSqr = P.max_dist_sqr;  // DistanceFilter::reset (DistanceFilter.cpp:27-30)
-  const unsigned long long INF64 = 0xffffffffffffffffULL;
+
+  // four lanes per query
+  const int quad = tid >> 2, ql = tid & 3;
+  const unsigned qmask = 0xfu << ((tid & 31) & ~3);
 
   while(eRetval == TSD_ICP_PROCESSING)
   {
     for(int m = tid; m < nM; m += ICP_THREADS) { s_best[m] = INF64; s_win[m] = 0xffffffffu; }
     __syncthreads();
 
-    // ---- A: pre-filter + exact 1-NN + distance filter ----
-    // Queries [0, ICP_THREADS) : one per thread, ring search.  Queries beyond (nS > 1024) : one per warp,
-    // the lanes scan the cells of the (2R+1)^2 window that covers the distance filter's radius in parallel,
-    // so that the few left-over queries do not double the time of the whole phase.
-    const int nFirst = min(nS, ICP_THREADS);
-    if(tid < nFirst)
+    // ---- A: pre-filter + exact 1-NN + distance filter, for the queries of this CTA ----
+    for(int q = quad; q < nQ; q += ICP_THREADS / 4)
     {
-      const int i = tid;
-      const double x = s_sx[i], y = s_sy[i];
+      const int i = q * ICP_CLUSTER + (int)rank;
+      const bool exists = i < nS;
+      const double x = exists ? s_sx[i] : 0.0, y = exists ? s_sy[i] : 0.0;
       // OutOfBoundsFilter2D.cpp:27-37: S.transform(pose) = S * R^T + t
       double tx = 0.0; tx += x * P.pose[0]; tx += y * P.pose[1]; tx = 0.0 + 1.0 * tx; tx += P.pose[2];
       double ty = 0.0; ty += x * P.pose[3]; ty += y * P.pose[4]; ty = 0.0 + 1.0 * ty; ty += P.pose[5];
-      bool search = !(tx < P.x_min || tx > P.x_max || ty < P.y_min || ty > P.y_max);
+      bool search = exists && !(tx < P.x_min || tx > P.x_max || ty < P.y_min || ty > P.y_max);
       int best = -1;
       double bestD = __longlong_as_double(0x7ff0000000000000LL);
       // A point whose nearest model point is provably farther than the distance filter's threshold cannot
-      // yield a pair (DistanceFilter.cpp:38): its search is skipped.  s_lb[i] is a lower bound of that
+      // yield a pair (DistanceFilter.cpp:38): its search is skipped.  s_lb[q] is a lower bound of that
       // distance, carried over from the last search and reduced by how far the point moved since.
-      double lbNew = s_lb[i];
+      double lbNew = exists ? s_lb[q] : 0.0;
       if(search && lbNew * lbNew > distSqr) search = false;
       else if(search) lbNew = 0.0;
       if(search)
@@ -276,33 +325,45 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
         search = any != 0;
         if(!search) lbNew = P.coarse_h * (1.0 - 1e-6);  // nothing within one coarse cell
       }
+      // (search, x, y are uniform over the four lanes of the query)
       if(search)
       {
         const int qx = cell_of(x, bx0, invh), qy = cell_of(y, by0, invh);
-        for(int r = 0; r <= P.max_rings; r++)
+        for(int r = 1; r <= P.max_rings; r++)
         {
-          const int x0 = qx - r, x1 = qx + r, y0 = qy - r, y1 = qy + r;
-          for(int by = y0; by <= y1; by++)
+          // cells of ring r, dealt to the four lanes; the first pass also takes the centre cell (ring 0 can never
+          // end the search: its bound is 0)
+          const int side = 2 * r, count = 8 * r + (r == 1 ? 1 : 0);
+          for(int c = ql; c < count; c += 4)
           {
-            const bool edgeRow = (by == y0 || by == y1);
-            const int step = edgeRow ? 1 : max(x1 - x0, 1);
-            for(int bx = x0; bx <= x1; bx += step)
+            int bx, by;
+            if(c == 8 * r) { bx = qx; by = qy; }
+            else
             {
-              const unsigned b = slot_of(bx, by);
-              if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
-              const int k1 = s_bstart[b + 1];
-              for(int k = s_bstart[b]; k < k1; k++)
-              {
-                const int m = s_bidx[k];
-                const double d0 = x - s_mx[m];
-                const double d1 = y - s_my[m];
-                double d = 0.0;
-                d += d0 * d0;
-                d += d1 * d1;
-                if(d < bestD) { bestD = d; best = m; }
-                else if(d == bestD && m < best) best = m;
-              }
+              const int sd = c / side, off = c - sd * side;
+              bx = (sd == 0) ? qx - r + off : (sd == 1) ? qx + r : (sd == 2) ? qx + r - off : qx - r;
+              by = (sd == 0) ? qy - r : (sd == 1) ? qy - r + off : (sd == 2) ? qy + r : qy + r - off;
             }
+            const unsigned b = slot_of(bx, by);
+            if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
+            const int k1 = s_bstart[b + 1];
+            for(int k = s_bstart[b]; k < k1; k++)
+            {
+              const int m = s_bidx[k];
+              const double d0 = x - s_mx[m];
+              const double d1 = y - s_my[m];
+              double d = 0.0;
+              d += d0 * d0;
+              d += d1 * d1;
+              if(d < bestD || (d == bestD && m < best)) { bestD = d; best = m; }
+            }
+          }
+#pragma unroll
+          for(int o = 1; o < 4; o <<= 1)
+          {
+            const double od = __shfl_xor_sync(qmask, bestD, o);
+            const int ob = __shfl_xor_sync(qmask, best, o);
+            if(ob >= 0 && (best < 0 || od < bestD || (od == bestD && ob < best))) { bestD = od; best = ob; }
           }
           // everything unvisited lies in cells at Chebyshev distance > r, i.e. farther than r*h
           const double lb = (double)r * h * (1.0 - 1e-9);
@@ -315,81 +376,72 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
           }
         }
       }
-      s_lb[i] = lbNew;
-      const bool keep = (best >= 0) && (bestD <= distSqr);  // DistanceFilter.cpp:38
-      s_nn[i] = keep ? best : -1;
-      s_d2[i] = bestD;
-      if(keep) atomicMin(&s_best[best], (unsigned long long)__double_as_longlong(bestD));
-    }
-    for(int i = ICP_THREADS + (tid >> 5); i < nS; i += ICP_THREADS / 32)
-    {
-      const int lane = tid & 31;
-      const double x = s_sx[i], y = s_sy[i];
-      double tx = 0.0; tx += x * P.pose[0]; tx += y * P.pose[1]; tx = 0.0 + 1.0 * tx; tx += P.pose[2];
-      double ty = 0.0; ty += x * P.pose[3]; ty += y * P.pose[4]; ty = 0.0 + 1.0 * ty; ty += P.pose[5];
-      const bool masked = (tx < P.x_min || tx > P.x_max || ty < P.y_min || ty > P.y_max);
-      int best = -1;
-      double bestD = __longlong_as_double(0x7ff0000000000000LL);
-      if(!masked)
+      if(exists && ql == 0)
       {
-        // smallest R with (R * h)^2 > distSqr: the window then holds every point the distance filter keeps
-        int R = 1;
-        while(R < P.max_rings && !(distSqr < ((double)R * h * (1.0 - 1e-9)) * ((double)R * h * (1.0 - 1e-9)))) R++;
-        const int W = 2 * R + 1;
-        const int qx = cell_of(x, bx0, invh), qy = cell_of(y, by0, invh);
-        for(int c = lane; c < W * W; c += 32)
-        {
-          const unsigned b = slot_of(qx - R + c % W, qy - R + c / W);
-          if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
-          const int k1 = s_bstart[b + 1];
-          for(int k = s_bstart[b]; k < k1; k++)
-          {
-            const int m = s_bidx[k];
-            const double d0 = x - s_mx[m];
-            const double d1 = y - s_my[m];
-            double d = 0.0;
-            d += d0 * d0;
-            d += d1 * d1;
-            if(d < bestD || (d == bestD && m < best)) { bestD = d; best = m; }
-          }
-        }
-      }
-#pragma unroll
-      for(int o = 16; o > 0; o >>= 1)
-      {
-        const double od = __shfl_xor_sync(0xffffffffu, bestD, o);
-        const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-        if(ob >= 0 && (best < 0 || od < bestD || (od == bestD && ob < best))) { bestD = od; best = ob; }
-      }
-      if(lane == 0)
-      {
-        const bool keep = (best >= 0) && (bestD <= distSqr);
-        s_nn[i] = keep ? best : -1;
-        s_d2[i] = bestD;
+        s_lb[q] = lbNew;
+        const bool keep = (best >= 0) && (bestD <= distSqr);  // DistanceFilter.cpp:38
+        s_nn[q] = keep ? best : -1;
+        s_d2[q] = bestD;
         if(keep) atomicMin(&s_best[best], (unsigned long long)__double_as_longlong(bestD));
       }
     }
     __syncthreads();
     // ---- B: ReciprocalFilter.cpp:32-78: closest scene point per model point (lowest scene index on ties) ----
-    for(int i = tid; i < nS; i += ICP_THREADS)
+    // level 1: among this CTA's queries
+    for(int q = tid; q < nQ; q += ICP_THREADS)
     {
-      const int m = s_nn[i];
-      if(m >= 0 && (unsigned long long)__double_as_longlong(s_d2[i]) == s_best[m]) atomicMin(&s_win[m], (unsigned)i);
+      const int i = q * ICP_CLUSTER + (int)rank;
+      if(i >= nS) continue;
+      const int m = s_nn[q];
+      if(m >= 0 && (unsigned long long)__double_as_longlong(s_d2[q]) == s_best[m]) atomicMin(&s_win[m], (unsigned)i);
     }
-    __syncthreads();
+    cluster.sync();
+    // level 2: the host of model point m = k * ICP_CLUSTER + rank reads the ICP_CLUSTER local results, one lane each
+    for(int k0 = 0; k0 < nH; k0 += ICP_THREADS / ICP_CLUSTER)
+    {
+      const int k = k0 + tid / ICP_CLUSTER;
+      const unsigned src = tid % ICP_CLUSTER;
+      const int m = k * ICP_CLUSTER + (int)rank;
+      unsigned long long bd = INF64;
+      unsigned wi = 0xffffffffu;
+      if(k < nH && m < nM)
+      {
+        bd = dsmem_ld_u64(dsmem_addr(s_best + m, src));
+        wi = dsmem_ld_u32(dsmem_addr(s_win + m, src));
+      }
+#pragma unroll
+      for(int o = 1; o < ICP_CLUSTER; o <<= 1)
+      {
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bd, o);
+        const unsigned ow = __shfl_xor_sync(0xffffffffu, wi, o);
+        if(ob < bd || (ob == bd && ow < wi)) { bd = ob; wi = ow; }
+      }
+      if(src == 0 && k < nH) s_fin[k] = (bd == INF64) ? 0xffffffffu : wi;
+    }
+    cluster.sync();
     // DistanceFilter.cpp:62-63
     distSqr *= P.multiplier;
     if(distSqr < P.min_dist_sqr) distSqr = P.min_dist_sqr;
 
     // ---- C: ClosedFormEstimator2D::setPairs (+ the pair list in model order when tracing) ----
+    // (replicated: every CTA reads all winners, one distributed-shared-memory load per model point)
     double acc[6] = {0, 0, 0, 0, 0, 0};  // cm0 cm1 cs0 cs1 r count
-    if(P.trace)
+    unsigned winOf[(ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS];
+#pragma unroll
+    for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
+    {
+      const int m = tid + j * ICP_THREADS;
+      winOf[j] = (m < nM) ? dsmem_ld_u32(dsmem_addr(s_fin + m / ICP_CLUSTER, m % ICP_CLUSTER)) : 0xffffffffu;
+    }
+    if(P.trace && rank == 0)
     {
       unsigned baseCount = 0;
-      for(int m0 = 0; m0 < nM; m0 += ICP_THREADS)
+#pragma unroll
+      for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
       {
-        const int m = m0 + tid;
-        const bool has = (m < nM) && (s_win[m] != 0xffffffffu);
+        const int m = tid + j * ICP_THREADS;
+        if(j * ICP_THREADS >= nM) break;
+        const bool has = winOf[j] != 0xffffffffu;
         const unsigned bal = __ballot_sync(0xffffffffu, has);
         if((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
         __syncthreads();
@@ -407,16 +459,18 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
           if((int)iter < P.max_iterations && pos < (unsigned)P.cap)
           {
             P.tr_model[(size_t)iter * P.cap + pos] = (unsigned)m;
-            P.tr_scene[(size_t)iter * P.cap + pos] = s_win[m];
+            P.tr_scene[(size_t)iter * P.cap + pos] = winOf[j];
           }
         }
         baseCount += total;
         __syncthreads();
       }
     }
-    for(int m = tid; m < nM; m += ICP_THREADS)
+#pragma unroll
+    for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
     {
-      const unsigned sidx = s_win[m];
+      const int m = tid + j * ICP_THREADS;
+      const unsigned sidx = winOf[j];
       if(sidx != 0xffffffffu)
       {
         acc[0] += s_mx[m]; acc[1] += s_my[m];
@@ -439,9 +493,11 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
       rms = r;
       // estimateTransformation (ClosedFormEstimator2D.cpp:74-109)
       double nd[2] = {0, 0};
-      for(int m = tid; m < nM; m += ICP_THREADS)
+#pragma unroll
+      for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
       {
-        const unsigned sidx = s_win[m];
+        const int m = tid + j * ICP_THREADS;
+        const unsigned sidx = winOf[j];
         if(sidx != 0xffffffffu)
         {
           const double xFCm = s_mx[m] - cm0, yFCm = s_my[m] - cm1;
@@ -487,10 +543,13 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
           const double nx = a + t0, ny = b + t1;
           s_sx[i] = nx;
           s_sy[i] = ny;
-          // the point moved by |(nx,ny) - (x,y)|: its nearest-neighbour distance shrank by at most that
-          const double mvx = nx - x, mvy = ny - y;
-          const double lb = s_lb[i] - sqrt(mvx * mvx + mvy * mvy) * (1.0 + 1e-9) - 1e-12;
-          s_lb[i] = lb > 0.0 ? lb : 0.0;
+          if((unsigned)(i % ICP_CLUSTER) == rank)
+          {
+            // the point moved by |(nx,ny) - (x,y)|: its nearest-neighbour distance shrank by at most that
+            const double mvx = nx - x, mvy = ny - y;
+            const double lb = s_lb[i / ICP_CLUSTER] - sqrt(mvx * mvx + mvy * mvy) * (1.0 + 1e-9) - 1e-12;
+            s_lb[i / ICP_CLUSTER] = lb > 0.0 ? lb : 0.0;
+          }
         }
       }
     }
@@ -498,7 +557,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
     {
       retval = TSD_ICP_NOTMATCHABLE;
     }
-    if(tid == 0 && (int)iter < P.max_iterations)
+    if(rank == 0 && tid == 0 && (int)iter < P.max_iterations)
     {
       P.tr_count[iter] = (int)pairs;
       P.tr_mse[iter] = rms;
@@ -515,7 +574,7 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
     rms_prev = rms;
   }
 
-  if(tid == 0)
+  if(rank == 0 && tid == 0)
   {
     // getFinalTransformation (Icp.cpp:528-546)
     P.result[0] = s_T[0]; P.result[1] = s_T[1]; P.result[2] = s_T[3];
@@ -526,15 +585,17 @@ __global__ void __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
     P.result[11] = (double)iter;
     P.result[12] = (double)eRetval;
   }
+  cluster.sync();  // no CTA's shared memory goes away while a neighbour may still address it
 }
 
 static size_t icp_smem_bytes(int nM, int nS)
 {
+  const size_t nQ = ((size_t)nS + ICP_CLUSTER - 1) / ICP_CLUSTER, nH = ((size_t)nM + ICP_CLUSTER - 1) / ICP_CLUSTER;
   size_t b = 0;
-  b += sizeof(double) * (2 * (size_t)nM + 2 * (size_t)nS + 2 * (size_t)nS);  // mx my sx sy d2 lb
-  b += sizeof(unsigned long long) * nM;                           // best
+  b += sizeof(double) * (2 * (size_t)nM + 2 * (size_t)nS + 2 * nQ);  // mx my sx sy d2 lb
+  b += sizeof(unsigned long long) * nM;                            // best
   b += sizeof(double) * (208 + 32);                               // red + T
-  b += sizeof(unsigned) * nM + sizeof(int) * nS + sizeof(unsigned) * 40;
+  b += sizeof(unsigned) * ((size_t)nM + nH) + sizeof(int) * nQ + sizeof(unsigned) * 40;
   b += sizeof(unsigned short) * (ICP_SLOTS + 2 + ICP_SLOTS + (size_t)nM + 2) + sizeof(unsigned) * 256;
   return b + 64;
 }
@@ -653,7 +714,7 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   p.tr_mse = h->d_tr_mse;
   p.tr_T = h->d_tr_T;
   if(p.max_iterations > 0) TSD_CUDA(cudaMemsetAsync(h->d_tr_count, 0xff, sizeof(int) * p.max_iterations, h->stream));
-  k_icp<<<1, ICP_THREADS, icp_smem_bytes(n_model, n_scene), h->stream>>>(p);
+  k_icp<<<ICP_CLUSTER, ICP_THREADS, icp_smem_bytes(n_model, n_scene), h->stream>>>(p);  // one cluster (__cluster_dims__)
   TSD_LAUNCHED();
   TSD_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(double) * 13, cudaMemcpyDeviceToHost, h->stream));
   TSD_CUDA(cudaStreamSynchronize(h->stream));
