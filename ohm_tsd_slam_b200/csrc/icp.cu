@@ -1,7 +1,7 @@
 // Icp::iterate on the device (K6-K8): the whole registration loop -- pre-filter, exact nearest-neighbour
 // pairing, distance filter, reciprocal filter, closed-form estimate, transform update -- is ONE kernel
-// launch of one persistent CTA; model, scene and the search structure live in shared memory for all
-// iterations, so an ICP run costs one H2D copy, one launch and one D2H copy.
+// launch of one thread-block cluster (ICP_CLUSTER CTAs, one SM each); model, scene and the search structure
+// live in shared memory for all iterations, so an ICP run costs one H2D copy, one launch and one D2H copy.
 //
 // Reference: src/obvision/registration/icp/Icp.cpp:464-512 (iterate), :410-462 (step), :371-408
 // (applyTransformation); assign/PairAssignment.cpp:38-84; assign/FlannPairAssignment.cpp:64-92;
@@ -15,6 +15,8 @@
 // filter's current threshold (such a pair is dropped by DistanceFilter.cpp:38 whatever its model index).
 // Hash collisions only add candidates, never remove any.  Distances are computed as FLANN's L2 functor does
 // ((0 + dx*dx) + dy*dy); ties go to the lowest model index, the rule the oracle's FLANN stand-in uses.
+//
+// Work split and communication inside the cluster: see k_icp.
 //
 // Sums of the estimator are block reductions with a fixed tree, so results are deterministic but not
 // bit-identical to the reference's sequential sums (and atan2/sin/cos differ from glibc in the last ulp
@@ -123,8 +125,8 @@ __device__ __forceinline__ void block_sum_n(double* v, double* s_red, int tid)
   for(int k = 0; k < NV; k++) v[k] = s_red[192 + k];
 }
 
-// Distributed shared memory is only ever READ remotely here (ld.shared::cluster through a mapa address).  Remote
-// 64-bit min atomics are not usable: for a shared::cluster address that is not the CTA's own window, the
+// Distributed shared memory is only ever written with plain stores (st.shared::cluster through a mapa address), each
+// word by exactly one remote thread between two cluster barriers.  Remote 64-bit min atomics are not usable: for a shared::cluster address that is not the CTA's own window, the
 // compiler's atomicMin(unsigned long long) expands to a plain load / compare / store (seen in the SASS, and as
 // lost updates in the pair lists), so every atomic below stays inside the CTA that owns the word.
 __device__ __forceinline__ uint32_t dsmem_addr(const void* own_smem, unsigned rank)
@@ -134,30 +136,26 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void* own_smem, unsigned ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
   return r;
 }
-__device__ __forceinline__ unsigned long long dsmem_ld_u64(uint32_t addr)
+__device__ __forceinline__ void dsmem_st_v2u64(uint32_t addr, unsigned long long a, unsigned long long b)
 {
-  unsigned long long v;
-  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
-  return v;
+  asm volatile("st.shared::cluster.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ unsigned dsmem_ld_u32(uint32_t addr)
+__device__ __forceinline__ void dsmem_st_u32(uint32_t addr, unsigned v)
 {
-  unsigned v;
-  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-
 // One thread-block CLUSTER of ICP_CLUSTER CTAs (one SM each) runs the whole loop.  Every CTA keeps the model, its
 // search structure, the scene and the transformation in its own shared memory and evolves them identically
 // (same code, same data, same reduction trees), so no state is ever broadcast.  What is split is the expensive
 // part, the nearest-neighbour search: query i belongs to CTA i % ICP_CLUSTER, and four lanes share a query (the
 // cells of a ring are dealt round-robin to the lanes, then two shuffles pick the winner).  The reciprocal filter
 // (closest scene point per model point) is reduced in two levels: every CTA filters its own queries with
-// shared-memory atomics, then model point m's host, CTA m % ICP_CLUSTER, reads the ICP_CLUSTER local results
-// through distributed shared memory and keeps the winner.  Two cluster barriers per iteration:
-//      NN search + local reciprocal filter                                   | cluster.sync |
-//      hosts gather (best distance, lowest scene index) of their model points | cluster.sync |
-//      estimator sums over the winners (read from the hosts), pose update, scene transform -- replicated
+// shared-memory atomics and stores each local winner into the inbox of model point m's host, CTA m % ICP_CLUSTER
+// (distributed shared memory, one 16-byte store); the host keeps the best of its ICP_CLUSTER candidates and stores
+// the final winner into every CTA's copy.  Two cluster barriers per iteration:
+//      NN search, local reciprocal filter, local winners -> hosts' inboxes   | cluster.sync |
+//      hosts pick (best distance, lowest scene index), winners -> every CTA   | cluster.sync |
+//      estimator sums over the winners, pose update, scene transform -- replicated, identical in every CTA
 __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
 {
   namespace cg = cooperative_groups;
@@ -179,19 +177,22 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
   double* s_red = reinterpret_cast<double*>(s_best + nM);                          // 208
   double* s_T = s_red + 208;                                                       // Tfinal 16, Tlast 16
   unsigned* s_win = reinterpret_cast<unsigned*>(s_T + 32);                         // nM: over this CTA's queries
-  unsigned* s_fin = s_win + nM;                                                    // nH: winners of the hosted model points
-  int* s_nn = reinterpret_cast<int*>(s_fin + nH);                                  // nQ
+  unsigned* s_fin = s_win + nM;                                                    // nM: final winner of every model point
+  int* s_nn = reinterpret_cast<int*>(s_fin + nM);                                  // nQ
   unsigned* s_scan = reinterpret_cast<unsigned*>(s_nn + nQ);                       // 40
   unsigned short* s_bstart = reinterpret_cast<unsigned short*>(s_scan + 40);       // ICP_SLOTS + 2
   unsigned short* s_bcnt = s_bstart + (ICP_SLOTS + 2);                             // ICP_SLOTS
   unsigned short* s_bidx = s_bcnt + ICP_SLOTS;                                     // nM (+1 pad)
   unsigned* s_coarse = reinterpret_cast<unsigned*>(s_bidx + ((nM + 2) & ~1));      // 128 words: coarse occupancy bitmap
   unsigned* s_occ = s_coarse + 128;                                                // 128 words: non-empty hash slots
+  // candidates sent to this host: ICP_CLUSTER x nH entries {distance bits, scene index}, one 16-byte store each
+  ulonglong2* s_inbox = reinterpret_cast<ulonglong2*>((reinterpret_cast<uintptr_t>(s_occ + 128) + 15) & ~(uintptr_t)15);
 
   const unsigned long long INF64 = 0xffffffffffffffffULL;
   for(int i = tid; i < nM; i += ICP_THREADS) { s_mx[i] = P.model[2 * i]; s_my[i] = P.model[2 * i + 1]; }
   for(int i = tid; i < nS; i += ICP_THREADS) { s_sx[i] = P.scene[2 * i]; s_sy[i] = P.scene[2 * i + 1]; }
   for(int i = tid; i < nQ; i += ICP_THREADS) s_lb[i] = 0.0;
+  for(int i = tid; i < ICP_CLUSTER * nH; i += ICP_THREADS) s_inbox[i] = make_ulonglong2(INF64, 0xffffffffULL);
   for(int i = tid; i < ICP_SLOTS; i += ICP_THREADS) s_bcnt[i] = 0;
   if(tid < 128) { s_coarse[tid] = 0u; s_occ[tid] = 0u; }
   if(tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0 : 0.0; s_T[16 + tid] = s_T[tid]; }
@@ -292,10 +293,15 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
     __syncthreads();
 
     // ---- A: pre-filter + exact 1-NN + distance filter, for the queries of this CTA ----
-    for(int q = quad; q < nQ; q += ICP_THREADS / 4)
+    // Four lanes per query scan the 3x3 cells around it (one pass for all queries: nQ <= ICP_THREADS / 4).  That
+    // settles every query with a model point within one cell edge.  The others are finished one after the other
+    // by their whole warp: the 32 lanes scan the rest of the (2R+1)^2 window that covers the distance filter's
+    // current radius, so that a few far-off points do not hold up the cluster.
     {
+      const int q = quad;
       const int i = q * ICP_CLUSTER + (int)rank;
-      const bool exists = i < nS;
+      const bool exists = q < nQ && i < nS;
+      const int lane = tid & 31;
       const double x = exists ? s_sx[i] : 0.0, y = exists ? s_sy[i] : 0.0;
       // OutOfBoundsFilter2D.cpp:27-37: S.transform(pose) = S * R^T + t
       double tx = 0.0; tx += x * P.pose[0]; tx += y * P.pose[1]; tx = 0.0 + 1.0 * tx; tx += P.pose[2];
@@ -326,54 +332,81 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
         if(!search) lbNew = P.coarse_h * (1.0 - 1e-6);  // nothing within one coarse cell
       }
       // (search, x, y are uniform over the four lanes of the query)
+      const int qx = cell_of(x, bx0, invh), qy = cell_of(y, by0, invh);
+      bool pending = false;
       if(search)
       {
-        const int qx = cell_of(x, bx0, invh), qy = cell_of(y, by0, invh);
-        for(int r = 1; r <= P.max_rings; r++)
+        for(int c = ql; c < 9; c += 4)
         {
-          // cells of ring r, dealt to the four lanes; the first pass also takes the centre cell (ring 0 can never
-          // end the search: its bound is 0)
-          const int side = 2 * r, count = 8 * r + (r == 1 ? 1 : 0);
-          for(int c = ql; c < count; c += 4)
+          const unsigned b = slot_of(qx - 1 + c % 3, qy - 1 + c / 3);
+          if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
+          const int k1 = s_bstart[b + 1];
+          for(int k = s_bstart[b]; k < k1; k++)
           {
-            int bx, by;
-            if(c == 8 * r) { bx = qx; by = qy; }
-            else
-            {
-              const int sd = c / side, off = c - sd * side;
-              bx = (sd == 0) ? qx - r + off : (sd == 1) ? qx + r : (sd == 2) ? qx + r - off : qx - r;
-              by = (sd == 0) ? qy - r : (sd == 1) ? qy - r + off : (sd == 2) ? qy + r : qy + r - off;
-            }
-            const unsigned b = slot_of(bx, by);
-            if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
-            const int k1 = s_bstart[b + 1];
-            for(int k = s_bstart[b]; k < k1; k++)
-            {
-              const int m = s_bidx[k];
-              const double d0 = x - s_mx[m];
-              const double d1 = y - s_my[m];
-              double d = 0.0;
-              d += d0 * d0;
-              d += d1 * d1;
-              if(d < bestD || (d == bestD && m < best)) { bestD = d; best = m; }
-            }
+            const int m = s_bidx[k];
+            const double d0 = x - s_mx[m];
+            const double d1 = y - s_my[m];
+            double d = 0.0;
+            d += d0 * d0;
+            d += d1 * d1;
+            if(d < bestD || (d == bestD && m < best)) { bestD = d; best = m; }
           }
+        }
 #pragma unroll
-          for(int o = 1; o < 4; o <<= 1)
+        for(int o = 1; o < 4; o <<= 1)
+        {
+          const double od = __shfl_xor_sync(qmask, bestD, o);
+          const int ob = __shfl_xor_sync(qmask, best, o);
+          if(ob >= 0 && (best < 0 || od < bestD || (od == bestD && ob < best))) { bestD = od; best = ob; }
+        }
+        // everything unvisited lies in cells at Chebyshev distance > 1, i.e. farther than h
+        const double lb = h * (1.0 - 1e-9);
+        const double lb2 = lb * lb;
+        if(bestD < lb2 || distSqr < lb2) lbNew = fmin(sqrt(bestD), lb) * (1.0 - 1e-9);  // shaved against rounding
+        else pending = true;
+      }
+      // smallest R with (R h)^2 > distSqr: the window then holds every point the distance filter can keep
+      int R = 2;
+      while(R < P.max_rings && !(distSqr < ((double)R * h * (1.0 - 1e-9)) * ((double)R * h * (1.0 - 1e-9)))) R++;
+      const int W = 2 * R + 1;
+      unsigned todo = __ballot_sync(0xffffffffu, pending && ql == 0);
+      while(todo)
+      {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const double px = __shfl_sync(0xffffffffu, x, src), py = __shfl_sync(0xffffffffu, y, src);
+        const int pqx = __shfl_sync(0xffffffffu, qx, src), pqy = __shfl_sync(0xffffffffu, qy, src);
+        double wd = __longlong_as_double(0x7ff0000000000000LL);
+        int wb = -1;
+        for(int c = lane; c < W * W; c += 32)
+        {
+          const int dx = c % W - R, dy = c / W - R;
+          if(dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) continue;  // done above
+          const unsigned b = slot_of(pqx + dx, pqy + dy);
+          if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
+          const int k1 = s_bstart[b + 1];
+          for(int k = s_bstart[b]; k < k1; k++)
           {
-            const double od = __shfl_xor_sync(qmask, bestD, o);
-            const int ob = __shfl_xor_sync(qmask, best, o);
-            if(ob >= 0 && (best < 0 || od < bestD || (od == bestD && ob < best))) { bestD = od; best = ob; }
+            const int m = s_bidx[k];
+            const double d0 = px - s_mx[m];
+            const double d1 = py - s_my[m];
+            double d = 0.0;
+            d += d0 * d0;
+            d += d1 * d1;
+            if(d < wd || (d == wd && m < wb)) { wd = d; wb = m; }
           }
-          // everything unvisited lies in cells at Chebyshev distance > r, i.e. farther than r*h
-          const double lb = (double)r * h * (1.0 - 1e-9);
-          const double lb2 = lb * lb;
-          if(bestD < lb2 || distSqr < lb2)
-          {
-            // nearest distance >= min(sqrt(bestD), lb), shaved by a relative 1e-9 against rounding
-            lbNew = fmin(sqrt(bestD), lb) * (1.0 - 1e-9);
-            break;
-          }
+        }
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1)
+        {
+          const double od = __shfl_xor_sync(0xffffffffu, wd, o);
+          const int ob = __shfl_xor_sync(0xffffffffu, wb, o);
+          if(ob >= 0 && (wb < 0 || od < wd || (od == wd && ob < wb))) { wd = od; wb = ob; }
+        }
+        if((lane & ~3) == src)
+        {
+          if(wb >= 0 && (best < 0 || wd < bestD || (wd == bestD && wb < best))) { bestD = wd; best = wb; }
+          lbNew = fmin(sqrt(bestD), (double)R * h * (1.0 - 1e-9)) * (1.0 - 1e-9);
         }
       }
       if(exists && ql == 0)
@@ -395,19 +428,36 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
       const int m = s_nn[q];
       if(m >= 0 && (unsigned long long)__double_as_longlong(s_d2[q]) == s_best[m]) atomicMin(&s_win[m], (unsigned)i);
     }
+    __syncthreads();
+    // the local winner of model point m goes to m's host: slot [this CTA][m / ICP_CLUSTER] of its inbox
+    for(int q = tid; q < nQ; q += ICP_THREADS)
+    {
+      const int i = q * ICP_CLUSTER + (int)rank;
+      if(i >= nS) continue;
+      const int m = s_nn[q];
+      if(m >= 0 && s_win[m] == (unsigned)i)
+      {
+        const unsigned host = m % ICP_CLUSTER, slot = rank * nH + m / ICP_CLUSTER;
+        dsmem_st_v2u64(dsmem_addr(s_inbox + slot, host), (unsigned long long)__double_as_longlong(s_d2[q]), (unsigned long long)i);
+      }
+    }
     cluster.sync();
-    // level 2: the host of model point m = k * ICP_CLUSTER + rank reads the ICP_CLUSTER local results, one lane each
+    // level 2: the host of model point m = k * ICP_CLUSTER + rank picks the winner among the ICP_CLUSTER candidates
+    // (lane l of a group looks at CTA l's), clears its inbox and tells every CTA (lane l tells CTA l)
     for(int k0 = 0; k0 < nH; k0 += ICP_THREADS / ICP_CLUSTER)
     {
       const int k = k0 + tid / ICP_CLUSTER;
-      const unsigned src = tid % ICP_CLUSTER;
+      const unsigned peer = tid % ICP_CLUSTER;
       const int m = k * ICP_CLUSTER + (int)rank;
+      const bool hosted = k < nH && m < nM;
       unsigned long long bd = INF64;
       unsigned wi = 0xffffffffu;
-      if(k < nH && m < nM)
+      if(hosted)
       {
-        bd = dsmem_ld_u64(dsmem_addr(s_best + m, src));
-        wi = dsmem_ld_u32(dsmem_addr(s_win + m, src));
+        const ulonglong2 e = s_inbox[peer * nH + k];
+        bd = e.x;
+        wi = (unsigned)e.y;
+        s_inbox[peer * nH + k] = make_ulonglong2(INF64, 0xffffffffULL);
       }
 #pragma unroll
       for(int o = 1; o < ICP_CLUSTER; o <<= 1)
@@ -416,7 +466,7 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
         const unsigned ow = __shfl_xor_sync(0xffffffffu, wi, o);
         if(ob < bd || (ob == bd && ow < wi)) { bd = ob; wi = ow; }
       }
-      if(src == 0 && k < nH) s_fin[k] = (bd == INF64) ? 0xffffffffu : wi;
+      if(hosted) dsmem_st_u32(dsmem_addr(s_fin + m, peer), (bd == INF64) ? 0xffffffffu : wi);
     }
     cluster.sync();
     // DistanceFilter.cpp:62-63
@@ -424,14 +474,14 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
     if(distSqr < P.min_dist_sqr) distSqr = P.min_dist_sqr;
 
     // ---- C: ClosedFormEstimator2D::setPairs (+ the pair list in model order when tracing) ----
-    // (replicated: every CTA reads all winners, one distributed-shared-memory load per model point)
+    // (replicated: every CTA holds all winners)
     double acc[6] = {0, 0, 0, 0, 0, 0};  // cm0 cm1 cs0 cs1 r count
     unsigned winOf[(ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS];
 #pragma unroll
     for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
     {
       const int m = tid + j * ICP_THREADS;
-      winOf[j] = (m < nM) ? dsmem_ld_u32(dsmem_addr(s_fin + m / ICP_CLUSTER, m % ICP_CLUSTER)) : 0xffffffffu;
+      winOf[j] = (m < nM) ? s_fin[m] : 0xffffffffu;
     }
     if(P.trace && rank == 0)
     {
@@ -595,7 +645,8 @@ static size_t icp_smem_bytes(int nM, int nS)
   b += sizeof(double) * (2 * (size_t)nM + 2 * (size_t)nS + 2 * nQ);  // mx my sx sy d2 lb
   b += sizeof(unsigned long long) * nM;                            // best
   b += sizeof(double) * (208 + 32);                               // red + T
-  b += sizeof(unsigned) * ((size_t)nM + nH) + sizeof(int) * nQ + sizeof(unsigned) * 40;
+  b += sizeof(unsigned) * (2 * (size_t)nM) + sizeof(int) * nQ + sizeof(unsigned) * 40;
+  b += 16 * ICP_CLUSTER * nH + 16;                                 // inbox
   b += sizeof(unsigned short) * (ICP_SLOTS + 2 + ICP_SLOTS + (size_t)nM + 2) + sizeof(unsigned) * 256;
   return b + 64;
 }
