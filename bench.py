@@ -275,7 +275,8 @@ def run_cuda(args):
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.workload, steps=1, warmup=0, threads=None)
+            b = cpu_baseline(args.workload, steps=100000, warmup=1, threads=None, budget_s=12.0)  # ~12 s of CPU work
+            line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -296,7 +297,7 @@ def profiled_traffic(kernel: str):
     return None, None
 
 
-def cpu_baseline(workload: str, steps: int, warmup: int, threads):
+def cpu_baseline(workload: str, steps: int, warmup: int, threads, budget_s=None):
     """The reference's own push (oracle/_ref, compiled from the reference sources) or, where that prebuilt
     library is absent, the plain-C port, on the host cores; bounded sample of the same workload."""
     from ohm_tsd_slam_b200.workload import DoubleLaserWorkload
@@ -325,7 +326,10 @@ def cpu_baseline(workload: str, steps: int, warmup: int, threads):
         g.set_max_truncation(cfg.max_truncation)
         push = g.push
         kind = "port"
-    pg = port.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)  # counts cell updates (the reference does not)
+    # Cell updates per push are a function of the scan and of the allocation state only (dense regime: everything
+    # allocated), so they repeat with the scan cycle: count them once per scan with the port (the reference keeps
+    # no such statistic), on a second grid that sees the same pushes.
+    pg = port.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)
     pg.set_max_truncation(cfg.max_truncation)
     for sc in wl.map_scans:
         push(sc)
@@ -333,32 +337,44 @@ def cpu_baseline(workload: str, steps: int, warmup: int, threads):
     g.fill(1.0, 1.0, only_uninitialized=True)
     pg.fill(1.0, 1.0, only_uninitialized=True)
     n_steps = len(wl.step_scans)
-    for i in range(warmup):
+    counts = []
+    for i in range(n_steps):
+        c = []
+        for sc in wl.step_scans[i]:
+            pg.push(sc)
+            c.append(pg.last_push_stats()["cell_updates"])
+        counts.append(c)
+    for i in range(max(warmup, 1)):
         for sc in wl.step_scans[i % n_steps]:
             push(sc)
-            pg.push(sc)
     updates = 0
     t = 0.0
+    done = 0
     for i in range(steps):
-        for sc in wl.step_scans[i % n_steps]:
+        for k, sc in enumerate(wl.step_scans[i % n_steps]):
             t0 = time.perf_counter()
             push(sc)
             t += time.perf_counter() - t0
-            pg.push(sc)
-            updates += pg.last_push_stats()["cell_updates"]
-    return {"value": updates / t / 1e9, "unit": UNIT, "cores": nthreads, "kind": kind,
-            "sample": f"{2 * steps} TsdGrid::push calls ({steps} step(s)) of the same workload after the same map build, "
+            updates += counts[i % n_steps][k]
+        done += 1
+        if budget_s is not None and t >= budget_s and done >= 3:
+            break
+    return {"value": updates / t / 1e9, "unit": UNIT, "cores": nthreads, "kind": kind, "steps": done,
+            "sample": f"{2 * done} TsdGrid::push calls ({done} step(s)) of the same workload after the same map build, "
                       f"{updates} cell updates, {t:.2f} s on {nthreads} thread(s) of {cores} host cores",
-            "ms_per_step": t / steps * 1e3}
+            "ms_per_step": t / done * 1e3}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warmup = max(0, min(args.warmup, 1))
-    b = cpu_baseline(args.workload, steps=steps, warmup=warmup, threads=None)
+    # a step = one scan cycle of both lasers (two pushes, ~35 ms on 16 cores): K steps as asked, capped so that the
+    # run ends within a few minutes
+    steps = max(1, min(args.steps, 5000))
+    warmup = max(0, min(args.warmup, 20))
+    b = cpu_baseline(args.workload, steps=steps, warmup=warmup, threads=None, budget_s=150.0)
+    steps = b["steps"]  # (fewer than asked only if 150 s of pushes were not enough)
     from ohm_tsd_slam_b200.workload import DoubleLaserWorkload
     wl = DoubleLaserWorkload(args.workload, invert=lambda T: np.eye(3), n_map=0, n_steps=1)
     line = {
@@ -376,7 +392,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="C2")

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turn the ncu outputs a gpurun call left in gpurun_out/ into the tracked summary under profiles/.
 
-  python profiles/summarize.py r01            # reads gpurun_out/r01_launches.csv + gpurun_out/r01_full.ncu-rep
+  python profiles/summarize.py r01            # reads gpurun_out/r01_launches.csv + gpurun_out/r01_full*.ncu-rep
 
 Writes profiles/<round>_launches.csv (copy of the launch list), profiles/<round>_summary.md (tables) and
 profiles/<round>_metrics.json (per-kernel means of the raw-page metrics, used for bench.py's roofline.traffic).
@@ -30,7 +30,7 @@ def launch_table(path, out):
     rows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[0].isdigit()]
     per = collections.defaultdict(list)
     for r in rows:
-        per[r[4].split("(")[0]].append(float(r[14]) / 1e3)
+        per[r[4].split("(")[0].split("<")[0].replace("void ", "")].append(float(r[14]) / 1e3)
     tot = sum(sum(v) for v in per.values())
     out.append("| kernel | launches | mean us | min us | max us | share of listed GPU time |")
     out.append("|---|---|---|---|---|---|")
@@ -51,7 +51,7 @@ def raw_tables(rep, out):
     idx = {h: i for i, h in enumerate(hdr)}
     agg = collections.defaultdict(lambda: collections.defaultdict(list))
     for r in rr[2:]:
-        k = r[idx["Kernel Name"]].split("(")[0]
+        k = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
         for w in WANT:
             if w in idx:
                 try:
@@ -131,7 +131,9 @@ def stall_table(rep, kernel, out, top=14):
 def main():
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     go = os.path.join(ROOT, "gpurun_out")
-    launches, rep = os.path.join(go, f"{rnd}_launches.csv"), os.path.join(go, f"{rnd}_full.ncu-rep")
+    import glob
+    launches = os.path.join(go, f"{rnd}_launches.csv")
+    reps = sorted(glob.glob(os.path.join(go, f"{rnd}_full*.ncu-rep")))
     out = [f"# {rnd}: ncu summary\n"]
     if os.path.exists(launches):
         shutil.copy(launches, os.path.join(ROOT, "profiles", f"{rnd}_launches.csv"))
@@ -140,12 +142,14 @@ def main():
                    " Per-launch times are cold-cache and serialised: compare shares, not absolutes. Full list: `" + f"{rnd}_launches.csv`.\n")
         launch_table(launches, out)
     metrics = {}
-    if os.path.exists(rep):
-        out.append("\n## ncu --set full (per launch, mean over the captured launches)\n")
-        metrics = raw_tables(rep, out)
-        for k in metrics:
-            if k in ("k_update", "k_raycast", "k_icp", "k_classify"):
-                stall_table(rep, k, out)
+    for rep in reps:
+        out.append(f"\n## ncu --set full, {os.path.basename(rep)} (per launch, mean over the captured launches)\n")
+        m = raw_tables(rep, out)
+        for k in m:
+            if k.split("<")[0] in ("k_update", "k_raycast", "k_icp", "k_classify"):
+                stall_table(rep, k.split("<")[0], out)
+        metrics.update({k.split("<")[0]: v for k, v in m.items()})
+    if metrics:
         json.dump(metrics, open(os.path.join(ROOT, "profiles", f"{rnd}_metrics.json"), "w"), indent=1)
     extra = os.path.join(ROOT, "profiles", f"{rnd}_notes.md")
     if os.path.exists(extra):
