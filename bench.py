@@ -231,6 +231,11 @@ def run_cuda(args):
             icp_out = icp.run(c[m > 0], nrm[m > 0], scene, sc0.pose)
         icp_ms = (time.perf_counter() - t0) / reps * 1e3
 
+    # ---------------- hypothesis scoring (BASELINE.json configs[3]: 10^5 hypotheses per scan; split over the ranks)
+    from ohm_tsd_slam_b200.workload import hypothesis_benchmark
+    hyp = hypothesis_benchmark(device=local, n_hyp=100000, reps=2, dist=dist if world > 1 else None,
+                               cpu_sample=0 if (args.no_cpu_baseline or world > 1) else 1000)
+
     launches = capi.kernel_launches() - launches0
 
     # max over ranks of the timed durations, sum of the work
@@ -271,6 +276,7 @@ def run_cuda(args):
                             "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
                             "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(pushes_per_step, 1)) if icp_ms else None,
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
+            "hypothesis_scoring": hyp,
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall,
         }

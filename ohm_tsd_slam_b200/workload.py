@@ -117,3 +117,164 @@ class MultiRobotWorkload:
             "pushes_per_step": 2 * self.n,
             "l2_policy": f"cell state per GPU ({band_bytes / 1e9:.1f} GB) is larger than L2 (126 MB): inputs larger than L2, no flush",
         }
+
+
+class HypothesisWorkload:
+    """BASELINE.json configs[3] (SURVEY.md 8d "C4"): one C1 scan, 10^5 pose hypotheses (model index, scene index),
+    a control set of 360 scene points, for the three scorers.  The matcher's pre-processing stays on the host in the
+    reference (RandomMatching.cpp:41-183); here the inputs are built with plain numpy: orientations by central
+    differences over the beam neighbours (the scorers only need *an* orientation per point), control set = the
+    first 360 valid scene points at a stride, hypotheses = all valid (model, scene) index pairs inside the angular
+    window, in canonical order, truncated / repeated to exactly n_hyp."""
+
+    PDF_PARAMS = np.array([0.45, 0.0, 0.25, 0.05, 0.25, 0.9, 20.0, np.pi / 180.0 * 3, 0.2, 0.08, 3.0, 0.5])  # PDFMatching ctor defaults
+
+    def __init__(self, model_xy, model_mask, scene_xy, scene_mask, spec, n_hyp: int = 100000, n_control: int = 360,
+                 phi_max: float = math.radians(30.0)):
+        M, S = np.asarray(model_xy, dtype=np.float64), np.asarray(scene_xy, dtype=np.float64)
+        n = len(M)
+        assert len(S) == n
+        self.M, self.S = M, S
+
+        def orientation(P, mask):
+            d = np.zeros_like(P)
+            d[1:-1] = P[2:] - P[:-2]
+            ok = np.zeros(n, dtype=bool)
+            ok[1:-1] = (mask[2:] > 0) & (mask[:-2] > 0) & (mask[1:-1] > 0)
+            # normal = tangent rotated by -90 deg; its angle
+            return np.where(ok, np.arctan2(-d[:, 0], d[:, 1]), 0.0), ok
+
+        self.phi_m, ok_m = orientation(M, np.asarray(model_mask))
+        self.phi_s, ok_s = orientation(S, np.asarray(scene_mask))
+        self.idx_m_valid = np.nonzero(ok_m)[0].astype(np.int32)
+        idx_s = np.nonzero(ok_s)[0]
+        stride = max(1, len(idx_s) // n_control)
+        self.idx_control = idx_s[::stride][:n_control].astype(np.int32)
+        C = len(self.idx_control)
+        self.control = np.ones((3, C))
+        self.control[0] = S[self.idx_control, 0]
+        self.control[1] = S[self.idx_control, 1]
+        self.phi_control = self.phi_s[self.idx_control]
+        self.phi_max = phi_max
+        span = int(phi_max / spec.angular_res)
+        pairs = []
+        for im in self.idx_m_valid:
+            lo, hi = max(0, im - span), min(n - 1, im + span)
+            js = idx_s[(idx_s >= lo) & (idx_s <= hi)]
+            pairs.append(np.stack([np.full(len(js), im), js], axis=1))
+            if sum(len(p) for p in pairs) >= n_hyp:
+                break
+        h = np.concatenate(pairs).astype(np.int32)
+        reps = -(-n_hyp // len(h))
+        self.hyps = np.ascontiguousarray(np.tile(h, (reps, 1))[:n_hyp])
+        self.model_valid = M[self.idx_m_valid]
+        self.phi_valid = self.phi_m[self.idx_m_valid]
+        self.model_angles = np.arctan2(self.model_valid[:, 1], self.model_valid[:, 0])
+        self.model_dists = np.hypot(self.model_valid[:, 0], self.model_valid[:, 1])
+        self.theta_min, self.theta_max = spec.phi_min, spec.phi_min + spec.angular_res * (spec.beams - 1)
+
+    def run_tsd(self, matcher, grid, pose, hyps=None):
+        return matcher.score_tsd(grid, self.hyps if hyps is None else hyps, self.M, self.S, self.phi_m, self.phi_s, self.phi_max,
+                                 self.control, pose, 0.25)
+
+    def run_rnm(self, matcher, hyps=None):
+        return matcher.score_rnm(self.hyps if hyps is None else hyps, self.M, self.S, self.phi_m, self.phi_s, self.phi_max,
+                                 self.control, self.phi_control, self.model_valid, self.phi_valid, self.theta_min,
+                                 self.theta_max, 1.0 / 0.15 ** 2, 0.33, self.control.shape[1] // 3)
+
+    def run_pdf(self, matcher, hyps=None):
+        return matcher.score_pdf(self.hyps if hyps is None else hyps, self.M, self.S, self.phi_m, self.phi_s, self.phi_max,
+                                 self.control, self.model_angles, self.model_dists, self.PDF_PARAMS)
+
+
+def hypothesis_benchmark(device: int = 0, n_hyp: int = 100000, reps: int = 3, dist=None, cpu_sample: int = 0):
+    """C4 on the device: a C1 map, one scan, n_hyp hypotheses through the three scorers (C ABI, host buffers:
+    H2D of hypotheses + control set and D2H of the per-hypothesis results inside the timing).  With `dist`
+    (torch.distributed, one rank per GPU) the hypothesis list is split in contiguous slices and the winner merged
+    (sharded.merge_best_hypothesis); times are the max over ranks.  cpu_sample > 0 also times the oracle's port on
+    that many hypotheses (bench.py's cpu_baseline leg only)."""
+    import time
+
+    from . import capi
+    from .sharded import merge_best_hypothesis
+
+    cfg = synth.config("C1")
+    g = capi.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid, device=device)
+    g.set_max_truncation(cfg.max_truncation)
+    hs = HostSensor(cfg.sensor, capi.invert3x3)
+    scans = list(cfg.scans(4))
+    for pose, r in scans[:3]:
+        hs.set_scan(r)
+        hs.T = np.eye(3)
+        hs.rays = hs.rays_local.copy()
+        hs.ray_norm = 1.0
+        hs.transform(synth.pose_matrix(*pose))
+        g.push(hs.scan())
+    pose, r = scans[3]
+    hs.set_scan(r)
+    hs.T = np.eye(3)
+    hs.rays = hs.rays_local.copy()
+    hs.ray_norm = 1.0
+    hs.transform(synth.pose_matrix(*pose))
+    sc = hs.scan()
+    M, _, mM, _ = g.raycast_mask(sc, hs.normalized_rays(cfg.cell_size).copy())
+    S, mS, _ = hs.scene()
+    wl = HypothesisWorkload(M, mM, S, mS, cfg.sensor, n_hyp=n_hyp)
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    lo, hi = rank * n_hyp // world, (rank + 1) * n_hyp // world
+    mine = np.ascontiguousarray(wl.hyps[lo:hi])
+    mt = capi.Matcher(device)
+    out = {"n_hypotheses": n_hyp, "control_points": int(wl.control.shape[1]), "model_points_valid": int(len(wl.model_valid)),
+           "n_gpus": world}
+
+    def amax(t):
+        import torch
+        tt = t.cuda()
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t.copy_(tt.cpu())
+
+    runs = {"tsd": lambda h: wl.run_tsd(mt, g, hs.pose, h), "rnm": lambda h: wl.run_rnm(mt, h), "pdf": lambda h: wl.run_pdf(mt, h)}
+    for name, fn in runs.items():
+        fn(mine)
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            res = fn(mine)
+            if dist:
+                score = res[0] if name != "rnm" else res[2]
+                b = res[1] if name == "tsd" else (res[3] if name == "rnm" else res[2])
+                merge_best_hypothesis(float(max(score[b], 0.0)) if b >= 0 else 0.0, lo + b if b >= 0 else -1, amax)
+        dt = (time.perf_counter() - t0) / reps
+        if dist:
+            import torch
+            t = torch.tensor([dt], dtype=torch.float64)
+            amax(t)
+            dt = float(t[0])
+        out[name] = {"ms": dt * 1e3, "hypotheses_per_s": n_hyp / dt}
+    if cpu_sample > 0:
+        from oracle import port  # (bench.py cpu_baseline leg)
+        gp = port.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)
+        gp.set_max_truncation(cfg.max_truncation)
+        hp = HostSensor(cfg.sensor, port.invert3x3)
+        for pose2, r2 in scans[:3]:
+            hp.set_scan(r2)
+            hp.T = np.eye(3)
+            hp.rays = hp.rays_local.copy()
+            hp.ray_norm = 1.0
+            hp.transform(synth.pose_matrix(*pose2))
+            gp.push(hp.scan())
+        h = wl.hyps[:cpu_sample]
+        cpu = {}
+        t0 = time.perf_counter()
+        port.score_tsd(gp, h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, hs.pose, 0.25)
+        cpu["tsd"] = cpu_sample / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        port.score_rnm(h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, wl.phi_control, wl.model_valid, wl.phi_valid,
+                       wl.theta_min, wl.theta_max, 1.0 / 0.15 ** 2, 0.33, wl.control.shape[1] // 3)
+        cpu["rnm"] = cpu_sample / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        port.score_pdf(h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, wl.model_angles, wl.model_dists, wl.PDF_PARAMS)
+        cpu["pdf"] = cpu_sample / (time.perf_counter() - t0)
+        out["cpu_port_hypotheses_per_s"] = dict(cpu, sample=cpu_sample, cores=1)
+    return out
