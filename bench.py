@@ -236,6 +236,12 @@ def run_cuda(args):
     hyp = hypothesis_benchmark(device=local, n_hyp=100000, reps=2, dist=dist if world > 1 else None,
                                cpu_sample=0 if (args.no_cpu_baseline or world > 1) else 1000)
 
+    # ---------------- large-map push sweep (BASELINE.json configs[2]): the bandwidth regime of the push
+    sweep = None
+    if world == 1 and not args.no_sweep:
+        from ohm_tsd_slam_b200.workload import large_grid_sweep
+        sweep = large_grid_sweep(device=local, layout_grid=14, peak_gbs=measured_peak()[0])
+
     launches = capi.kernel_launches() - launches0
 
     # max over ranks of the timed durations, sum of the work
@@ -277,6 +283,7 @@ def run_cuda(args):
                             "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(pushes_per_step, 1)) if icp_ms else None,
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
             "hypothesis_scoring": hyp,
+            "large_grid_sweep": sweep,
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall,
         }
@@ -403,6 +410,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 16384^2 push sweep (4.6 GB of HBM, a few seconds)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "reference":

@@ -278,3 +278,59 @@ def hypothesis_benchmark(device: int = 0, n_hyp: int = 100000, reps: int = 3, di
         cpu["pdf"] = cpu_sample / (time.perf_counter() - t0)
         out["cpu_port_hypotheses_per_s"] = dict(cpu, sample=cpu_sample, cores=1)
     return out
+
+
+def large_grid_sweep(device: int = 0, layout_grid: int = 14, rooms=(40.0, 80.0, 160.0, 320.0, 380.0), reps: int = 5,
+                     peak_gbs: float | None = None):
+    """BASELINE.json configs[2] (SURVEY.md 8d "C3"): pushes into a 16384^2 grid, dense regime (every partition
+    allocated), with a 250 m sensor in the middle of an empty square room of growing size, so that the share of
+    the map one push rewrites sweeps from ~1 % to most of the field of view.  Free space far from the sensor is
+    classified "empty" and streamed by K3 (33x33 cells per partition): the bandwidth regime of the push.
+    Returns one row per room: tiles, updates, kernel times (CUDA events inside the library), Gcell-updates/s and
+    algorithmic GB/s (32 B per update) of the whole push and of k_update alone."""
+    import torch
+
+    from . import capi
+
+    spec = synth.SensorSpec(max_range=250.0)
+    cell = 0.025
+    g = capi.Grid(cell, 5, layout_grid, device=device)
+    g.set_max_truncation(3 * cell)
+    g.fill(1.0, 1.0)
+    g.set_timing(True)
+    side = (1 << layout_grid) * cell
+    stream = torch.cuda.ExternalStream(g.stream_ptr, device=torch.device("cuda", device))
+    rows = []
+    for k, room in enumerate(rooms):
+        world = synth.World.room_with_obstacles(side / 2, side / 2, room, room, 0, 1)
+        rng = np.random.default_rng(100 + k)
+        hs = HostSensor(spec, capi.invert3x3)
+        hs.set_scan(synth.scan_from_pose(world, spec, side / 2, side / 2, 0.3, rng))
+        hs.T = np.eye(3)
+        hs.rays = hs.rays_local.copy()
+        hs.ray_norm = 1.0
+        hs.transform(synth.pose_matrix(side / 2, side / 2, 0.3))
+        sc = hs.scan()
+        for _ in range(2):
+            g.push(sc)
+        g.stage_scan(sc)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.sync()
+        e0.record(stream)
+        for _ in range(reps):
+            g.push_staged()
+        e1.record(stream)
+        g.sync()
+        ms = e0.elapsed_time(e1) / reps
+        st, km = g.last_push_stats(), g.last_push_kernel_ms()
+        upd = st["cell_updates"]
+        row = {"room_m": room, "active_tiles": st["active_tiles"], "emptied_tiles": st["emptied_tiles"],
+               "tile_share": (st["active_tiles"] + st["emptied_tiles"]) / float(g.n_partitions), "cell_updates": upd,
+               "push_ms": ms, "classify_ms": km["classify"], "update_ms": km["update"],
+               "gcell_updates_per_s": upd / ms / 1e6, "algorithmic_gbs": 32.0 * upd / ms / 1e6,
+               "k_update_algorithmic_gbs": 32.0 * upd / km["update"] / 1e6}
+        if peak_gbs:
+            row["k_update_frac_of_hbm_peak"] = row["k_update_algorithmic_gbs"] / peak_gbs
+        rows.append(row)
+    return {"grid": f"{1 << layout_grid}x{1 << layout_grid} @ 2.5 cm, dense, {g.n_partitions} partitions, sensor 270 deg / 250 m",
+            "rows": rows}
