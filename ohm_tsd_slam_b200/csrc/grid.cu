@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
 }
 
 #define UPDATE_THREADS 256
+#define ITEM_CHUNK 32  // items whose metadata k_update fetches at a time
 #ifndef UPDATE_CTAS_PER_SM
 #define UPDATE_CTAS_PER_SM 3
 #endif
@@ -485,32 +486,8 @@ __device__ __forceinline__ void empty_pair(double2& tv, double2& wv)
 // rewrites stores its own first column / row / cell into the strips of its -x, -y, -xy neighbours that mirror
 // them.  What is left for k_borders is to *pull* the strips of partitions that became initialised outside this
 // mechanism (allocated by this push, by freeFootprint or by an upload).
-__device__ __forceinline__ bool strip_has_source(const PushParams& pp, int p, int px, int py, int b)
-{
-  if(b < 32) return px < pp.parts_x - 1 && pp.flags[p + 1];
-  if(b < 64) return py < pp.parts_y - 1 && pp.flags[p + pp.parts_x];
-  return px < pp.parts_x - 1 && py < pp.parts_y - 1 && pp.flags[p + pp.parts_x + 1];
-}
-
-// Allocation flags of the -x / -y / -xy neighbours of partition e (0 where the neighbour is outside this grid /
-// band).  Loaded one item ahead of their use (mirror_to_neighbours), only by the threads that own a first-column
-// or first-row cell.
-struct MirrorFlags { unsigned x, y, xy; };
-__device__ __forceinline__ MirrorFlags load_mirror_flags(const PushParams& pp, uint32_t e, bool edge)
-{
-  MirrorFlags f = {0u, 0u, 0u};
-  if(edge && e != 0xffffffffu)
-  {
-    const int p = (int)(e & 0x7fffffffu);
-    const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
-    const bool hasX = px > 0, hasY = py > pp.row_begin;
-    if(hasX) f.x = pp.flags[p - 1];
-    if(hasY) f.y = pp.flags[p - pp.parts_x];
-    if(hasX && hasY) f.xy = pp.flags[p - pp.parts_x - 1];
-  }
-  return f;
-}
-
+// Which neighbours exist and are allocated comes as a bit mask per item (k_update's chunk prologue): bits 0-2 the
+// mirror targets -x / -y / -xy (inside this grid or band), bits 3-5 the border sources +x / +y / +xy.
 // thread (xp, y) holds the final values of cells (y, xp) and (y, xp + 1) of the partition at `base`
 __device__ __forceinline__ void mirror_to_neighbours(const PushParams& pp, unsigned nb, size_t base, int xp, int y,
                                                      const double2& tv, const double2& wv)
@@ -586,28 +563,59 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
   };
 
   // Static striding over the item list (a ticket counter with one __syncthreads per item was measured slower:
-  // 55 us vs 48 us on C2).  The list entries are fetched two items ahead, the neighbour flags one item ahead.
+  // 55 us vs 48 us on C2).  The per-item metadata -- list entry, partition weight, which neighbours are allocated
+  // (mirror targets -x/-y/-xy, border sources +x/+y/+xy) -- is fetched for 32 items at a time by the first warp
+  // and parked in shared memory: one memory round trip and two barriers per 32 items instead of dependent global
+  // loads in front of every item (on maps beyond L2 those were half of all stall samples).
   const uint32_t G = gridDim.x;
-  uint32_t eCur = entry(blockIdx.x);
-  uint32_t eNext = entry(blockIdx.x + G);
-  MirrorFlags mfCur = load_mirror_flags(pp, eCur, edge);
-  stage_in(eCur, 0);
+  __shared__ uint32_t s_ent[ITEM_CHUNK + 1];
+  __shared__ uint32_t s_nbm[ITEM_CHUNK];
+  __shared__ double s_wt[ITEM_CHUNK];
   int stage = 0;
-  for(uint32_t item = blockIdx.x; item < nItems; item += G, stage ^= 1)
+  for(uint32_t chunk0 = blockIdx.x; chunk0 < nItems; chunk0 += ITEM_CHUNK * G)
   {
-    const uint32_t eNext2 = entry(item + 2 * G);
-    const MirrorFlags mfNext = load_mirror_flags(pp, eNext, edge);
-    stage_in(eNext, stage ^ 1);
+    __syncthreads();  // the previous chunk is consumed
+    if(t <= ITEM_CHUNK)
+    {
+      const uint32_t it = chunk0 + (uint32_t)t * G;
+      const uint32_t e = entry(it);
+      s_ent[t] = e;
+      if(t < ITEM_CHUNK && e != 0xffffffffu)
+      {
+        s_wt[t] = (it < nActive) ? pp.active_w[it] : 0.0;
+        const int p = (int)(e & 0x7fffffffu);
+        const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
+        const bool hasL = px > 0, hasD = py > pp.row_begin;
+        const bool hasR = px < pp.parts_x - 1, hasU = py < pp.parts_y - 1;
+        unsigned m = 0;
+        if(hasL && pp.flags[p - 1]) m |= 1u;
+        if(hasD && pp.flags[p - pp.parts_x]) m |= 2u;
+        if(hasL && hasD && pp.flags[p - pp.parts_x - 1]) m |= 4u;
+        if(hasR && pp.flags[p + 1]) m |= 8u;
+        if(hasU && pp.flags[p + pp.parts_x]) m |= 16u;
+        if(hasR && hasU && pp.flags[p + pp.parts_x + 1]) m |= 32u;
+        s_nbm[t] = m;
+      }
+    }
+    __syncthreads();
+    if(chunk0 == blockIdx.x) stage_in(s_ent[0], 0);
+    for(int k = 0; k < ITEM_CHUNK; k++, stage ^= 1)
+    {
+    const uint32_t item = chunk0 + (uint32_t)k * G;
+    if(item >= nItems) break;
+    const uint32_t eCur = s_ent[k];
+    stage_in(s_ent[k + 1], stage ^ 1);
+    const unsigned nbm = s_nbm[k];
+    const unsigned nb = edge ? (nbm & 7u) : 0u;
     const uint32_t p = eCur & 0x7fffffffu;
     const bool wasInit = (eCur & 0x80000000u) != 0;
     const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
     const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
     double* T = pp.tsd + base;
     double* W = pp.weight + base;
-    const unsigned nb = (mfCur.x ? 1u : 0u) | (mfCur.y ? 2u : 0u) | (mfCur.xy ? 4u : 0u);
     if(item < nActive)
     {
-      const double wTile = pp.active_w[item];
+      const double wTile = s_wt[k];
       const int gx = px * TSD_TILE + xp;
       const int gy = py * TSD_TILE + yb;
       const double2 cA = *reinterpret_cast<const double2*>(pp.coltab + gx);
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
         }
         if(nb) mirror_to_neighbours(pp, nb, base, xp, y, tv, wv);
       }
-      if(!wasInit && t < 65 && !strip_has_source(pp, (int)p, px, py, t))
+      if(!wasInit && t < 65 && !((nbm >> (t < 32 ? 3 : (t < 64 ? 4 : 5))) & 1u))
       {
         T[TSD_BORDER_OFF + t] = initT;
         W[TSD_BORDER_OFF + t] = initW;
@@ -676,7 +684,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
         *reinterpret_cast<double2*>(W + ci) = wv;
         if(nb) mirror_to_neighbours(pp, nb, base, xp, y, tv, wv);
       }
-      if(t < 65 && !strip_has_source(pp, (int)p, px, py, t))
+      if(t < 65 && !((nbm >> (t < 32 ? 3 : (t < 64 ? 4 : 5))) & 1u))
       {
         double tv = T[TSD_BORDER_OFF + t], wv = W[TSD_BORDER_OFF + t];
         empty_cell(tv, wv);
@@ -685,9 +693,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
       }
       if(t == 0) updatesWide += 33 * 33;
     }
-    eCur = eNext;
-    eNext = eNext2;
-    mfCur = mfNext;
+    }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 
