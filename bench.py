@@ -164,7 +164,7 @@ def run_cuda(args):
     def host_step(i, count=None):
         for sc in wl.step_scans[i % n_steps]:
             if band:
-                mine = band.note_scan(grid.scan_box(sc))
+                mine = band.note_scan(band._box(sc))
                 band.flags_dirty = True
                 if not mine:
                     continue

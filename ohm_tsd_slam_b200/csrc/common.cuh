@@ -223,6 +223,7 @@ struct tsd_grid
   double cell_size, inv_cell_size, max_truncation;
   double min_x, max_x, min_y, max_y;
   bool pushed_once;
+  bool stats_fresh;                // h_counters holds the statistics of the last push (blocking tsdg_push)
 
   double* d_tsd;
   double* d_weight;

@@ -826,6 +826,8 @@ __device__ __forceinline__ void push_tail(const PushParams& pp)
 {
   for(int i = 0; i < 8; i++) pp.counters[8 + i] = pp.counters[i];
   pp.stats64[1] = pp.stats64[0];
+  pp.counters[20] = (uint32_t)(pp.stats64[0] & 0xffffffffULL);  // the same figure next to the counters: one D2H copy
+  pp.counters[21] = (uint32_t)(pp.stats64[0] >> 32);
   for(int i = 0; i < 8; i++) pp.counters[i] = 0;
   pp.counters[18] = 0;
   pp.stats64[0] = 0;
@@ -1334,7 +1336,7 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMalloc(&g->d_stats64, sizeof(unsigned long long) * 4));
   TSD_CUDA(cudaMalloc(&g->d_coltab, sizeof(double) * 3 * g->cells_x));
   TSD_CUDA(cudaMalloc(&g->d_rowtab, sizeof(double) * 3 * g->cells_y));
-  TSD_CUDA(cudaMallocHost(&g->h_counters, sizeof(uint32_t) * 16));
+  TSD_CUDA(cudaMallocHost(&g->h_counters, sizeof(uint32_t) * 32));
   TSD_CUDA(cudaMallocHost(&g->h_stats64, sizeof(unsigned long long) * 4));
   TSD_CUDA(cudaMemsetAsync(g->d_flags, 0, g->n_parts, g->stream));
   TSD_CUDA(cudaMemsetAsync(g->d_initw, 0, sizeof(double) * g->n_parts, g->stream));
@@ -1470,6 +1472,7 @@ int tsdg_push_staged(tsd_grid_t* g)
   PushParams pp = make_params(g);
   pp.scan = g->staged;
   pp.dirs = g->d_dirs;
+  g->stats_fresh = false;
   const tsd::ScanDev* scan = &g->staged;
   // counters [0] active [1] emptied are per push; [2] pending and [3] refresh-all persist until consumed below
   // (pending [2] and refresh-all [3] were zeroed by the previous push's tail; [0..1], [4..7] and the 64-bit
@@ -1771,17 +1774,23 @@ int tsdg_push(tsd_grid_t* g, const tsd_scan_t* scan)
 {
   int rc = tsdg_push_async(g, scan);
   if(rc) return rc;
-  return tsdg_sync(g);
+  // the blocking call brings the push statistics back with its one synchronisation
+  TSD_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(uint32_t) * 24, cudaMemcpyDeviceToHost, g->stream));
+  rc = tsdg_sync(g);
+  g->stats_fresh = (rc == TSD_OK);
+  return rc;
 }
 
 int tsdg_last_push_stats(tsd_grid_t* g, tsd_push_stats_t* out)
 {
   if(!g || !out) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
-  TSD_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(uint32_t) * 16, cudaMemcpyDeviceToHost, g->stream));
-  TSD_CUDA(cudaMemcpyAsync(g->h_stats64, g->d_stats64, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, g->stream));
-  TSD_CUDA(cudaStreamSynchronize(g->stream));
-  out->cell_updates = g->h_stats64[1];
+  if(!g->stats_fresh)
+  {
+    TSD_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(uint32_t) * 24, cudaMemcpyDeviceToHost, g->stream));
+    TSD_CUDA(cudaStreamSynchronize(g->stream));
+  }
+  out->cell_updates = (uint64_t)g->h_counters[20] | ((uint64_t)g->h_counters[21] << 32);
   out->active_tiles = g->h_counters[8 + 7];
   out->cell_visits = (uint64_t)g->h_counters[8 + 0] * TSD_TILE_CELLS;
   out->emptied_tiles = g->h_counters[8 + 6];

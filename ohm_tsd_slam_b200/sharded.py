@@ -373,10 +373,20 @@ class DistBand:
         self.grid.stream_order(cur.cuda_stream, 1)
         self.flags_dirty = False
 
+    def _box(self, scan: Scan):
+        """tsdg_scan_box, cached on the scan object (keyed by what the box depends on): a step of N robots asks for
+        2N boxes on every rank."""
+        key = (float(scan.pose[0, 2]), float(scan.pose[1, 2]), float(scan.spec.max_range))
+        c = getattr(scan, "_box_cache", None)
+        if c is None or c[0] != key:
+            c = (key, self.grid.scan_box(scan))
+            scan._box_cache = c
+        return c[1]
+
     def push(self, scan: Scan, sync: bool = False):
         """Every rank calls this with the same scan; ranks the scan cannot reach skip it."""
         self.flags_dirty = True
-        if self.note_scan(self.grid.scan_box(scan)):
+        if self.note_scan(self._box(scan)):
             self.grid.push_async(scan)
         if sync:
             self.sync_halos()
@@ -384,7 +394,7 @@ class DistBand:
     def stage_and_note(self, scan: Scan) -> bool:
         """Staged variant: H2D of the scan if this rank has to push it; follow with push_staged()."""
         self.flags_dirty = True
-        mine = self.note_scan(self.grid.scan_box(scan))
+        mine = self.note_scan(self._box(scan))
         if mine:
             self.grid.stage_scan(scan)
         return mine
