@@ -231,6 +231,24 @@ def run_cuda(args):
             icp_out = icp.run(c[m > 0], nrm[m > 0], scene, sc0.pose)
         icp_ms = (time.perf_counter() - t0) / reps * 1e3
 
+    # ---------------- map publication: RayCastAxisAligned2D::calcCoords + grid2ColorImage on the device,
+    # host buffers in and out (occupancy grid cells_x * cells_y bytes both ways, crossings, 1024^2 RGB image)
+    pub = None
+    if world == 1:
+        occ = np.full(grid.cells * grid.cells, -1, dtype=np.int8)
+        grid.axis_map(occupied=occ)
+        grid.color_image(1024, 1024)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            pc, _, occ = grid.axis_map(occupied=occ)
+        t_axis = (time.perf_counter() - t0) / 3
+        t0 = time.perf_counter()
+        for _ in range(3):
+            grid.color_image(1024, 1024)
+        t_img = (time.perf_counter() - t0) / 3
+        pub = {"axis_aligned_map_ms": t_axis * 1e3, "crossings": int(len(pc)), "free_cells": int((occ == 0).sum()),
+               "color_image_1024_ms": t_img * 1e3}
+
     # ---------------- hypothesis scoring (BASELINE.json configs[3]: 10^5 hypotheses per scan; split over the ranks)
     from ohm_tsd_slam_b200.workload import hypothesis_benchmark
     hyp = hypothesis_benchmark(device=local, n_hyp=100000, reps=2, dist=dist if world > 1 else None,
@@ -282,6 +300,7 @@ def run_cuda(args):
                             "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
                             "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(pushes_per_step, 1)) if icp_ms else None,
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
+            "map_publication": pub,
             "hypothesis_scoring": hyp,
             "large_grid_sweep": sweep,
             "clocks": sampler.summary(),
@@ -290,6 +309,8 @@ def run_cuda(args):
         if world == 1 and not args.no_cpu_baseline:
             b = cpu_baseline(args.workload, steps=100000, warmup=1, threads=None, budget_s=12.0)  # ~12 s of CPU work
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if pub is not None and "map_publication_ms" in b:
+                pub["reference_cpu_ms"] = b["map_publication_ms"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -372,7 +393,14 @@ def cpu_baseline(workload: str, steps: int, warmup: int, threads, budget_s=None)
         done += 1
         if budget_s is not None and t >= budget_s and done >= 3:
             break
-    return {"value": updates / t / 1e9, "unit": UNIT, "cores": nthreads, "kind": kind, "steps": done,
+    extra = {}
+    if use_ref:  # the map publisher's two calls on the same map (serial code in the reference)
+        t0 = time.perf_counter()
+        g.axis_map()
+        t1 = time.perf_counter()
+        g.color_image(1024, 1024)
+        extra["map_publication_ms"] = {"axis_aligned_map": (t1 - t0) * 1e3, "color_image_1024": (time.perf_counter() - t1) * 1e3}
+    return {**extra, "value": updates / t / 1e9, "unit": UNIT, "cores": nthreads, "kind": kind, "steps": done,
             "sample": f"{2 * done} TsdGrid::push calls ({done} step(s)) of the same workload after the same map build, "
                       f"{updates} cell updates, {t:.2f} s on {nthreads} thread(s) of {cores} host cores",
             "ms_per_step": t / done * 1e3}

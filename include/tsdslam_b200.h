@@ -219,6 +219,22 @@ int tsdg_raycast_band_keys(tsd_grid_t* grid, const tsd_scan_t* scan, const doubl
 int tsdg_last_raycast_steps(tsd_grid_t* grid, uint64_t* fine_steps, uint64_t* coarse_steps);
 
 /* ------------------------------------------------------------------------------------------------
+ * Map publication (ThreadGrid.cpp:84,125), on the device: the map never travels to the host.
+ * ------------------------------------------------------------------------------------------------ */
+/* RayCastAxisAligned2D::calcCoords (RayCastAxisAligned2D.cpp:13-105): zero crossings of the TSD along the cell rows
+ * and columns of every allocated inner partition, in the reference's order (partitions row-major; rows, then
+ * columns).  coords: 2 doubles per crossing, room for cap_points crossings (TSD_E_RANGE if there are more: the
+ * first cap_points are written); *count = number of DOUBLES written, as the reference's cnt.  normals (may be
+ * NULL): as in the reference every normal is the one at the first crossing (the call passes the array base,
+ * RayCastAxisAligned2D.cpp:52,73), and the array is left alone when that lookup fails.  occupied (may be NULL):
+ * cells_x * cells_y bytes, in/out: 0 free, -1 occupied / unknown; cells calcCoords does not write keep the
+ * caller's value (ThreadGrid initialises the array to -1 once). */
+int tsdg_axis_aligned_map(tsd_grid_t* grid, double* coords, uint32_t cap_points, double* normals, uint32_t* count,
+                          int8_t* occupied);
+/* TsdGrid::grid2ColorImage (TsdGrid.cpp:429-488): 3 bytes per pixel, width x height. */
+int tsdg_color_image(tsd_grid_t* grid, uint8_t* image, uint32_t width, uint32_t height);
+
+/* ------------------------------------------------------------------------------------------------
  * Icp + FlannPairAssignment + OutOfBoundsFilter2D + DistanceFilter + ReciprocalFilter +
  * ClosedFormEstimator2D, wired as ThreadLocalize.cpp:210-225 and run as ThreadLocalize.cpp:571-581.
  * ---------------------------------------------------------------------------------------------- */

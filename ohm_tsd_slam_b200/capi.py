@@ -31,6 +31,7 @@ EXPORTS = [
     "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
+    "tsdg_axis_aligned_map", "tsdg_color_image",
     "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
@@ -60,6 +61,8 @@ def lib():
     L.tsdg_destroy.argtypes = [C.c_void_p]
     L.tsdg_band_push_finish.argtypes = [C.c_void_p]
     L.tsdg_scan_box.argtypes = [C.c_void_p, _sp, C.POINTER(C.c_int32)]
+    L.tsdg_axis_aligned_map.argtypes = [C.c_void_p, _dp, C.c_uint32, _dp, C.POINTER(C.c_uint32), C.c_void_p]
+    L.tsdg_color_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.tsdg_band_flags.argtypes = [C.c_void_p, _vpp, C.POINTER(C.c_uint64)]
     L.tsdg_band_export.argtypes = [C.c_void_p, C.c_void_p]
     L.tsdg_band_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -273,6 +276,24 @@ class Grid:
         check(lib().tsdg_raycast(self.h, scan.byref(), _d(rays), _d(coords), _d(normals), C.byref(cnt)))
         k = int(cnt.value)
         return coords[:k].reshape(-1, 2), normals[:k].reshape(-1, 2)
+
+    def axis_map(self, with_normals: bool = False, occupied=None, cap_points=None):
+        """RayCastAxisAligned2D::calcCoords: (coords (k, 2), normals (k, 2) or None, occupied int8[cells*cells])."""
+        cells = self.cells
+        cap = cap_points or (cells * cells) // 2
+        coords = np.zeros(2 * cap)
+        normals = np.full(2 * cap, np.nan) if with_normals else None
+        occ = np.full(cells * cells, -1, dtype=np.int8) if occupied is None else occupied
+        cnt = C.c_uint32()
+        check(lib().tsdg_axis_aligned_map(self.h, _d(coords), cap, _d(normals) if with_normals else None, C.byref(cnt),
+                                          occ.ctypes.data_as(C.c_void_p)))
+        k = int(cnt.value) // 2
+        return coords[:2 * k].reshape(-1, 2), (normals[:2 * k].reshape(-1, 2) if with_normals else None), occ
+
+    def color_image(self, width: int, height: int):
+        img = np.zeros(3 * width * height, dtype=np.uint8)
+        check(lib().tsdg_color_image(self.h, img.ctypes.data_as(C.c_void_p), width, height))
+        return img.reshape(height, width, 3)
 
     def band_push_finish(self):
         check(lib().tsdg_band_push_finish(self.h))

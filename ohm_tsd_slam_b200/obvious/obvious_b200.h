@@ -465,6 +465,11 @@ public:
     OBVIOUS_B200_CHECK(rc);
     return true;
   }
+  // TsdGrid.cpp:429-488 (ThreadGrid.cpp:125)
+  void grid2ColorImage(unsigned char* image, unsigned int width, unsigned int height)
+  {
+    OBVIOUS_B200_CHECK(tsdg_color_image(_h, image, width, height));
+  }
   tsd_grid_t* handle() const { return _h; }
 
 private:
@@ -510,6 +515,25 @@ public:
     uint32_t cnt = 0;
     OBVIOUS_B200_CHECK(tsdg_raycast(grid->handle(), &s, R->data(), coords, normals, &cnt));
     *ctr = cnt;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// obvious::RayCastAxisAligned2D (reconstruct/grid/RayCastAxisAligned2D.h): the map publisher's ray caster
+// (ThreadGrid.cpp:84).  coords must hold cellsX * cellsY doubles, as ThreadGrid allocates it (:21).
+// ---------------------------------------------------------------------------------------------------------
+class RayCastAxisAligned2D
+{
+public:
+  RayCastAxisAligned2D() {}
+  virtual ~RayCastAxisAligned2D() {}
+  // RayCastAxisAligned2D.cpp:13-105
+  void calcCoords(TsdGrid* grid, obfloat* coords, obfloat* normals, unsigned int* cnt, char* occupiedGrid = NULL)
+  {
+    uint32_t n = 0;
+    const uint32_t cap = (uint32_t)(((size_t)grid->getCellsX() * grid->getCellsY()) / 2);
+    OBVIOUS_B200_CHECK(tsdg_axis_aligned_map(grid->handle(), coords, cap, normals, &n, (int8_t*)occupiedGrid));
+    *cnt = n;
   }
 };
 

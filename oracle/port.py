@@ -52,6 +52,8 @@ def lib():
         L.port_grid_interpolate_bilinear.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
         L.port_grid_interpolate_normal.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
         L.port_grid_num_partitions.argtypes = [C.c_void_p]
+        L.port_axis_map.argtypes = [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint32), C.c_void_p]
+        L.port_color_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.port_grid_partition_states.argtypes = [C.c_void_p, _ip, _dp]
         L.port_grid_download_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
         L.port_grid_upload_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
@@ -205,6 +207,23 @@ class Grid:
         lib().port_raycast_mask(self.h, scan.byref(), _d(rays), _d(coords), _d(normals), mask.ctypes.data_as(_bp),
                                 C.byref(cnt))
         return coords, normals, mask, int(cnt.value)
+
+    def axis_map(self, with_normals: bool = False, occupied=None, cap_doubles=None):
+        """RayCastAxisAligned2D::calcCoords: (coords (k, 2), normals (k, 2) or None, occupied int8[cells*cells])."""
+        cap = cap_doubles or self.cells * self.cells
+        coords = np.zeros(cap)
+        normals = np.full(cap, np.nan) if with_normals else None
+        occ = np.full(self.cells * self.cells, -1, dtype=np.int8) if occupied is None else occupied
+        cnt = C.c_uint32()
+        lib().port_axis_map(self.h, _d(coords), _d(normals) if with_normals else None, C.byref(cnt),
+                            occ.ctypes.data_as(C.c_void_p))
+        k = int(cnt.value) // 2
+        return coords[:2 * k].reshape(-1, 2), (normals[:2 * k].reshape(-1, 2) if with_normals else None), occ
+
+    def color_image(self, width: int, height: int):
+        img = np.zeros(3 * width * height, dtype=np.uint8)
+        lib().port_color_image(self.h, img.ctypes.data_as(C.c_void_p), width, height)
+        return img.reshape(height, width, 3)
 
     def raycast_steps(self):
         a, b = C.c_uint64(), C.c_uint64()

@@ -577,3 +577,127 @@ void port_invert3x3(const double in[9], double out[9])
     for(int i = 0; i < 3; i++) out[3 * i + c] = x[i];
   }
 }
+
+/* ---------------------------------------------------------------- map publication (ThreadGrid.cpp:84,125) */
+
+/* RayCastAxisAligned2D::calcCoords (RayCastAxisAligned2D.cpp:13-105): zero crossings of the TSD along the cell
+ * rows and columns of every allocated inner partition (borders included), plus an occupancy grid.  coords gets
+ * 2 doubles per crossing, *cnt counts doubles (as the reference does).  normals / occupied may be NULL.
+ * Reference quirk kept: the normal is always evaluated at coords[0..1] -- the FIRST crossing -- because the
+ * call passes the array base (RayCastAxisAligned2D.cpp:52,73), and it is left untouched when that fails. */
+void port_axis_map(port_grid_t* g, double* coords, double* normals, uint32_t* cnt, int8_t* occupied)
+{
+  const unsigned int partitionsInX = (unsigned)(g->cells_x / g->dim);
+  const unsigned int partitionsInY = partitionsInX;
+  const double cellSize = g->cell_size;
+  const unsigned int dim = (unsigned)g->dim;
+  const unsigned int cellsPPart = dim * dim;
+  const unsigned int cellsPPX = dim;
+  const unsigned int pitch = dim + 1;
+  unsigned int gridOffset = 0;
+  *cnt = 0;
+  for(unsigned int y = 1; y < partitionsInY - 1; y++)
+  {
+    for(unsigned int x = 1; x < partitionsInX - 1; x++)
+    {
+      const part_t* p = &g->parts[y * partitionsInX + x];
+      if(p->initialized)
+      {
+        /* isEmpty() is false for an initialised partition (TsdGridPartition.h:72) */
+        if(occupied) gridOffset = y * cellsPPart * partitionsInX + x * cellsPPX;
+        for(unsigned int py = 0; py < dim + 1; py++)
+        {
+          double tsd_prev = p->grid[py * pitch + 0].tsd;
+          double interp = 0.0;
+          if(occupied) occupied[gridOffset + py * (unsigned)g->cells_x] = ((tsd_prev > 0.0) ? 0 : -1);
+          for(unsigned int px = 1; px < dim + 1; px++)
+          {
+            const double tsd = p->grid[py * pitch + px].tsd;
+            if(occupied) occupied[gridOffset + py * (unsigned)g->cells_x + px] = ((tsd > 0.0) ? 0 : -1);
+            if((tsd_prev > 0 && tsd < 0) || (tsd_prev < 0 && tsd > 0))
+            {
+              interp = tsd_prev / (tsd_prev - tsd);
+              coords[(*cnt)] = px * cellSize + cellSize * (interp - 1.0) + (x * dim) * cellSize;
+              coords[(*cnt) + 1] = py * cellSize + (y * dim) * cellSize;
+              if(normals) port_interpolate_normal_one(g, coords, &normals[*cnt]);
+              (*cnt) += 2;
+            }
+            tsd_prev = tsd;
+          }
+        }
+        for(unsigned int px = 0; px < dim + 1; px++)
+        {
+          double tsd_prev = p->grid[0 * pitch + px].tsd;
+          double interp = 0.0;
+          for(unsigned int py = 1; py < dim + 1; py++)
+          {
+            const double tsd = p->grid[py * pitch + px].tsd;
+            if((tsd_prev > 0 && tsd < 0) || (tsd_prev < 0 && tsd > 0))
+            {
+              interp = tsd_prev / (tsd_prev - tsd);
+              coords[(*cnt)] = px * cellSize + (x * dim) * cellSize;
+              coords[(*cnt) + 1] = py * cellSize + cellSize * (interp - 1.0) + (y * dim) * cellSize;
+              if(normals) port_interpolate_normal_one(g, coords, &normals[*cnt]);
+              (*cnt) += 2;
+            }
+            tsd_prev = tsd;
+          }
+        }
+      }
+      else if(p->init_weight > 0.0) /* isEmpty(): seen as free space, never allocated */
+      {
+        if(occupied)
+        {
+          gridOffset = y * cellsPPart * partitionsInX + x * cellsPPX;
+          for(unsigned int py = 0; py < dim; py++)
+            for(unsigned int px = 0; px < dim; px++) occupied[gridOffset + py * (unsigned)g->cells_x + px] = 0;
+        }
+      }
+    }
+  }
+}
+
+/* TsdGrid::grid2ColorImage (TsdGrid.cpp:429-488); px / py are running sums, as in the reference */
+void port_color_image(port_grid_t* g, uint8_t* image, uint32_t width, uint32_t height)
+{
+  unsigned char rgb[3];
+  const double stepW = g->max_x / (double)width;
+  const double stepH = g->max_y / (double)height;
+  double py = 0.0;
+  unsigned int i = 0;
+  for(unsigned int h = 0; h < height; h++)
+  {
+    double px = 0.0;
+    for(unsigned int w = 0; w < width; w++, i++)
+    {
+      double coord[2] = {px, py};
+      int p, x, y;
+      double dx, dy;
+      double tsd = NAN;
+      int isEmpty = 0;
+      if(coord2cell(g, coord, &p, &x, &y, &dx, &dy))
+      {
+        const part_t* part = &g->parts[p];
+        if(part->initialized) tsd = part->grid[y * (g->dim + 1) + x].tsd;
+        isEmpty = (!part->initialized && part->init_weight > 0.0);
+      }
+      if(tsd > 0.0)
+      {
+        rgb[0] = (unsigned char)(tsd * 255.0);
+        rgb[1] = 255;
+        rgb[2] = (unsigned char)(tsd * 255.0);
+      }
+      else if(tsd < 0.0)
+      {
+        rgb[0] = (unsigned char)((1.0 + tsd) * 255.0);
+        rgb[1] = 0;
+        rgb[2] = 0;
+      }
+      else if(isEmpty) { rgb[0] = 255; rgb[1] = 255; rgb[2] = 255; }
+      else { rgb[0] = 0; rgb[1] = 0; rgb[2] = 0; }
+      memcpy(&image[3 * i], rgb, 3);
+      px += stepW;
+    }
+    py += stepH;
+  }
+}

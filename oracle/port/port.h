@@ -37,6 +37,9 @@ int port_grid_download_partition(port_grid_t* g, int32_t p, double* tsd, double*
 int port_grid_upload_partition(port_grid_t* g, int32_t p, const double* tsd, const double* weight);
 void port_grid_fill(port_grid_t* g, double tsd, double weight, int only_uninitialized);
 void port_back_project(const tsd_scan_t* scan, int32_t n, const double* xy, int32_t* idx);
+/* RayCastAxisAligned2D::calcCoords / TsdGrid::grid2ColorImage (map publication, ThreadGrid.cpp:84,125) */
+void port_axis_map(port_grid_t* g, double* coords, double* normals, uint32_t* cnt, int8_t* occupied);
+void port_color_image(port_grid_t* g, uint8_t* image, uint32_t width, uint32_t height);
 
 int port_raycast_mask(port_grid_t* g, const tsd_scan_t* scan, const double* rays_world, double* coords,
                       double* normals, uint8_t* mask, uint32_t* count);

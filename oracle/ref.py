@@ -39,6 +39,9 @@ def lib():
         L.ref_grid_load.argtypes = [C.c_char_p]
         L.ref_grid_store.argtypes = [C.c_void_p, C.c_char_p]
         L.ref_grid_destroy.argtypes = [C.c_void_p]
+        L.ref_axis_map.argtypes = [C.c_void_p, _dp, _dp, C.c_void_p]
+        L.ref_axis_map.restype = C.c_uint
+        L.ref_color_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
         L.ref_grid_set_max_truncation.argtypes = [C.c_void_p, C.c_double]
         for f in ("ref_grid_get_max_truncation", "ref_grid_min_x", "ref_grid_max_x", "ref_grid_min_y", "ref_grid_max_y"):
             getattr(L, f).restype = C.c_double
@@ -303,6 +306,24 @@ class Grid:
         mask = np.zeros(n, dtype=np.uint8)
         cnt = lib().ref_raycast_mask(self.h, sensor.h, _d(coords), _d(normals), mask.ctypes.data_as(_bp))
         return coords, normals, mask, int(cnt)
+
+    def axis_map(self, with_normals: bool = False, occupied=None, cap_doubles=None):
+        """RayCastAxisAligned2D::calcCoords: (coords (k, 2), normals (k, 2) or None, occupied int8[cells*cells])."""
+        cells = int(lib().ref_grid_cells_x(self.h))
+        cap = cap_doubles or cells * cells
+        coords = np.zeros(cap)
+        normals = np.full(cap, np.nan) if with_normals else None
+        occ = np.full(cells * cells, -1, dtype=np.int8) if occupied is None else occupied
+        lib().ref_axis_map.restype = C.c_uint
+        cnt = lib().ref_axis_map(self.h, _d(coords), _d(normals) if with_normals else None,
+                                 occ.ctypes.data_as(C.c_void_p))
+        k = int(cnt) // 2
+        return coords[:2 * k].reshape(-1, 2), (normals[:2 * k].reshape(-1, 2) if with_normals else None), occ
+
+    def color_image(self, width: int, height: int):
+        img = np.zeros(3 * width * height, dtype=np.uint8)
+        lib().ref_color_image(self.h, img.ctypes.data_as(C.c_void_p), width, height)
+        return img.reshape(height, width, 3)
 
     def store(self, path: str) -> bool:
         return bool(lib().ref_grid_store(self.h, path.encode()))

@@ -37,6 +37,7 @@
 
 #include "obcore/base/Logger.h"
 #include "obcore/math/linalg/linalg.h"
+#include "obvision/reconstruct/grid/RayCastAxisAligned2D.h"
 #include "obvision/reconstruct/grid/RayCastPolar2D.h"
 #include "obvision/reconstruct/grid/SensorPolar2D.h"
 #include "obvision/reconstruct/grid/TsdGrid.h"
@@ -338,6 +339,23 @@ unsigned int ref_raycast_compact(void* g, void* s, double* coords, double* norma
   unsigned int cnt = 0;
   rc.calcCoordsFromCurrentView((TsdGrid*)g, (SensorPolar2D*)s, coords, normals, &cnt);
   return cnt;
+}
+
+// ---------------------------------------------------------------- map publication (ThreadGrid.cpp:84,125)
+// RayCastAxisAligned2D::calcCoords (RayCastAxisAligned2D.cpp:13-105); normals / occupied may be NULL.
+// Returns the reference's cnt (number of doubles written to coords).
+unsigned int ref_axis_map(void* g, double* coords, double* normals, signed char* occupied)
+{
+  RayCastAxisAligned2D rc;
+  unsigned int cnt = 0;
+  rc.calcCoords((TsdGrid*)g, coords, normals, &cnt, (char*)occupied);
+  return cnt;
+}
+
+// TsdGrid::grid2ColorImage (TsdGrid.cpp:429-488)
+void ref_color_image(void* g, unsigned char* image, unsigned int width, unsigned int height)
+{
+  ((TsdGrid*)g)->grid2ColorImage(image, width, height);
 }
 
 // ---------------------------------------------------------------- ICP (wired as ThreadLocalize.cpp:210-225)

@@ -14,6 +14,7 @@
 
 #include "obcore/base/Logger.h"
 #include "obcore/math/mathbase.h"
+#include "obvision/reconstruct/grid/RayCastAxisAligned2D.h"
 #include "obvision/reconstruct/grid/RayCastPolar2D.h"
 #include "obvision/reconstruct/grid/SensorPolar2D.h"
 #include "obvision/reconstruct/grid/TsdGrid.h"
@@ -132,5 +133,24 @@ int main(int argc, char** argv)
     k++;
   }
   fclose(f);
+  {
+    // what ThreadGrid::eventLoop does with the map (ThreadGrid.cpp:17-28, :84, :125): crossings + occupancy grid,
+    // colour image.  One summary line: -1 <crossings> <sum x> <sum y> <free cells> <image byte sum> 0
+    const unsigned int cx = grid->getCellsX(), cy = grid->getCellsY();
+    std::vector<char> occ((size_t)cx * cy, -1);
+    std::vector<double> gridCoords((size_t)cx * cy);
+    obvious::RayCastAxisAligned2D raycasterMap;
+    unsigned int mapSize = 0;
+    raycasterMap.calcCoords(grid, gridCoords.data(), NULL, &mapSize, occ.data());
+    double sx = 0.0, sy = 0.0;
+    for(unsigned int i = 0; i < mapSize / 2; i++) { sx += gridCoords[2 * i]; sy += gridCoords[2 * i + 1]; }
+    unsigned long freeCells = 0;
+    for(size_t i = 0; i < occ.size(); i++) freeCells += (occ[i] == 0);
+    std::vector<unsigned char> img((size_t)3 * 160 * 120);
+    grid->grid2ColorImage(img.data(), 160, 120);
+    unsigned long imgSum = 0;
+    for(size_t i = 0; i < img.size(); i++) imgSum += img[i];
+    printf("-1 %u %.17g %.17g %lu %lu 0\n", mapSize / 2, sx, sy, freeCells, imgSum);
+  }
   return 0;
 }

@@ -251,3 +251,45 @@ def replay_golden_sequence(backend, name: str, exact_icp: bool, pose_tol: float 
     if not same(ok, G["normal_ok"]) or not same(nn[ok > 0], G["normal_n"][ok > 0]):
         fails.append("interpolateNormal differs")
     return fails
+
+
+def axis_map_scenario(cfg, n_scans: int, invert):
+    """The scans of the map-publication fixtures (tests/golden/axis_map_*.npz): n_scans along the trajectory,
+    pushed at their ground-truth poses."""
+    hs = HostSensor(cfg.sensor, invert)
+    out = []
+    for pose, r in cfg.scans(n_scans):
+        hs.set_scan(r)
+        hs.T = synth.pose_matrix(*pose)
+        out.append(hs.scan())
+    return out
+
+
+def check_axis_map(backend, name: str, **kw):
+    """Replays tests/golden/axis_map_<name>.npz (generated from the reference) on `backend`: crossings, the quirky
+    normals, the occupancy grid and the colour image must match bit for bit.  Returns failure strings."""
+    G = np.load(os.path.join(GOLDEN, f"axis_map_{name}.npz"))
+    cfg = synth.config(name)
+    g = backend.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid, **kw)
+    g.set_max_truncation(cfg.max_truncation)
+    for sc in axis_map_scenario(cfg, int(G["n_scans"]), backend.invert3x3):
+        g.push(sc)
+    fails = []
+    coords, normals, occ = g.axis_map(with_normals=True)
+    if not same(coords, G["coords"]):
+        fails.append(f"crossings differ: {coords.shape} vs {G['coords'].shape}")
+    elif not same(normals, G["normals"]):
+        fails.append("normals differ")
+    if not same(occ, G["occupied"]):
+        fails.append(f"occupancy differs in {int((occ != G['occupied']).sum())} cells")
+    c2, n2, occ2 = g.axis_map(with_normals=False, occupied=np.full(occ.shape, 7, dtype=np.int8))
+    if n2 is not None or not same(c2, G["coords"]):
+        fails.append("crossings without normals differ")
+    # cells the reference writes become 0 / -1, all others keep the caller's value
+    go = G["occupied"]
+    if not (same(occ2[go == 0], go[go == 0]) and np.isin(occ2[go == -1], (-1, 7)).all()):
+        fails.append("occupancy (in/out array) differs")
+    img = g.color_image(320, 200)
+    if not same(img, G["image"]):
+        fails.append(f"colour image differs in {int((img != G['image']).any(axis=2).sum())} pixels")
+    return fails

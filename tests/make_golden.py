@@ -132,8 +132,31 @@ def run_matchers(name: str):
     print(name, "matchers written")
 
 
+def run_axis_map(name: str, n_scans: int):
+    """Map publication (ThreadGrid.cpp:84,125): RayCastAxisAligned2D::calcCoords and TsdGrid::grid2ColorImage of the
+    reference after n_scans pushes at the ground-truth poses (tests/harness.py axis_map_scenario replays them)."""
+    from tests.harness import axis_map_scenario
+    cfg = synth.config(name)
+    ref.set_threads(1)
+    g = ref.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)
+    g.set_max_truncation(cfg.max_truncation)
+    s = ref.Sensor(cfg.sensor)
+    for sc in axis_map_scenario(cfg, n_scans, ref.invert):
+        s.set_data(sc.ranges, sc.mask)
+        s.pose = sc.pose
+        g.push(s)
+    coords, normals, occ = g.axis_map(with_normals=True)
+    img = g.color_image(320, 200)
+    np.savez_compressed(os.path.join(OUT, f"axis_map_{name}.npz"), n_scans=n_scans, coords=coords, normals=normals,
+                        occupied=occ, image=img)
+    print(name, "axis map written:", len(coords), "crossings,", int((occ == 0).sum()), "free cells")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "axis":  # one reference grid per process (see oracle/README.md)
+        run_axis_map(sys.argv[2], int(sys.argv[3]))
+        sys.exit(0)
     run_sequence("tiny", 10, 12)
     run_sequence("C1", 6, 6)
     run_matchers("tiny")

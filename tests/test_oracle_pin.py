@@ -125,3 +125,11 @@ def test_back_project_edge_cases():
     idx = port.back_project(sc, xy)
     assert idx[0] == -2 and idx[1] == 0 and idx[2] == (cfg.sensor.beams - 1) // 2
     assert idx[3] == cfg.sensor.beams - 1 and idx[4] == -1 and idx[5] == -1 and idx[6] == -2
+
+
+@pytest.mark.parametrize("name", ["tiny", "C1"])
+def test_port_map_publication_matches_reference_golden(name):
+    """RayCastAxisAligned2D::calcCoords + TsdGrid::grid2ColorImage (SURVEY 8f rank 1) of the port vs the fixtures
+    generated from the reference."""
+    from tests.harness import check_axis_map
+    assert check_axis_map(port, name) == []
