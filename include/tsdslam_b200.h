@@ -234,6 +234,12 @@ int tsdg_axis_aligned_map(tsd_grid_t* grid, double* coords, uint32_t cap_points,
 /* TsdGrid::grid2ColorImage (TsdGrid.cpp:429-488): 3 bytes per pixel, width x height. */
 int tsdg_color_image(tsd_grid_t* grid, uint8_t* image, uint32_t width, uint32_t height);
 
+/* The reference's checkpoint format: TsdGrid::storeGrid (TsdGrid.cpp:548-607) and TsdGrid(path, FILE_SOURCE)
+ * (:25-110).  Text, 6 significant digits per value, borders not stored (the next push refreshes them).  The files
+ * are interchangeable with the reference's. */
+int tsdg_store(tsd_grid_t* grid, const char* path);
+int tsdg_load(const char* path, int device, tsd_grid_t** out);
+
 /* ------------------------------------------------------------------------------------------------
  * Icp + FlannPairAssignment + OutOfBoundsFilter2D + DistanceFilter + ReciprocalFilter +
  * ClosedFormEstimator2D, wired as ThreadLocalize.cpp:210-225 and run as ThreadLocalize.cpp:571-581.

@@ -31,7 +31,7 @@ EXPORTS = [
     "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
-    "tsdg_axis_aligned_map", "tsdg_color_image",
+    "tsdg_axis_aligned_map", "tsdg_color_image", "tsdg_store", "tsdg_load",
     "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
@@ -63,6 +63,8 @@ def lib():
     L.tsdg_scan_box.argtypes = [C.c_void_p, _sp, C.POINTER(C.c_int32)]
     L.tsdg_axis_aligned_map.argtypes = [C.c_void_p, _dp, C.c_uint32, _dp, C.POINTER(C.c_uint32), C.c_void_p]
     L.tsdg_color_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.tsdg_store.argtypes = [C.c_void_p, C.c_char_p]
+    L.tsdg_load.argtypes = [C.c_char_p, C.c_int, _vpp]
     L.tsdg_band_flags.argtypes = [C.c_void_p, _vpp, C.POINTER(C.c_uint64)]
     L.tsdg_band_export.argtypes = [C.c_void_p, C.c_void_p]
     L.tsdg_band_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -145,9 +147,11 @@ def invert3x3(m) -> np.ndarray:
 class Grid:
     """obvious::TsdGrid on the device."""
 
-    def __init__(self, cell_size: float, layout_partition: int, layout_grid: int, device: int = 0, band=None):
+    def __init__(self, cell_size: float, layout_partition: int, layout_grid: int, device: int = 0, band=None, handle=None):
         h = C.c_void_p()
-        if band is None:
+        if handle is not None:
+            h = handle
+        elif band is None:
             check(lib().tsdg_create(cell_size, layout_partition, layout_grid, device, C.byref(h)))
         else:
             check(lib().tsdg_create_band(cell_size, layout_partition, layout_grid, device, band[0], band[1], C.byref(h)))
@@ -157,6 +161,20 @@ class Grid:
         self.cells = 1 << layout_grid
         self.parts_per_side = self.cells // self.dim
         self.n_partitions = self.parts_per_side ** 2
+
+    @classmethod
+    def load(cls, path: str, device: int = 0):
+        """TsdGrid(path, FILE_SOURCE): a grid from the reference's checkpoint format (tsdg_load)."""
+        h = C.c_void_p()
+        check(lib().tsdg_load(path.encode(), device, C.byref(h)))
+        with open(path) as f:
+            cs, lp, lg = float(f.readline()), int(f.readline()), int(f.readline())
+        return cls(cs, lp, lg, device=device, handle=h)
+
+    def store(self, path: str) -> bool:
+        """TsdGrid::storeGrid"""
+        check(lib().tsdg_store(self.h, path.encode()))
+        return True
 
     def close(self):
         if getattr(self, "h", None):

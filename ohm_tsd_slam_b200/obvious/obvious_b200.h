@@ -389,6 +389,9 @@ enum EnumTsdGridInterpolate
   INTERPOLATE_SUCCESS = 0, INTERPOLATE_INVALIDINDEX = 1, INTERPOLATE_EMPTYPARTITION = 2, INTERPOLATE_ISNAN = 3
 };
 
+enum EnumTsdGridPartitionIdentifier { UNINITIALIZED = 0, EMPTY = 1, CONTENT = 2 };  // TsdGrid.h:33-35
+enum EnumTsdGridLoadSource { FILE_SOURCE = 0, STRING_SOURCE = 1 };                  // TsdGrid.h:37-39
+
 class TsdGrid
 {
 public:
@@ -398,6 +401,28 @@ public:
   {
     OBVIOUS_B200_CHECK(tsdg_create(cellSize, (int)layoutPartition, (int)layoutGrid, device, &_h));
     refresh();
+  }
+  // TsdGrid.cpp:25-110: a grid from a file written by storeGrid (FILE_SOURCE only)
+  TsdGrid(const std::string& data, const EnumTsdGridLoadSource source = FILE_SOURCE, int device = 0) : _h(NULL), _pushed(false)
+  {
+    if(source != FILE_SOURCE)
+    {
+      fprintf(stderr, "obvious_b200: TsdGrid(STRING_SOURCE) is not supported\n");
+      std::exit(3);
+    }
+    if(tsdg_load(data.c_str(), device, &_h) != TSD_OK)
+    {
+      fprintf(stderr, "obvious_b200: %s\n", tsd_last_error());
+      std::exit(2);  // the reference exits as well (TsdGrid.cpp:39-43)
+    }
+    _pushed = true;
+    refresh();
+  }
+  // TsdGrid.cpp:548-607
+  bool storeGrid(const std::string& path)
+  {
+    if(!path.size()) return false;
+    return tsdg_store(_h, path.c_str()) == TSD_OK;
   }
   virtual ~TsdGrid() { tsdg_destroy(_h); }
   TsdGrid(const TsdGrid&) = delete;

@@ -52,6 +52,9 @@ def lib():
         L.port_grid_interpolate_bilinear.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
         L.port_grid_interpolate_normal.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
         L.port_grid_num_partitions.argtypes = [C.c_void_p]
+        L.port_grid_store.argtypes = [C.c_void_p, C.c_char_p]
+        L.port_grid_load.argtypes = [C.c_char_p]
+        L.port_grid_load.restype = C.c_void_p
         L.port_axis_map.argtypes = [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint32), C.c_void_p]
         L.port_color_image.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
         L.port_grid_partition_states.argtypes = [C.c_void_p, _ip, _dp]
@@ -127,9 +130,15 @@ def back_project(scan: Scan, xy):
     return idx
 
 
+def _file_header(path: str):
+    """(cell_size, layout_partition, layout_grid) of a stored grid (first three lines of the reference's format)."""
+    with open(path) as f:
+        return float(f.readline()), int(f.readline()), int(f.readline())
+
+
 class Grid:
-    def __init__(self, cell_size: float, layout_partition: int, layout_grid: int):
-        self.h = lib().port_grid_create(cell_size, layout_partition, layout_grid)
+    def __init__(self, cell_size: float, layout_partition: int, layout_grid: int, handle=None):
+        self.h = lib().port_grid_create(cell_size, layout_partition, layout_grid) if handle is None else handle
         self.cell_size = cell_size
         self.dim = 1 << layout_partition
         self.cells = 1 << layout_grid
@@ -140,6 +149,18 @@ class Grid:
         if getattr(self, "h", None):
             lib().port_grid_destroy(self.h)
             self.h = None
+
+    @classmethod
+    def load(cls, path: str):
+        """TsdGrid(path, FILE_SOURCE)"""
+        cs, lp, lg = _file_header(path)
+        h = lib().port_grid_load(path.encode())
+        if not h:
+            raise RuntimeError(f"port_grid_load({path}) failed")
+        return cls(cs, lp, lg, handle=h)
+
+    def store(self, path: str) -> bool:
+        return bool(lib().port_grid_store(self.h, path.encode()))
 
     def set_max_truncation(self, v):
         lib().port_grid_set_max_truncation(self.h, v)

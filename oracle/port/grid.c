@@ -701,3 +701,90 @@ void port_color_image(port_grid_t* g, uint8_t* image, uint32_t width, uint32_t h
     py += stepH;
   }
 }
+
+/* ---------------------------------------------------------------- checkpoint format (TsdGrid.cpp:25-110, :548-607) */
+
+/* TsdGrid::storeGrid: text, one value per line, the stream's default formatting (6 significant digits, "%g") */
+int port_grid_store(port_grid_t* g, const char* path)
+{
+  if(!path || !path[0]) return 0;
+  FILE* f = fopen(path, "w");
+  if(!f) return 0;
+  int layout_partition = 0, layout_grid = 0;
+  while((1 << layout_partition) < g->dim) layout_partition++;
+  while((1 << layout_grid) < g->cells_x) layout_grid++;
+  fprintf(f, "%g\n%d\n%d\n%g\n", g->cell_size, layout_partition, layout_grid, g->max_truncation);
+  const int pitch = g->dim + 1;
+  for(int y = 0; y < g->parts_y; y++)
+    for(int x = 0; x < g->parts_x; x++)
+    {
+      const part_t* p = &g->parts[y * g->parts_x + x];
+      if(p->initialized)
+      {
+        fprintf(f, "2\n"); /* CONTENT */
+        for(int py = 0; py < g->dim; py++)
+          for(int px = 0; px < g->dim; px++) fprintf(f, "%g\n%g\n", p->grid[py * pitch + px].tsd, p->grid[py * pitch + px].weight);
+      }
+      else if(p->init_weight > 0.0) fprintf(f, "1\n%g\n", p->init_weight); /* EMPTY */
+      else fprintf(f, "0\n");                                               /* UNINITIALIZED */
+    }
+  fclose(f);
+  return 1;
+}
+
+static double get_double_line(FILE* f) /* tools.cpp:190-200 */
+{
+  char line[1024];
+  if(!fgets(line, sizeof(line), f)) return NAN;
+  if(line[0] == '\n' || line[0] == 0) return NAN;
+  return strtod(line, NULL);
+}
+
+static int get_int_line(FILE* f) /* tools.cpp:207-215 */
+{
+  char line[1024];
+  if(!fgets(line, sizeof(line), f)) return 0;
+  if(line[0] == '\n' || line[0] == 0) return 0;
+  return atoi(line);
+}
+
+/* TsdGrid::TsdGrid(const std::string&, FILE_SOURCE) */
+port_grid_t* port_grid_load(const char* path)
+{
+  FILE* f = fopen(path, "r");
+  if(!f) return NULL;
+  const double cellSize = get_double_line(f);
+  const int layoutPartition = get_int_line(f);
+  const int layoutGrid = get_int_line(f);
+  if(layoutGrid < 0 || layoutPartition < 0 || layoutGrid > 15 || layoutPartition > 15) { fclose(f); return NULL; }
+  const double maxTruncation = get_double_line(f);
+  port_grid_t* g = port_grid_create(cellSize, layoutPartition, layoutGrid);
+  if(!g) { fclose(f); return NULL; }
+  port_grid_set_max_truncation(g, maxTruncation);
+  const int pitch = g->dim + 1;
+  for(int y = 0; y < g->parts_y; y++)
+    for(int x = 0; x < g->parts_x; x++)
+    {
+      const int id = get_int_line(f);
+      part_t* p = &g->parts[y * g->parts_x + x];
+      if(id == 0) continue;
+      else if(id == 1)
+      {
+        p->init_weight = get_double_line(f);
+        p->init_weight = (MAXWEIGHT < p->init_weight) ? MAXWEIGHT : p->init_weight; /* std::min(a, b): b < a ? b : a */
+      }
+      else if(id == 2)
+      {
+        part_init(g, p, g->max_truncation);
+        for(int py = 0; py < g->dim; py++)
+          for(int px = 0; px < g->dim; px++)
+          {
+            p->grid[py * pitch + px].tsd = get_double_line(f);
+            p->grid[py * pitch + px].weight = get_double_line(f);
+          }
+      }
+      else { fclose(f); port_grid_destroy(g); return NULL; }
+    }
+  fclose(f);
+  return g;
+}

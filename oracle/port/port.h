@@ -40,6 +40,9 @@ void port_back_project(const tsd_scan_t* scan, int32_t n, const double* xy, int3
 /* RayCastAxisAligned2D::calcCoords / TsdGrid::grid2ColorImage (map publication, ThreadGrid.cpp:84,125) */
 void port_axis_map(port_grid_t* g, double* coords, double* normals, uint32_t* cnt, int8_t* occupied);
 void port_color_image(port_grid_t* g, uint8_t* image, uint32_t width, uint32_t height);
+/* TsdGrid::storeGrid / the file constructor (TsdGrid.cpp:548-607, :25-110): the reference's checkpoint format */
+int port_grid_store(port_grid_t* g, const char* path);
+port_grid_t* port_grid_load(const char* path);
 
 int port_raycast_mask(port_grid_t* g, const tsd_scan_t* scan, const double* rays_world, double* coords,
                       double* normals, uint8_t* mask, uint32_t* count);

@@ -328,6 +328,15 @@ class Grid:
     def store(self, path: str) -> bool:
         return bool(lib().ref_grid_store(self.h, path.encode()))
 
+    @classmethod
+    def load(cls, path: str):
+        """TsdGrid(path, FILE_SOURCE)"""
+        with open(path) as f:
+            cs, lp, lg = float(f.readline()), int(f.readline()), int(f.readline())
+        with _quiet_stdout():
+            h = lib().ref_grid_load(path.encode())
+        return cls(cs, lp, lg, handle=h)
+
 
 class Icp:
     """obvious::Icp wired as ThreadLocalize.cpp:210-225."""

@@ -133,3 +133,37 @@ def test_port_map_publication_matches_reference_golden(name):
     generated from the reference."""
     from tests.harness import check_axis_map
     assert check_axis_map(port, name) == []
+
+
+def test_port_checkpoint_format_matches_reference_library(tmp_path):
+    """storeGrid / file constructor of the port vs the reference library, where it is present: identical bytes,
+    identical grid after loading and after the next push."""
+    if not ref.available():
+        pytest.skip("oracle/_ref/libohm_ref.so not built here")
+    from tests.harness import axis_map_scenario, compare_grids
+    cfg = synth.config("tiny")
+    gp = port.Grid(cfg.cell_size, 5, cfg.layout_grid)
+    gr = ref.Grid(cfg.cell_size, 5, cfg.layout_grid)
+    gp.set_max_truncation(cfg.max_truncation)
+    gr.set_max_truncation(cfg.max_truncation)
+    sen = ref.Sensor(cfg.sensor)
+    scans = axis_map_scenario(cfg, 6, ref.invert)
+
+    def push_ref(g, sc):
+        sen.set_data(sc.ranges, sc.mask)
+        sen.pose = sc.pose
+        g.push(sen)
+
+    for sc in scans[:5]:
+        gp.push(sc)
+        push_ref(gr, sc)
+    fp, fr = str(tmp_path / "port.txt"), str(tmp_path / "ref.txt")
+    assert gp.store(fp) and gr.store(fr)
+    assert open(fp, "rb").read() == open(fr, "rb").read()
+    lp, lr = port.Grid.load(fr), ref.Grid.load(fr)
+    ok, lines = compare_grids(lr, lp)
+    assert ok, lines
+    lp.push(scans[5])
+    push_ref(lr, scans[5])
+    ok, lines = compare_grids(lr, lp)
+    assert ok, lines
