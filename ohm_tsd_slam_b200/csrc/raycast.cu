@@ -44,7 +44,6 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
   const int xDim = g.cells_x, yDim = g.cells_y;
   const double cellSize = g.cell_size;
 
-  __shared__ double2 s_pos[RC_WARPS][64];  // two passes of 32 positions per warp
   unsigned long long key = NO_EVENT;
   unsigned long long nFine = 0, nCoarse = 0;
   bool found = false;
@@ -108,28 +107,27 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
     }
 
     // :243-270 fine loop, 32 steps per pass.
-    // The position chain of a pass is computed by all lanes (uniform DADDs), lane 0 parks the 32 positions in
-    // shared memory and every lane picks up its own; the chain of pass c+1 is issued between the loads and the
-    // use of pass c's samples, so the L2 latency of the samples hides behind it.
+    // The position chain of a pass is computed by all lanes (uniform DADDs), every lane keeps the position of its
+    // own step; the chain of pass c+1 is issued between the loads and the use of pass c's samples, so the L2
+    // latency of the samples hides behind it.
     // The loop counter `i += 1.0` of the reference only decides when the loop ends: it is replayed exactly
     // (serially) only for passes that come within 2 steps of idxMax; elsewhere idxMin + k decides safely.
-    double2* buf = s_pos[threadIdx.x >> 5];
+    // (every lane runs the whole chain and keeps the position of its own step in registers: parking the positions
+    //  in shared memory made each addition wait for the previous store to read its operands)
+    double nmx = 0.0, nmy = 0.0;
     double iExact = idxMin;          // i of iteration kExact (exact serial value)
     unsigned long long kExact = 0;
     unsigned long long base = 0;
-    int cur = 0;
 #pragma unroll 8
     for(int k = 0; k < 32; k++)
     {
       pos0 += ray0;
       pos1 += ray1;
-      if(lane == 0) buf[k] = make_double2(pos0, pos1);
+      if(k == lane) { nmx = pos0; nmy = pos1; }
     }
-    __syncwarp();
     while(true)
     {
-      const double2 mp = buf[cur * 32 + lane];
-      const double mx = mp.x, my = mp.y;
+      const double mx = nmx, my = nmy;
       // validity of this lane's iteration: i_k <= idxMax
       const double est = idxMin + (double)(base + (unsigned)lane);
       bool valid;
@@ -155,13 +153,13 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
       const SampleLoads sl = sample_issue(g, mx, my);  // all lanes: addresses are clamped, results masked below
       // next pass's positions while the loads above are in flight
       {
-        double2* nb = buf + (cur ^ 1) * 32;
+
 #pragma unroll 8
         for(int k = 0; k < 32; k++)
         {
           pos0 += ray0;
           pos1 += ray1;
-          if(lane == 0) nb[k] = make_double2(pos0, pos1);
+          if(k == lane) { nmx = pos0; nmy = pos1; }
         }
       }
       const int rv = sample_finish(sl, &t);
@@ -210,8 +208,6 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
       nFine += 32;
       base += 32;
       carry = __shfl_sync(0xffffffffu, v, 31);
-      cur ^= 1;
-      __syncwarp();
     }
   }
 
