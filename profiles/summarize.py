@@ -26,11 +26,18 @@ BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 TIME_US = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 
 
+def kname(full: str, keep_template: bool = False) -> str:
+    """'void (anonymous namespace)::k_axis<0>(AxisParams)' -> 'k_axis' (or 'k_axis<0>')"""
+    s = full.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "")
+    s = s.split("(")[0]
+    return s if keep_template else s.split("<")[0]
+
+
 def launch_table(path, out):
     rows = [r for r in csv.reader(open(path)) if len(r) > 14 and r[0].isdigit()]
     per = collections.defaultdict(list)
     for r in rows:
-        per[r[4].split("(")[0].split("<")[0].replace("void ", "")].append(float(r[14]) / 1e3)
+        per[kname(r[4])].append(float(r[14]) / 1e3)
     tot = sum(sum(v) for v in per.values())
     out.append("| kernel | launches | mean us | min us | max us | share of listed GPU time |")
     out.append("|---|---|---|---|---|---|")
@@ -51,7 +58,7 @@ def raw_tables(rep, out):
     idx = {h: i for i, h in enumerate(hdr)}
     agg = collections.defaultdict(lambda: collections.defaultdict(list))
     for r in rr[2:]:
-        k = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
+        k = kname(r[idx["Kernel Name"]], keep_template=True)
         for w in WANT:
             if w in idx:
                 try:
@@ -138,7 +145,8 @@ def main():
     if os.path.exists(launches):
         shutil.copy(launches, os.path.join(ROOT, "profiles", f"{rnd}_launches.csv"))
         out.append("## Launch list\n")
-        out.append("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline`."
+        out.append("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sweep`"
+                   " (the whole bench: map build, pushes, ray casts, ICP, map publication, 10^5-hypothesis scoring)."
                    " Per-launch times are cold-cache and serialised: compare shares, not absolutes. Full list: `" + f"{rnd}_launches.csv`.\n")
         launch_table(launches, out)
     metrics = {}
