@@ -123,19 +123,29 @@ def run_cuda(args):
     # ---------------- device-resident leg: `value` times the pushes (and the halo synchronisation of a sharded grid)
     # with CUDA events on the library's stream; the H2D staging of each scan (tsdg_stage_scan, from pinned host
     # memory) sits between the event pairs, outside them.
+    # A step = one scan cycle: the two lasers of every robot.  The two scans of a robot form one batch
+    # (tsdg_stage_batch / tsdg_push_batch: the result of two TsdGrid::push calls, one classification + one update
+    # launch for both; --no-batch pushes them one by one).
+    def batches(i):
+        sc = wl.step_scans[i % n_steps]
+        if args.no_batch:
+            return [[s1] for s1 in sc]
+        return [list(sc[k:k + 2]) for k in range(0, len(sc), 2)]
+
     def resident_step(i, acc, samples=None):
-        for sc in wl.step_scans[i % n_steps]:
+        for b in batches(i):
             if band:
-                if not band.stage_and_note(sc):
+                mine = [band.note_scan(band._box(s1)) for s1 in b]
+                band.flags_dirty = True
+                if not any(mine):
                     continue
-            else:
-                grid.stage_scan(sc)
+            grid.stage_batch(b)
             e0, e1 = ev_pair()
             e0.record(stream)
             grid.push_staged()
             e1.record(stream)
             acc.append((e0, e1))
-            if samples is not None:  # (synchronises, between the event pairs) kernel times + update count of this push
+            if samples is not None:  # (synchronises, between the event pairs) kernel times + update count of this launch
                 samples.append((grid.last_push_kernel_ms(), grid.last_push_stats()["cell_updates"]))
         if band:
             e0, e1 = ev_pair()
@@ -162,25 +172,28 @@ def run_cuda(args):
 
     # exact update count of one step on this rank, and of its heaviest push (the roofline launch)
     def host_step(i, count=None):
-        for sc in wl.step_scans[i % n_steps]:
+        for b in batches(i):
             if band:
-                mine = band.note_scan(band._box(sc))
+                mine = [band.note_scan(band._box(s1)) for s1 in b]
                 band.flags_dirty = True
-                if not mine:
+                if not any(mine):
                     continue
-            grid.push(sc)  # blocking: H2D of the scan, kernels, synchronise
+            grid.push_batch(b)  # blocking: H2D of the scans, kernels, D2H of the statistics, synchronise
             if count is not None:
-                count.append(grid.last_push_stats()["cell_updates"])  # D2H of the statistics
+                count.append(grid.last_push_stats()["cell_updates"])
+                scans_pushed[0] += len(b)
         if band:
             band.sync_halos()
             grid.sync()
 
     upd_steps = []
+    scans_pushed = [0]
     for i in range(n_steps):
         c = []
         host_step(i, c)
         upd_steps.append(c)
     pushes_per_step = len(upd_steps[0])
+    scans_per_step = scans_pushed[0] / n_steps  # scans this rank integrates per step
     upd_per_step = float(np.mean([sum(c) for c in upd_steps]))
     upd_total_dev = sum(sum(upd_steps[i % n_steps]) for i in range(args.steps))
     # roofline samples: full-size pushes only (on a sharded grid a rank also sees the tail of its neighbour's scans)
@@ -287,9 +300,10 @@ def run_cuda(args):
             "config": dict(wl.describe(), parallelism=(f"one band of partition rows per GPU ({world} bands), scans replicated, pushes without "
                                                        f"communication, boundary rows to the neighbours once per step (NCCL P2P)"
                                                        if world > 1 else "single GPU"),
-                           cell_updates_per_step=upd_per_step_all, pushes_per_step_rank0=pushes_per_step),
+                           cell_updates_per_step=upd_per_step_all, push_launch_pairs_per_step_rank0=pushes_per_step,
+                           batched=not args.no_batch),
             "hbm_gbs_algorithmic": value * ALG_BYTES_PER_UPDATE,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pushes_per_step * (n * 8 + n + 8 * 25), "d2h_bytes_per_step": pushes_per_step * (16 * 4 + 4 * 8),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scans_per_step * (n * 8 + n + 8 * 25)), "d2h_bytes_per_step": pushes_per_step * 24 * 4,
                     "ms_per_step": e2e_ms_max / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_update (TsdGrid::push cell update, K2+K3)", "achieved": achieved, "peak": peak,
@@ -298,7 +312,7 @@ def run_cuda(args):
             "push_kernel_ms": {k: float(np.mean([x[k] for x in kms])) for k in kms[0]},
             "raycast_icp": {"raycast_ms": rc_ms, "icp_ms": icp_ms, "raycast_hits": int(cnt),
                             "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
-                            "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(pushes_per_step, 1)) if icp_ms else None,
+                            "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(scans_per_step, 1)) if icp_ms else None,
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
             "map_publication": pub,
             "hypothesis_scoring": hyp,
@@ -438,6 +452,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch", action="store_true", help="push the two lasers of a robot one by one (two launch pairs)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 16384^2 push sweep (4.6 GB of HBM, a few seconds)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup

@@ -155,6 +155,15 @@ int tsdg_sync(tsd_grid_t* grid);
  * host-to-device traffic.  Lets a caller keep the measurement resident (bench.py's device-resident leg). */
 int tsdg_stage_scan(tsd_grid_t* grid, const tsd_scan_t* scan);
 int tsdg_push_staged(tsd_grid_t* grid);
+/* n scans in the order given, with the result of n TsdGrid::push calls (ThreadMapping::eventLoop drains its queue
+ * of sensors one push after the other, ThreadMapping.cpp:43-62).  Consecutive scans of the same sensor model are
+ * taken two at a time: one classification and one update launch for both, partitions seen by both scans (the two
+ * lasers of a robot) are read and written once.  tsdg_push_batch blocks like tsdg_push; the statistics reported
+ * afterwards are those of the last launch (both scans of a pair together).  tsdg_stage_batch (n <= 2, same sensor
+ * model) + tsdg_push_staged is the device-resident variant. */
+int tsdg_push_batch(tsd_grid_t* grid, const tsd_scan_t* scans, int32_t n);
+int tsdg_push_batch_async(tsd_grid_t* grid, const tsd_scan_t* scans, int32_t n);
+int tsdg_stage_batch(tsd_grid_t* grid, const tsd_scan_t* scans, int32_t n);
 /* The handle's cudaStream_t, for callers that time or order work with CUDA events. */
 void* tsdg_stream(tsd_grid_t* grid);
 /* Orders the handle's stream against a caller's stream without blocking the host: direction 0 = `other`

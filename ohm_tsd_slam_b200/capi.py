@@ -27,7 +27,7 @@ EXPORTS = [
     "tsd_last_error", "tsd_device_count", "tsd_kernel_launches", "tsd_invert3x3",
     "tsdg_create", "tsdg_create_band", "tsdg_band_push_finish", "tsdg_band_export", "tsdg_band_connect", "tsdg_band_connect_local", "tsdg_band_halo_sync",
     "tsdg_band_flags", "tsdg_scan_box", "tsdg_band_row", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
-    "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged",
+    "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged", "tsdg_push_batch", "tsdg_push_batch_async", "tsdg_stage_batch",
     "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
@@ -78,6 +78,9 @@ def lib():
     L.tsdg_push.argtypes = [C.c_void_p, _sp]
     L.tsdg_push_async.argtypes = [C.c_void_p, _sp]
     L.tsdg_stage_scan.argtypes = [C.c_void_p, _sp]
+    L.tsdg_push_batch.argtypes = [C.c_void_p, _sp, C.c_int32]
+    L.tsdg_push_batch_async.argtypes = [C.c_void_p, _sp, C.c_int32]
+    L.tsdg_stage_batch.argtypes = [C.c_void_p, _sp, C.c_int32]
     L.tsdg_push_staged.argtypes = [C.c_void_p]
     L.tsdg_sync.argtypes = [C.c_void_p]
     L.tsdg_stream.restype = C.c_void_p
@@ -209,6 +212,26 @@ class Grid:
 
     def push_async(self, scan: Scan):
         check(lib().tsdg_push_async(self.h, scan.byref()))
+
+    @staticmethod
+    def _scan_array(scans):
+        arr = (ScanStruct * len(scans))()
+        for i, sc in enumerate(scans):
+            arr[i] = sc.struct
+        return arr
+
+    def push_batch(self, scans):
+        """The scans in order, as len(scans) pushes would; pairs of scans share their launches (tsdg_push_batch)."""
+        arr = self._scan_array(scans)
+        check(lib().tsdg_push_batch(self.h, arr, len(scans)))
+
+    def push_batch_async(self, scans):
+        arr = self._scan_array(scans)
+        check(lib().tsdg_push_batch_async(self.h, arr, len(scans)))
+
+    def stage_batch(self, scans):
+        arr = self._scan_array(scans)
+        check(lib().tsdg_stage_batch(self.h, arr, len(scans)))
 
     def stage_scan(self, scan: Scan):
         check(lib().tsdg_stage_scan(self.h, scan.byref()))

@@ -231,6 +231,7 @@ struct tsd_grid
   double* d_initw;     // n_parts
   // per-push work lists (capacity n_owned each) and their per-item data
   uint32_t* d_active;  // bit 31: partition was initialised before this push
+  uint32_t* d_kinds;   // per work-list entry: 2-bit outcome per scan of the launch
   double* d_active_w;  // 0.01 * partWeight per active item
   uint32_t* d_emptied;
   uint32_t* d_newly;   // partitions allocated by the current push
@@ -273,7 +274,8 @@ struct tsd_grid
   unsigned long long* h_stats64;
   tsd_push_stats_t last_stats;
   int sm_count;
-  tsd::ScanDev staged;  // scan staged by tsdg_stage_scan (device pointers + scalars)
+  tsd::ScanDev staged[2];  // scans staged by tsdg_stage_scan / tsdg_stage_batch (device pointers + scalars)
+  int staged_n;
   // halo synchronisation over peer memory (bands only): [0] = the band below, [1] = the band above
   uint32_t* d_signal;        // [0]/[1] data-ready from below/above, [2]/[3] ack from below/above, [4] CTA ticket
   struct Peer
@@ -294,6 +296,7 @@ struct tsd_grid
 namespace tsd
 {
 int grid_stage_scan(tsd_grid* g, const tsd_scan_t* scan, ScanDev* sd, const double* rays_world);  // one H2D copy
+int grid_stage_scans(tsd_grid* g, const tsd_scan_t* scans, int n, ScanDev* sd, const double* rays_world);
 int grid_ensure_scratch(tsd_grid* g, size_t bytes);
 GridView grid_view(const tsd_grid* g);
 }

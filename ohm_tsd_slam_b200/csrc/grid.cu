@@ -91,9 +91,12 @@ using namespace tsd;
 // kernels
 // ------------------------------------------------------------------------------------------------
 
+#define PUSH_MAX_SCANS 2  // scans one push launch integrates (tsdg_push_batch)
+
 struct PushParams
 {
-  ScanDev scan;
+  ScanDev scans[PUSH_MAX_SCANS];
+  int nscan;
   double cell_size;
   double max_trunc;
   double inv_max_trunc;  // 1.0 / maxTruncation (TsdGridPartition.cpp:94)
@@ -108,25 +111,26 @@ struct PushParams
   double* weight;
   uint8_t* flags;
   double* initw;
-  uint32_t* active;
-  double* active_w;
+  uint32_t* active;    // work list: partition | bit 31 = allocated before this push
+  uint32_t* kinds;     // per list entry: 2 bits per scan (0 untouched, 1 increaseEmptiness, 2 active)
+  double* active_w;    // per list entry and scan: partition weight (capacity n_owned per scan)
+  int list_cap;        // n_owned
   uint32_t* emptied;
   uint32_t* newly;    // partitions allocated by this push (count: counters[4], owned ones only in the list)
   uint32_t* pending;
   uint32_t* counters;
   unsigned long long* stats64;
-  const double* coltab;
-  const double* rowtab;
+  const double* coltab;  // per scan: 3 * cells_x
+  const double* rowtab;  // per scan: 3 * cells_y
   const double2* dirs;
 };
 
 // Per grid column X = ((double)ix + 0.5) * cellSize (TsdGridPartition.cpp:127): the two products of
 // SensorPolar2D.cpp:125 that depend on X only, with gslcblas' accumulation order (temp = 0; temp += a*b ...),
 // and the squared offset of TsdGrid.cpp:262.  Same per grid row.  Runs inside k_classify (first threads).
-__device__ __forceinline__ void fill_tables(const PushParams& pp, double* coltab, double* rowtab, int i)
+__device__ __forceinline__ void fill_tables(const PushParams& pp, const ScanDev& sc, double* coltab, double* rowtab, int i0)
 {
-  const double* Pi = pp.scan.Pi;
-  const int i0 = i;
+  const double* Pi = sc.Pi;
   if(i0 < pp.cl_w * TSD_TILE)
   {
     const int i = pp.cl_px0 * TSD_TILE + i0;
@@ -135,7 +139,7 @@ __device__ __forceinline__ void fill_tables(const PushParams& pp, double* coltab
     a += Pi[0] * X;
     double b = 0.0;
     b += Pi[3] * X;
-    const double d = X - pp.scan.P[2];
+    const double d = X - sc.P[2];
     coltab[i] = a;
     coltab[pp.cells_x + i] = b;
     coltab[2 * pp.cells_x + i] = d * d;
@@ -144,7 +148,7 @@ __device__ __forceinline__ void fill_tables(const PushParams& pp, double* coltab
   {
     const int i = pp.cl_py0 * TSD_TILE + i0;
     const double Y = ((double)i + 0.5) * pp.cell_size;
-    const double d = Y - pp.scan.P[5];
+    const double d = Y - sc.P[5];
     rowtab[i] = Pi[1] * Y;
     rowtab[pp.cells_y + i] = Pi[4] * Y;
     rowtab[2 * pp.cells_y + i] = d * d;
@@ -178,22 +182,27 @@ __device__ __forceinline__ int back_project_edge(const ScanDev& s, const double2
 
 #define CLASSIFY_THREADS 256
 
-// K1: TsdGridComponent::isInRange (TsdGridComponent.cpp:43-124) for every partition.  Four lanes per partition
-// (one per edge point), eight partitions per warp; the beam interval [minIdx, maxIdx] is scanned by the four
-// lanes.  The first cells_x / cells_y threads of the grid also fill the column / row tables of this push.
+// K1: TsdGridComponent::isInRange (TsdGridComponent.cpp:43-124) for every partition of the range box.  Four lanes
+// per partition (one per edge point), eight partitions per warp; the beam interval [minIdx, maxIdx] is scanned by
+// the four lanes.  The first threads also fill the column / row tables of this push.
+// A push launch can integrate up to PUSH_MAX_SCANS scans (tsdg_push_batch): every partition is classified for scan
+// 0, then for scan 1, with the state scan 0 left (allocation flag, emptiness weight) -- the order TsdGrid::push
+// calls would produce -- and gets ONE work-list entry with a 2-bit outcome per scan.
+template <int NS>
 __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, double* coltab, double* rowtab)
 {
   const int gtid = blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
-  fill_tables(pp, coltab, rowtab, gtid);  // (columns / rows of the range box only)
+#pragma unroll
+  for(int si = 0; si < NS; si++)
+    fill_tables(pp, pp.scans[si], coltab + (size_t)si * 3 * pp.cells_x, rowtab + (size_t)si * 3 * pp.cells_y, gtid);
   const int lane = threadIdx.x & 31;
   const int sub = lane & 3;
   const int gshift = lane & ~3;
   const unsigned gmask = 0xfu << gshift;
   const int q = gtid >> 2;  // index inside the range box; everything outside fails the range cull below anyway
-  // no lane leaves before the warp-wide part below: `alive` carries the reference's early returns
-  bool alive = q < pp.cl_w * pp.cl_h;
-  const ScanDev& s = pp.scan;
-  const int px = alive ? pp.cl_px0 + q % pp.cl_w : 0, py = alive ? pp.cl_py0 + q / pp.cl_w : 0;
+  // no lane leaves before the warp-wide parts below: `alive` carries the reference's early returns
+  const bool exists = q < pp.cl_w * pp.cl_h;
+  const int px = exists ? pp.cl_px0 + q % pp.cl_w : 0, py = exists ? pp.cl_py0 + q / pp.cl_w : 0;
   const int p = py * pp.parts_x + px;
   const unsigned int x0 = px * TSD_TILE, y0 = py * TSD_TILE;
   const double cs = pp.cell_size;
@@ -207,99 +216,109 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
   const double ceny = (e0y + e0y + e2y + e2y) / 4.0;
   const double ddx = e1x - e0x, ddy = e2y - e0y;
   const double circumradius = sqrt(ddx * ddx + ddy * ddy) * 0.5;
-
-  const double trx = s.P[2], try_ = s.P[5];
-  // euklideanDistance(pos, centroid) (mathbase.h:369-378)
-  double sqr = 0.0;
-  {
-    const double t0 = trx - cenx;
-    sqr += t0 * t0;
-    const double t1 = try_ - ceny;
-    sqr += t1 * t1;
-  }
-  const double distance = sqrt(sqr);
-  const double closest = distance - circumradius - pp.max_trunc;
-  if(closest > s.max_range) alive = false;
-  const double farthest = distance + circumradius + pp.max_trunc;
-  if(farthest < s.min_range) alive = false;
-
-  // one edge point per lane
-  int idxEdge = 0;
-  if(alive)
-  {
-    const double X = (sub & 1) ? e1x : e0x;
-    const double Y = (sub & 2) ? e2y : e0y;
-    idxEdge = back_project_edge(s, pp.dirs, X, Y);
-  }
-  bool visibleEdge = true;
-  if(idxEdge == -1) { idxEdge = s.n - 1; visibleEdge = false; }
-  else if(idxEdge == -2) { idxEdge = 0; visibleEdge = false; }
-  if(idxEdge > s.n - 1) idxEdge = s.n - 1;  // the reference would read past the scan here
-  const unsigned vis4 = (__ballot_sync(0xffffffffu, visibleEdge) >> gshift) & 0xfu;
-  if(vis4 == 0u) alive = false;  // !isAnyEdgeVisible
-  const bool allVisible = (vis4 == 0xfu);
-  int minIdx = idxEdge, maxIdx = idxEdge;
-#pragma unroll
-  for(int o = 1; o < 4; o <<= 1)
-  {
-    const int a = __shfl_xor_sync(0xffffffffu, minIdx, o);
-    const int b = __shfl_xor_sync(0xffffffffu, maxIdx, o);
-    minIdx = min(minIdx, a);
-    maxIdx = max(maxIdx, b);
-  }
-
-  // TsdGridComponent.cpp:96-118: the beams between the outermost edge beams.  Narrow intervals are scanned by
-  // the partition's four lanes, wide ones (partitions next to the sensor) by the whole warp.
-  bool vis = false, empty = true;
-  const bool wide = alive && (maxIdx - minIdx > 96);
-  if(alive && !wide)
-  {
-    for(int j = minIdx + sub; j <= maxIdx; j += 4)
-    {
-      const double d = s.ranges[j];
-      const bool m = s.mask[j] != 0;
-      vis = vis || ((d > closest) && m);
-      if(isinf(d)) empty = empty && (distance < s.low_refl);
-      else empty = empty && (d > farthest) && m;
-    }
-  }
-  unsigned wideLeaders = __ballot_sync(0xffffffffu, wide && sub == 0);
-  while(wideLeaders)
-  {
-    const int gl = __ffs(wideLeaders) - 1;
-    wideLeaders &= wideLeaders - 1;
-    const int lo = __shfl_sync(0xffffffffu, minIdx, gl), hi = __shfl_sync(0xffffffffu, maxIdx, gl);
-    const double cl = __shfl_sync(0xffffffffu, closest, gl), fa = __shfl_sync(0xffffffffu, farthest, gl);
-    const double di = __shfl_sync(0xffffffffu, distance, gl);
-    bool v = false, e = true;
-    for(int j = lo + lane; j <= hi; j += 32)
-    {
-      const double d = s.ranges[j];
-      const bool m = s.mask[j] != 0;
-      v = v || ((d > cl) && m);
-      if(isinf(d)) e = e && (di < s.low_refl);
-      else e = e && (d > fa) && m;
-    }
-    const bool anyV = __any_sync(0xffffffffu, v);
-    const bool allE = __all_sync(0xffffffffu, e);
-    if((lane >> 2) == (gl >> 2)) { vis = anyV; empty = allE; }
-  }
-  const unsigned mVis = __ballot_sync(0xffffffffu, vis);
-  const unsigned mEmpty = __ballot_sync(0xffffffffu, empty);
-  if(!alive) return;
-  if((mVis & gmask) == 0u) return;
-  const bool allEmpty = (mEmpty & gmask) == gmask;
   const bool owned = (py >= pp.row_begin && py < pp.row_end);
-  const bool wasInit = pp.flags[p] != 0;
-  if(allVisible && allEmpty)
+
+  // state of the partition as the scans of this launch see it one after the other (first lane of the group)
+  bool stateKnown = false, wasInit = false, wasInitBefore = false, allocatedHere = false;
+  unsigned kinds = 0;
+  double wItem[NS];
+  unsigned nActive = 0, nEmptied = 0;
+
+#pragma unroll
+  for(int si = 0; si < NS; si++)
   {
-    // increaseEmptiness (TsdGridPartition.cpp:136-164)
-    if(sub == 0)
+    const ScanDev& s = pp.scans[si];
+    wItem[si] = 0.0;
+    bool alive = exists;
+    const double trx = s.P[2], try_ = s.P[5];
+    // euklideanDistance(pos, centroid) (mathbase.h:369-378)
+    double sqr = 0.0;
     {
-      if(wasInit)
+      const double t0 = trx - cenx;
+      sqr += t0 * t0;
+      const double t1 = try_ - ceny;
+      sqr += t1 * t1;
+    }
+    const double distance = sqrt(sqr);
+    const double closest = distance - circumradius - pp.max_trunc;
+    if(closest > s.max_range) alive = false;
+    const double farthest = distance + circumradius + pp.max_trunc;
+    if(farthest < s.min_range) alive = false;
+
+    // one edge point per lane
+    int idxEdge = 0;
+    if(alive)
+    {
+      const double X = (sub & 1) ? e1x : e0x;
+      const double Y = (sub & 2) ? e2y : e0y;
+      idxEdge = back_project_edge(s, pp.dirs, X, Y);
+    }
+    bool visibleEdge = true;
+    if(idxEdge == -1) { idxEdge = s.n - 1; visibleEdge = false; }
+    else if(idxEdge == -2) { idxEdge = 0; visibleEdge = false; }
+    if(idxEdge > s.n - 1) idxEdge = s.n - 1;  // the reference would read past the scan here
+    const unsigned vis4 = (__ballot_sync(0xffffffffu, visibleEdge) >> gshift) & 0xfu;
+    if(vis4 == 0u) alive = false;  // !isAnyEdgeVisible
+    const bool allVisible = (vis4 == 0xfu);
+    int minIdx = idxEdge, maxIdx = idxEdge;
+#pragma unroll
+    for(int o = 1; o < 4; o <<= 1)
+    {
+      const int a = __shfl_xor_sync(0xffffffffu, minIdx, o);
+      const int b = __shfl_xor_sync(0xffffffffu, maxIdx, o);
+      minIdx = min(minIdx, a);
+      maxIdx = max(maxIdx, b);
+    }
+
+    // TsdGridComponent.cpp:96-118: the beams between the outermost edge beams.  Narrow intervals are scanned by
+    // the partition's four lanes, wide ones (partitions next to the sensor) by the whole warp.
+    bool vis = false, empty = true;
+    const bool wide = alive && (maxIdx - minIdx > 96);
+    if(alive && !wide)
+    {
+      for(int j = minIdx + sub; j <= maxIdx; j += 4)
       {
-        if(owned) pp.emptied[atomicAdd(&pp.counters[1], 1u)] = (uint32_t)p;
+        const double d = s.ranges[j];
+        const bool m = s.mask[j] != 0;
+        vis = vis || ((d > closest) && m);
+        if(isinf(d)) empty = empty && (distance < s.low_refl);
+        else empty = empty && (d > farthest) && m;
       }
+    }
+    unsigned wideLeaders = __ballot_sync(0xffffffffu, wide && sub == 0);
+    while(wideLeaders)
+    {
+      const int gl = __ffs(wideLeaders) - 1;
+      wideLeaders &= wideLeaders - 1;
+      const int lo = __shfl_sync(0xffffffffu, minIdx, gl), hi = __shfl_sync(0xffffffffu, maxIdx, gl);
+      const double cl = __shfl_sync(0xffffffffu, closest, gl), fa = __shfl_sync(0xffffffffu, farthest, gl);
+      const double di = __shfl_sync(0xffffffffu, distance, gl);
+      bool v = false, e = true;
+      for(int j = lo + lane; j <= hi; j += 32)
+      {
+        const double d = s.ranges[j];
+        const bool m = s.mask[j] != 0;
+        v = v || ((d > cl) && m);
+        if(isinf(d)) e = e && (di < s.low_refl);
+        else e = e && (d > fa) && m;
+      }
+      const bool anyV = __any_sync(0xffffffffu, v);
+      const bool allE = __all_sync(0xffffffffu, e);
+      if((lane >> 2) == (gl >> 2)) { vis = anyV; empty = allE; }
+    }
+    const unsigned mVis = __ballot_sync(0xffffffffu, vis);
+    const unsigned mEmpty = __ballot_sync(0xffffffffu, empty);
+    if(!alive || (mVis & gmask) == 0u || sub != 0) continue;
+    const bool allEmpty = (mEmpty & gmask) == gmask;
+    if(!stateKnown)
+    {
+      wasInit = wasInitBefore = pp.flags[p] != 0;
+      stateKnown = true;
+    }
+    if(allVisible && allEmpty)
+    {
+      // increaseEmptiness (TsdGridPartition.cpp:136-164)
+      if(wasInit) kinds |= 1u << (2 * si);
       else
       {
         double w = pp.initw[p];
@@ -307,33 +326,44 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
         w = ob_min(w, TSD_MAXWEIGHT);
         pp.initw[p] = w;
       }
-      if(owned) atomicAdd(&pp.counters[6], 1u);  // statistics count a band's own partitions
+      nEmptied++;
     }
-    return;
+    else
+    {
+      // active: TsdGrid.cpp:237-243
+      double distCentroid = sqrt((cenx - trx) * (cenx - trx) + (ceny - try_) * (ceny - try_));
+      if(distCentroid > s.max_range) distCentroid = s.max_range;
+      double partWeight = (s.max_range - distCentroid) / s.max_range;
+      partWeight *= partWeight;
+      double w = 0.01;  // TsdGridPartition.h:194-196 (the fabs(sd) < _eps branch is dead: _eps < 0)
+      w *= partWeight;
+      wItem[si] = w;
+      kinds |= 2u << (2 * si);
+      if(!wasInit)
+      {
+        pp.flags[p] = 1;
+        wasInit = true;
+        allocatedHere = true;
+      }
+      nActive++;
+    }
   }
-  // active: TsdGrid.cpp:237-243
-  if(sub == 0)
+  if(sub != 0 || !owned) return;  // lists and statistics are about a band's own partitions
+  if(kinds)
   {
-    double distCentroid = sqrt((cenx - trx) * (cenx - trx) + (ceny - try_) * (ceny - try_));
-    if(distCentroid > s.max_range) distCentroid = s.max_range;
-    double partWeight = (s.max_range - distCentroid) / s.max_range;
-    partWeight *= partWeight;
-    double w = 0.01;  // TsdGridPartition.h:194-196 (the fabs(sd) < _eps branch is dead: _eps < 0)
-    w *= partWeight;
-    if(owned)
-    {
-      const uint32_t slot = atomicAdd(&pp.counters[0], 1u);
-      pp.active[slot] = (uint32_t)p | (wasInit ? 0x80000000u : 0u);
-      pp.active_w[slot] = w;
-    }
-    if(!wasInit)
-    {
-      pp.flags[p] = 1;
-      if(owned) atomicAdd(&pp.counters[4], 1u);
-      if(owned) pp.newly[atomicAdd(&pp.counters[18], 1u)] = (uint32_t)p;
-    }
-    if(owned) atomicAdd(&pp.counters[7], 1u);
+    const uint32_t slot = atomicAdd(&pp.counters[0], 1u);
+    pp.active[slot] = (uint32_t)p | (wasInitBefore ? 0x80000000u : 0u);
+    pp.kinds[slot] = kinds;
+#pragma unroll
+    for(int si = 0; si < NS; si++) pp.active_w[(size_t)si * pp.list_cap + slot] = wItem[si];
   }
+  if(allocatedHere)
+  {
+    atomicAdd(&pp.counters[4], 1u);
+    pp.newly[atomicAdd(&pp.counters[18], 1u)] = (uint32_t)p;
+  }
+  if(nEmptied) atomicAdd(&pp.counters[6], nEmptied);
+  if(nActive) atomicAdd(&pp.counters[7], nActive);
 }
 
 #define UPDATE_THREADS 256
@@ -393,10 +423,10 @@ __device__ __forceinline__ int beam_index_fast(const BeamModel& bm, const double
 // Two horizontally adjacent cells of TsdGrid.cpp:250-274 + TsdGridPartition::addTsd (TsdGridPartition.h:170-212),
 // written straight-line so that the two dependency chains interleave; only the division is skipped when neither
 // cell is rewritten.  Returns the number of cells rewritten (0..2).
-__device__ __forceinline__ unsigned update_pair(const PushParams& pp, const double2 cA, const double2 cB, const double2 cD,
-                                                double rA, double rB, double rD, double wTile, double2& tv, double2& wv)
+__device__ __forceinline__ unsigned update_pair(const PushParams& pp, const ScanDev& s, const double2 cA, const double2 cB,
+                                                const double2 cD, double rA, double rB, double rD, double wTile, double2& tv,
+                                                double2& wv)
 {
-  const ScanDev& s = pp.scan;
   const double x0 = (cA.x + rA) + s.Pi[2] * 1.0;
   const double y0 = (cB.x + rB) + s.Pi[5] * 1.0;
   const double x1 = (cA.y + rA) + s.Pi[2] * 1.0;
@@ -518,13 +548,15 @@ __device__ __forceinline__ void push_tail(const PushParams& pp);
 // K2 + K3.  Persistent CTAs with a two-stage cp.async pipeline over their partitions.
 // Thread t of 256 owns the cell pair x = 2*(t%16), 2*(t%16)+1 in rows t/16 and t/16 + 16: a warp reads two
 // adjacent 256-B rows (512 contiguous bytes) per 16-byte vector load.
-template <int CTAS_PER_SM>
+// A work-list entry carries the outcome of every scan of the launch for its partition (k_classify); the scans are
+// applied one after the other to the cells while they sit in registers, so a partition seen by both lasers of a
+// robot is read and written once.
+template <int CTAS_PER_SM, int NS>
 __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushParams pp)
 {
-  // the scan (8.6 KB + 1 KB) and the beam-boundary table (17 KB) are read through L1 (read-only path): they
+  // the scans (8.6 KB + 1 KB each) and the beam-boundary table (17 KB) are read through L1 (read-only path): they
   // stay resident per SM for the whole launch, with no per-CTA staging pass
-  const uint32_t nActive = pp.counters[0];
-  const uint32_t nItems = nActive + pp.counters[1];
+  const uint32_t nItems = pp.counters[0];
   const int t = threadIdx.x;
   const int xp = (t & 15) * 2;
   const int yb = t >> 4;
@@ -533,16 +565,11 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
   unsigned long long updatesWide = 0;
 
   // list entry of item `it`: partition index, bit 31 = its cells existed before this push (so they are read)
-  auto entry = [&](uint32_t it) -> uint32_t
-  {
-    if(it >= nItems) return 0xffffffffu;
-    return (it < nActive) ? pp.active[it] : (pp.emptied[it - nActive] | 0x80000000u);
-  };
+  auto entry = [&](uint32_t it) -> uint32_t { return (it < nItems) ? pp.active[it] : 0xffffffffu; };
 
   // Two-stage pipeline over the CTA's partitions: the 16 KB of cell state of partition i+1 are copied into
   // shared memory with cp.async (LDGSTS, L1 bypass) while partition i is computed.  Every thread copies exactly
   // the four 16-byte pieces it will read itself, so the only synchronisation is its own cp.async.wait_group.
-  // The list entries themselves are fetched two items ahead, so no address waits on a load.
   __shared__ __align__(16) double2 s_cells[2][2][2 * UPDATE_THREADS];  // [stage][tsd|weight][row j * 256 + t]
   auto stage_in = [&](uint32_t e, int stage)
   {
@@ -563,14 +590,14 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
   };
 
   // Static striding over the item list (a ticket counter with one __syncthreads per item was measured slower:
-  // 55 us vs 48 us on C2).  The per-item metadata -- list entry, partition weight, which neighbours are allocated
-  // (mirror targets -x/-y/-xy, border sources +x/+y/+xy) -- is fetched for 32 items at a time by the first warp
-  // and parked in shared memory: one memory round trip and two barriers per 32 items instead of dependent global
-  // loads in front of every item (on maps beyond L2 those were half of all stall samples).
+  // 55 us vs 48 us on C2).  The per-item metadata -- list entry, scan outcomes, partition weights, which neighbours
+  // are allocated (mirror targets -x/-y/-xy, border sources +x/+y/+xy) -- is fetched for 32 items at a time by the
+  // first warps and parked in shared memory: one memory round trip and two barriers per 32 items instead of
+  // dependent global loads in front of every item (on maps beyond L2 those were half of all stall samples).
   const uint32_t G = gridDim.x;
   __shared__ uint32_t s_ent[ITEM_CHUNK + 1];
-  __shared__ uint32_t s_nbm[ITEM_CHUNK];
-  __shared__ double s_wt[ITEM_CHUNK];
+  __shared__ uint32_t s_nbm[ITEM_CHUNK];   // bits 0-5 neighbour masks, bits 8.. the 2-bit outcomes of the scans
+  __shared__ double s_wt[NS][ITEM_CHUNK];
   int stage = 0;
   for(uint32_t chunk0 = blockIdx.x; chunk0 < nItems; chunk0 += ITEM_CHUNK * G)
   {
@@ -582,12 +609,13 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
       s_ent[t] = e;
       if(t < ITEM_CHUNK && e != 0xffffffffu)
       {
-        s_wt[t] = (it < nActive) ? pp.active_w[it] : 0.0;
+#pragma unroll
+        for(int si = 0; si < NS; si++) s_wt[si][t] = pp.active_w[(size_t)si * pp.list_cap + it];
         const int p = (int)(e & 0x7fffffffu);
         const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
         const bool hasL = px > 0, hasD = py > pp.row_begin;
         const bool hasR = px < pp.parts_x - 1, hasU = py < pp.parts_y - 1;
-        unsigned m = 0;
+        unsigned m = pp.kinds[it] << 8;
         if(hasL && pp.flags[p - 1]) m |= 1u;
         if(hasD && pp.flags[p - pp.parts_x]) m |= 2u;
         if(hasL && hasD && pp.flags[p - pp.parts_x - 1]) m |= 4u;
@@ -601,98 +629,117 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
     if(chunk0 == blockIdx.x) stage_in(s_ent[0], 0);
     for(int k = 0; k < ITEM_CHUNK; k++, stage ^= 1)
     {
-    const uint32_t item = chunk0 + (uint32_t)k * G;
-    if(item >= nItems) break;
-    const uint32_t eCur = s_ent[k];
-    stage_in(s_ent[k + 1], stage ^ 1);
-    const unsigned nbm = s_nbm[k];
-    const unsigned nb = edge ? (nbm & 7u) : 0u;
-    const uint32_t p = eCur & 0x7fffffffu;
-    const bool wasInit = (eCur & 0x80000000u) != 0;
-    const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
-    const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
-    double* T = pp.tsd + base;
-    double* W = pp.weight + base;
-    if(item < nActive)
-    {
-      const double wTile = s_wt[k];
-      const int gx = px * TSD_TILE + xp;
-      const int gy = py * TSD_TILE + yb;
-      const double2 cA = *reinterpret_cast<const double2*>(pp.coltab + gx);
-      const double2 cB = *reinterpret_cast<const double2*>(pp.coltab + pp.cells_x + gx);
-      const double2 cD = *reinterpret_cast<const double2*>(pp.coltab + 2 * pp.cells_x + gx);
-      double rA[2], rB[2], rD[2];
-#pragma unroll
-      for(int j = 0; j < 2; j++)
-      {
-        rA[j] = pp.rowtab[gy + 16 * j];
-        rB[j] = pp.rowtab[pp.cells_y + gy + 16 * j];
-        rD[j] = pp.rowtab[2 * pp.cells_y + gy + 16 * j];
-      }
-      double initT = 0.0, initW = 0.0;
-      if(!wasInit)
-      {
-        // TsdGridPartition::init (TsdGridPartition.cpp:98-119)
-        initW = pp.initw[p];
-        initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
-      }
+      const uint32_t item = chunk0 + (uint32_t)k * G;
+      if(item >= nItems) break;
+      const uint32_t eCur = s_ent[k];
+      stage_in(s_ent[k + 1], stage ^ 1);
+      const unsigned nbm = s_nbm[k];
+      const unsigned nb = edge ? (nbm & 7u) : 0u;
+      const unsigned kinds = nbm >> 8;
+      const uint32_t p = eCur & 0x7fffffffu;
+      const bool wasInit = (eCur & 0x80000000u) != 0;
+      const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
+      const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
+      double* T = pp.tsd + base;
+      double* W = pp.weight + base;
+      // the border cell this thread looks after (t < 65): only strips WITHOUT an allocated source neighbour are
+      // the partition's own business (the others mirror the neighbour, which keeps them current)
+      const bool myStrip = t < 65 && !((nbm >> (t < 32 ? 3 : (t < 64 ? 4 : 5))) & 1u);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
+      double2 tv[2], wv[2];
+      double bt = 0.0, bw = 0.0;
+      bool alloc = wasInit, dirty[2] = {false, false}, stripDirty = false;
+      if(wasInit)
+      {
+#pragma unroll
+        for(int j = 0; j < 2; j++)
+        {
+          tv[j] = s_cells[stage][0][j * UPDATE_THREADS + t];
+          wv[j] = s_cells[stage][1][j * UPDATE_THREADS + t];
+        }
+        if(myStrip && (kinds & 0x5u))  // some scan runs increaseEmptiness over the border cells too
+        {
+          bt = T[TSD_BORDER_OFF + t];
+          bw = W[TSD_BORDER_OFF + t];
+        }
+      }
+#pragma unroll
+      for(int si = 0; si < NS; si++)
+      {
+        const unsigned kind = (kinds >> (2 * si)) & 3u;
+        if(kind == 2u)
+        {
+          const ScanDev& sc = pp.scans[si];
+          const double* ct = pp.coltab + (size_t)si * 3 * pp.cells_x;
+          const double* rt = pp.rowtab + (size_t)si * 3 * pp.cells_y;
+          const double wTile = s_wt[si][k];
+          const int gx = px * TSD_TILE + xp;
+          const int gy = py * TSD_TILE + yb;
+          const double2 cA = *reinterpret_cast<const double2*>(ct + gx);
+          const double2 cB = *reinterpret_cast<const double2*>(ct + pp.cells_x + gx);
+          const double2 cD = *reinterpret_cast<const double2*>(ct + 2 * pp.cells_x + gx);
+          if(!alloc)
+          {
+            // TsdGridPartition::init (TsdGridPartition.cpp:98-119)
+            const double initW = pp.initw[p];
+            const double initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+            for(int j = 0; j < 2; j++)
+            {
+              tv[j] = make_double2(initT, initT);
+              wv[j] = make_double2(initW, initW);
+              dirty[j] = true;
+            }
+            bt = initT;
+            bw = initW;
+            stripDirty = true;
+            alloc = true;
+          }
+#pragma unroll
+          for(int j = 0; j < 2; j++)
+          {
+            const double rA = rt[gy + 16 * j];
+            const double rB = rt[pp.cells_y + gy + 16 * j];
+            const double rD = rt[2 * pp.cells_y + gy + 16 * j];
+            const unsigned u = update_pair(pp, sc, cA, cB, cD, rA, rB, rD, wTile, tv[j], wv[j]);
+            updates += u;
+            dirty[j] = dirty[j] || (u != 0u);
+          }
+        }
+        else if(kind == 1u)
+        {
+          // K3: increaseEmptiness on an allocated partition, all 33x33 cells
+#pragma unroll
+          for(int j = 0; j < 2; j++)
+          {
+            empty_pair(tv[j], wv[j]);
+            dirty[j] = true;
+          }
+          if(myStrip)
+          {
+            empty_cell(bt, bw);
+            stripDirty = true;
+          }
+          if(t == 0) updatesWide += 33 * 33;
+        }
+      }
 #pragma unroll
       for(int j = 0; j < 2; j++)
       {
         const int y = yb + 16 * j;
         const int ci = y * TSD_TILE + xp;
-        double2 tv, wv;
-        if(wasInit)
+        if(dirty[j])
         {
-          tv = s_cells[stage][0][j * UPDATE_THREADS + t];
-          wv = s_cells[stage][1][j * UPDATE_THREADS + t];
+          *reinterpret_cast<double2*>(T + ci) = tv[j];
+          *reinterpret_cast<double2*>(W + ci) = wv[j];
         }
-        else
-        {
-          tv = make_double2(initT, initT);
-          wv = make_double2(initW, initW);
-        }
-        const unsigned u = update_pair(pp, cA, cB, cD, rA[j], rB[j], rD[j], wTile, tv, wv);
-        updates += u;
-        if(!wasInit || u)
-        {
-          *reinterpret_cast<double2*>(T + ci) = tv;
-          *reinterpret_cast<double2*>(W + ci) = wv;
-        }
-        if(nb) mirror_to_neighbours(pp, nb, base, xp, y, tv, wv);
+        if(nb) mirror_to_neighbours(pp, nb, base, xp, y, tv[j], wv[j]);
       }
-      if(!wasInit && t < 65 && !((nbm >> (t < 32 ? 3 : (t < 64 ? 4 : 5))) & 1u))
+      if(myStrip && stripDirty)
       {
-        T[TSD_BORDER_OFF + t] = initT;
-        W[TSD_BORDER_OFF + t] = initW;
+        T[TSD_BORDER_OFF + t] = bt;
+        W[TSD_BORDER_OFF + t] = bw;
       }
-    }
-    else
-    {
-      // K3: increaseEmptiness on an initialised partition, all 33x33 cells
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-#pragma unroll
-      for(int j = 0; j < 2; j++)
-      {
-        const int y = yb + 16 * j;
-        const int ci = y * TSD_TILE + xp;
-        double2 tv = s_cells[stage][0][j * UPDATE_THREADS + t];
-        double2 wv = s_cells[stage][1][j * UPDATE_THREADS + t];
-        empty_pair(tv, wv);
-        *reinterpret_cast<double2*>(T + ci) = tv;
-        *reinterpret_cast<double2*>(W + ci) = wv;
-        if(nb) mirror_to_neighbours(pp, nb, base, xp, y, tv, wv);
-      }
-      if(t < 65 && !((nbm >> (t < 32 ? 3 : (t < 64 ? 4 : 5))) & 1u))
-      {
-        double tv = T[TSD_BORDER_OFF + t], wv = W[TSD_BORDER_OFF + t];
-        empty_cell(tv, wv);
-        T[TSD_BORDER_OFF + t] = tv;
-        W[TSD_BORDER_OFF + t] = wv;
-      }
-      if(t == 0) updatesWide += 33 * 33;
-    }
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1085,6 +1132,8 @@ static PushParams make_params(const tsd_grid* g)
   pp.initw = g->d_initw;
   pp.active = g->d_active;
   pp.active_w = g->d_active_w;
+  pp.kinds = g->d_kinds;
+  pp.list_cap = g->n_owned;
   pp.emptied = g->d_emptied;
   pp.newly = g->d_newly;
   pp.pending = g->d_pending;
@@ -1116,7 +1165,8 @@ int grid_ensure_scratch(tsd_grid* g, size_t bytes)
 }
 
 // One device block and one pinned mirror hold everything a scan brings with it, so that staging is a single
-// H2D copy:  [ ranges: cap doubles | mask: cap bytes | rays: 2*cap doubles ].  The ray-caster's results come
+// H2D copy:  [ ranges: cap doubles | mask: cap bytes | ranges of a second scan | its mask | rays: 2*cap doubles ]
+// (a push copies the first two or four parts, a ray cast everything).  The ray-caster's results come
 // back in one D2H copy of  [ out: 4*cap doubles | keys: cap u64 | steps: 2 u64 ].
 static int ensure_scan_capacity(tsd_grid* g, int n)
 {
@@ -1125,7 +1175,7 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
   cudaFree(g->d_in); cudaFree(g->d_dirs); cudaFree(g->d_rc);
   cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc);
   const int cap = ((n + 63) / 64) * 64 + 64;
-  g->in_bytes = sizeof(double) * cap + cap + sizeof(double) * 2 * cap;
+  g->in_bytes = 2 * (sizeof(double) * cap + cap) + sizeof(double) * 2 * cap;
   g->rc_bytes = sizeof(double) * 4 * cap + sizeof(unsigned long long) * cap + sizeof(unsigned long long) * 2;
   TSD_CUDA(cudaMalloc(&g->d_in, g->in_bytes));
   TSD_CUDA(cudaMalloc(&g->d_rc, g->rc_bytes));
@@ -1136,10 +1186,10 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
   memset(g->h_rc, 0, g->rc_bytes);
   g->d_ranges = reinterpret_cast<double*>(g->d_in);
   g->d_mask = g->d_in + sizeof(double) * cap;
-  g->d_rays = reinterpret_cast<double*>(g->d_in + sizeof(double) * cap + cap);
+  g->d_rays = reinterpret_cast<double*>(g->d_in + 2 * (sizeof(double) * cap + cap));
   g->h_ranges = reinterpret_cast<double*>(g->h_in);
   g->h_mask = g->h_in + sizeof(double) * cap;
-  g->h_rays = reinterpret_cast<double*>(g->h_in + sizeof(double) * cap + cap);
+  g->h_rays = reinterpret_cast<double*>(g->h_in + 2 * (sizeof(double) * cap + cap));
   g->d_rc_out = reinterpret_cast<double*>(g->d_rc);
   g->d_rc_keys = reinterpret_cast<unsigned long long*>(g->d_rc + sizeof(double) * 4 * cap);
   g->d_rc_steps = g->d_rc_keys + cap;
@@ -1154,23 +1204,41 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
 
 int grid_stage_scan(tsd_grid* g, const tsd_scan_t* scan, ScanDev* sd, const double* rays_world)
 {
-  if(!scan || scan->n < 1 || !scan->ranges || !scan->mask) { set_error("invalid scan"); return TSD_E_INVALID; }
+  return grid_stage_scans(g, scan, 1, sd, rays_world);
+}
+
+// Stages 1 or 2 scans (same sensor model) with ONE H2D copy; sd[i] gets scan i.
+int grid_stage_scans(tsd_grid* g, const tsd_scan_t* scans, int n, ScanDev* sd, const double* rays_world)
+{
+  if(!scans || n < 1 || n > PUSH_MAX_SCANS) { set_error("invalid scan batch"); return TSD_E_INVALID; }
+  for(int i = 0; i < n; i++)
+    if(scans[i].n < 1 || !scans[i].ranges || !scans[i].mask) { set_error("invalid scan"); return TSD_E_INVALID; }
+  const tsd_scan_t* scan = &scans[0];
+  if(n == 2 && (scans[1].n != scan->n || scans[1].phi_min != scan->phi_min || scans[1].angular_res != scan->angular_res))
+  {
+    set_error("the scans of a batch must come from the same sensor model");
+    return TSD_E_INVALID;
+  }
   int rc = ensure_scan_capacity(g, scan->n);
   if(rc) return rc;
-  fill_scan_dev(scan, sd);
   // the previous call's async copy out of the pinned staging block must have drained
   TSD_CUDA(cudaStreamSynchronize(g->stream));
-  memcpy(g->h_ranges, scan->ranges, sizeof(double) * scan->n);
-  memcpy(g->h_mask, scan->mask, scan->n);
-  size_t bytes = sizeof(double) * g->scan_cap + scan->n;
+  const size_t slotBytes = sizeof(double) * g->scan_cap + g->scan_cap;
+  for(int i = 0; i < n; i++)
+  {
+    fill_scan_dev(&scans[i], &sd[i]);
+    memcpy(g->h_in + i * slotBytes, scans[i].ranges, sizeof(double) * scans[i].n);
+    memcpy(g->h_in + i * slotBytes + sizeof(double) * g->scan_cap, scans[i].mask, scans[i].n);
+    sd[i].ranges = reinterpret_cast<double*>(g->d_in + i * slotBytes);
+    sd[i].mask = g->d_in + i * slotBytes + sizeof(double) * g->scan_cap;
+  }
+  size_t bytes = (n - 1) * slotBytes + sizeof(double) * g->scan_cap + scan->n;
   if(rays_world)
   {
     memcpy(g->h_rays, rays_world, sizeof(double) * 2 * scan->n);
-    bytes = sizeof(double) * g->scan_cap + g->scan_cap + sizeof(double) * 2 * scan->n;
+    bytes = 2 * slotBytes + sizeof(double) * 2 * scan->n;
   }
   TSD_CUDA(cudaMemcpyAsync(g->d_in, g->h_in, bytes, cudaMemcpyHostToDevice, g->stream));
-  sd->ranges = g->d_ranges;
-  sd->mask = g->d_mask;
   if(g->dirs_n != scan->n || g->dirs_phi_min != scan->phi_min || g->dirs_res != scan->angular_res)
   {
     // directions of the half-beam boundaries B_k = phiMin + (k - 1/2) res, k = 0..n (beam_index.cuh)
@@ -1326,7 +1394,7 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMalloc(&g->d_flags, g->n_parts));
   TSD_CUDA(cudaMalloc(&g->d_initw, sizeof(double) * g->n_parts));
   TSD_CUDA(cudaMalloc(&g->d_active, sizeof(uint32_t) * g->n_owned));
-  TSD_CUDA(cudaMalloc(&g->d_active_w, sizeof(double) * g->n_owned));
+  TSD_CUDA(cudaMalloc(&g->d_active_w, sizeof(double) * g->n_owned * PUSH_MAX_SCANS));
   TSD_CUDA(cudaMalloc(&g->d_emptied, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_newly, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_signal, sizeof(uint32_t) * 8));
@@ -1334,8 +1402,9 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMalloc(&g->d_pending, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_counters, sizeof(uint32_t) * 32));
   TSD_CUDA(cudaMalloc(&g->d_stats64, sizeof(unsigned long long) * 4));
-  TSD_CUDA(cudaMalloc(&g->d_coltab, sizeof(double) * 3 * g->cells_x));
-  TSD_CUDA(cudaMalloc(&g->d_rowtab, sizeof(double) * 3 * g->cells_y));
+  TSD_CUDA(cudaMalloc(&g->d_coltab, sizeof(double) * 3 * g->cells_x * PUSH_MAX_SCANS));
+  TSD_CUDA(cudaMalloc(&g->d_rowtab, sizeof(double) * 3 * g->cells_y * PUSH_MAX_SCANS));
+  TSD_CUDA(cudaMalloc(&g->d_kinds, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMallocHost(&g->h_counters, sizeof(uint32_t) * 32));
   TSD_CUDA(cudaMallocHost(&g->h_stats64, sizeof(unsigned long long) * 4));
   TSD_CUDA(cudaMemsetAsync(g->d_flags, 0, g->n_parts, g->stream));
@@ -1365,7 +1434,7 @@ int tsdg_destroy(tsd_grid_t* g)
       cudaIpcCloseMemHandle(g->peer[b].tsd); cudaIpcCloseMemHandle(g->peer[b].weight); cudaIpcCloseMemHandle(g->peer[b].signal);
     }
   cudaFree(g->d_pending); cudaFree(g->d_counters);
-  cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_dirs); cudaFree(g->d_in);
+  cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_kinds); cudaFree(g->d_dirs); cudaFree(g->d_in);
   cudaFree(g->d_rc); cudaFree(g->d_scratch);
   cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters);
   cudaFreeHost(g->h_stats64);
@@ -1455,13 +1524,16 @@ static void scan_partition_box(const tsd_grid* g, double tx, double ty, double m
   }
 }
 
-int tsdg_stage_scan(tsd_grid_t* g, const tsd_scan_t* scan)
+int tsdg_stage_scan(tsd_grid_t* g, const tsd_scan_t* scan) { return tsdg_stage_batch(g, scan, 1); }
+
+int tsdg_stage_batch(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
 {
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
-  int rc = grid_stage_scan(g, scan, &g->staged, nullptr);
+  int rc = grid_stage_scans(g, scans, n, g->staged, nullptr);
   if(rc) return rc;
   g->has_staged = true;
+  g->staged_n = n;
   return TSD_OK;
 }
 
@@ -1470,15 +1542,24 @@ int tsdg_push_staged(tsd_grid_t* g)
   if(!g || !g->has_staged) { set_error("no staged scan"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));
   PushParams pp = make_params(g);
-  pp.scan = g->staged;
+  const int ns = g->staged_n;
+  pp.nscan = ns;
+  for(int i = 0; i < ns; i++) pp.scans[i] = g->staged[i];
   pp.dirs = g->d_dirs;
   g->stats_fresh = false;
-  const tsd::ScanDev* scan = &g->staged;
-  // counters [0] active [1] emptied are per push; [2] pending and [3] refresh-all persist until consumed below
-  // (pending [2] and refresh-all [3] were zeroed by the previous push's tail; [0..1], [4..7] and the 64-bit
-  //  statistics are zeroed by k_tables' first thread)
+  // counters [0] work-list entries, [4..7] statistics are per push; [2] pending and [3] refresh-all persist until
+  // consumed by the push tail, which also zeroes the per-push ones
   int box[4];
-  scan_partition_box(g, pp.scan.P[2], pp.scan.P[5], pp.scan.max_range, box);
+  scan_partition_box(g, pp.scans[0].P[2], pp.scans[0].P[5], pp.scans[0].max_range, box);
+  for(int i = 1; i < ns; i++)
+  {
+    int b2[4];
+    scan_partition_box(g, pp.scans[i].P[2], pp.scans[i].P[5], pp.scans[i].max_range, b2);
+    box[0] = b2[0] < box[0] ? b2[0] : box[0];
+    box[1] = b2[1] < box[1] ? b2[1] : box[1];
+    box[2] = b2[2] > box[2] ? b2[2] : box[2];
+    box[3] = b2[3] > box[3] ? b2[3] : box[3];
+  }
   if(g->band)
   {
     // a band keeps allocation flags / emptiness weights of its own rows and of the two rows next to them
@@ -1495,11 +1576,12 @@ int tsdg_push_staged(tsd_grid_t* g)
   const int nmax = TSD_TILE * (pp.cl_w > pp.cl_h ? pp.cl_w : pp.cl_h);
   const int nthreads = (4 * pp.cl_w * pp.cl_h > nmax) ? 4 * pp.cl_w * pp.cl_h : nmax;
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[0], g->stream));
-  k_classify<<<(nthreads + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
+  const int cctas = (nthreads + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS;
+  if(ns == 2) k_classify<2><<<cctas, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
+  else k_classify<1><<<cctas, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[1], g->stream));
   const size_t smem = 0;
-  (void)scan;
   static const int ctasPerSm = []{ const char* e = getenv("TSD_UPDATE_CTAS"); const int v = e ? atoi(e) : UPDATE_CTAS_PER_SM; return (v == 3 || v == 4) ? v : UPDATE_CTAS_PER_SM; }();
   int ctas = g->sm_count * ctasPerSm;
   if(ctas > g->n_owned) ctas = g->n_owned;
@@ -1507,8 +1589,16 @@ int tsdg_push_staged(tsd_grid_t* g)
   // strips that depend on the halo row above the band are refreshed after the exchange, tsdg_band_push_finish.)
   pp.fused_tail = g->refresh_all_pending ? 0 : 1;
   if(g->band) g->band_push_open = true;
-  if(ctasPerSm == 3) k_update<3><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
-  else k_update<4><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+  if(ns == 2)
+  {
+    if(ctasPerSm == 3) k_update<3, 2><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+    else k_update<4, 2><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+  }
+  else
+  {
+    if(ctasPerSm == 3) k_update<3, 1><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+    else k_update<4, 1><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+  }
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[2], g->stream));
   if(pp.fused_tail)
@@ -1538,6 +1628,39 @@ int tsdg_push_async(tsd_grid_t* g, const tsd_scan_t* scan)
   int rc = tsdg_stage_scan(g, scan);
   if(rc) return rc;
   return tsdg_push_staged(g);
+}
+
+// Integrates n scans in the order given, as n TsdGrid::push calls would (ThreadMapping::eventLoop drains its queue of
+// sensors one push after the other, ThreadMapping.cpp:43-62).  Two scans of the same sensor model at a time share
+// one classify + one update launch: partitions both scans touch are read and written once.
+int tsdg_push_batch_async(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
+{
+  if(!g || !scans || n < 1) return TSD_E_INVALID;
+  int i = 0;
+  while(i < n)
+  {
+    int take = 1;
+    if(i + 1 < n && scans[i + 1].n == scans[i].n && scans[i + 1].phi_min == scans[i].phi_min &&
+       scans[i + 1].angular_res == scans[i].angular_res)
+      take = 2;
+    int rc = tsdg_stage_batch(g, scans + i, take);
+    if(rc) return rc;
+    rc = tsdg_push_staged(g);
+    if(rc) return rc;
+    i += take;
+  }
+  return TSD_OK;
+}
+
+int tsdg_push_batch(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
+{
+  int rc = tsdg_push_batch_async(g, scans, n);
+  if(rc) return rc;
+  // statistics of the LAST launch of the batch (both scans of a pair together) come back with the synchronisation
+  TSD_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(uint32_t) * 24, cudaMemcpyDeviceToHost, g->stream));
+  rc = tsdg_sync(g);
+  g->stats_fresh = (rc == TSD_OK);
+  return rc;
 }
 
 void* tsdg_stream(tsd_grid_t* g) { return g ? (void*)g->stream : nullptr; }
@@ -1792,7 +1915,7 @@ int tsdg_last_push_stats(tsd_grid_t* g, tsd_push_stats_t* out)
   }
   out->cell_updates = (uint64_t)g->h_counters[20] | ((uint64_t)g->h_counters[21] << 32);
   out->active_tiles = g->h_counters[8 + 7];
-  out->cell_visits = (uint64_t)g->h_counters[8 + 0] * TSD_TILE_CELLS;
+  out->cell_visits = (uint64_t)g->h_counters[8 + 7] * TSD_TILE_CELLS;
   out->emptied_tiles = g->h_counters[8 + 6];
   out->newly_initialized = g->h_counters[8 + 4];
   out->fallback_cells = g->h_counters[8 + 5];
