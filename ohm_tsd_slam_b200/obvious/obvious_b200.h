@@ -456,6 +456,18 @@ public:
     OBVIOUS_B200_CHECK(tsdg_push(_h, &s));
     _pushed = true;
   }
+  // Not in the reference: every queued sensor in one call, with the result of push() on each in turn.
+  // ThreadMapping::eventLoop drains its queue exactly like that (ThreadMapping.cpp:43-62); two sensors of the same
+  // model (the two lasers of a robot) then share one classification and one cell-update launch (tsdg_push_batch).
+  void pushBatch(const std::vector<SensorPolar2D*>& sensors)
+  {
+    if(sensors.empty()) return;
+    std::vector<tsd_scan_t> s(sensors.size());
+    std::vector<std::vector<uint8_t> > m(sensors.size());
+    for(size_t i = 0; i < sensors.size(); i++) sensors[i]->snapshot(&s[i], &m[i]);
+    OBVIOUS_B200_CHECK(tsdg_push_batch(_h, s.data(), (int32_t)s.size()));
+    _pushed = true;
+  }
   bool containsData() { return _pushed; }
   // TsdGrid.h:284-304
   EnumTsdGridInterpolate interpolateBilinear(obfloat coord[2], obfloat* tsd)
