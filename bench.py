@@ -264,8 +264,9 @@ def run_cuda(args):
 
     # ---------------- hypothesis scoring (BASELINE.json configs[3]: 10^5 hypotheses per scan; split over the ranks)
     from ohm_tsd_slam_b200.workload import hypothesis_benchmark
-    hyp = hypothesis_benchmark(device=local, n_hyp=100000, reps=2, dist=dist if world > 1 else None,
-                               cpu_sample=0 if (args.no_cpu_baseline or world > 1) else 1000)
+    want_cpu = not (args.no_cpu_baseline or world > 1)
+    hyp = hypothesis_benchmark(device=local, n_hyp=100000, reps=2, dist=dist if world > 1 else None, keep_inputs=want_cpu)
+    hyp_inputs = hyp.pop("_inputs", None)
 
     # ---------------- large-map push sweep (BASELINE.json configs[2]): the bandwidth regime of the push
     sweep = None
@@ -325,9 +326,42 @@ def run_cuda(args):
             line["cpu_baseline"] = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
             if pub is not None and "map_publication_ms" in b:
                 pub["reference_cpu_ms"] = b["map_publication_ms"]
+            if hyp_inputs is not None:
+                hyp["cpu_port_hypotheses_per_s"] = cpu_hypothesis_baseline(hyp_inputs, sample=1000)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_hypothesis_baseline(inp, sample: int):
+    """The three scorers of the plain-C port (one core) on the first `sample` hypotheses of the same workload."""
+    from ohm_tsd_slam_b200 import synth
+    from ohm_tsd_slam_b200.scan import HostSensor
+    from oracle import port
+    wl, cfg = inp["workload"], inp["cfg"]
+    gp = port.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)
+    gp.set_max_truncation(cfg.max_truncation)
+    hp = HostSensor(cfg.sensor, port.invert3x3)
+    for pose, r in inp["map_scans"]:
+        hp.set_scan(r)
+        hp.T = np.eye(3)
+        hp.rays = hp.rays_local.copy()
+        hp.ray_norm = 1.0
+        hp.transform(synth.pose_matrix(*pose))
+        gp.push(hp.scan())
+    h = wl.hyps[:sample]
+    cpu = {}
+    t0 = time.perf_counter()
+    port.score_tsd(gp, h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, inp["pose"], 0.25)
+    cpu["tsd"] = sample / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    port.score_rnm(h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, wl.phi_control, wl.model_valid, wl.phi_valid,
+                   wl.theta_min, wl.theta_max, 1.0 / 0.15 ** 2, 0.33, wl.control.shape[1] // 3)
+    cpu["rnm"] = sample / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    port.score_pdf(h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, wl.model_angles, wl.model_dists, wl.PDF_PARAMS)
+    cpu["pdf"] = sample / (time.perf_counter() - t0)
+    return dict(cpu, sample=sample, cores=1)
 
 
 def profiled_traffic(kernel: str):

@@ -187,12 +187,12 @@ class HypothesisWorkload:
                                  self.control, self.model_angles, self.model_dists, self.PDF_PARAMS)
 
 
-def hypothesis_benchmark(device: int = 0, n_hyp: int = 100000, reps: int = 3, dist=None, cpu_sample: int = 0):
+def hypothesis_benchmark(device: int = 0, n_hyp: int = 100000, reps: int = 3, dist=None, keep_inputs: bool = False):
     """C4 on the device: a C1 map, one scan, n_hyp hypotheses through the three scorers (C ABI, host buffers:
     H2D of hypotheses + control set and D2H of the per-hypothesis results inside the timing).  With `dist`
     (torch.distributed, one rank per GPU) the hypothesis list is split in contiguous slices and the winner merged
-    (sharded.merge_best_hypothesis); times are the max over ranks.  cpu_sample > 0 also times the oracle's port on
-    that many hypotheses (bench.py's cpu_baseline leg only)."""
+    (sharded.merge_best_hypothesis); times are the max over ranks.  keep_inputs: also return the inputs under
+    "_inputs" (bench.py's CPU baseline leg times a checker on a sample of them)."""
     import time
 
     from . import capi
@@ -252,31 +252,8 @@ def hypothesis_benchmark(device: int = 0, n_hyp: int = 100000, reps: int = 3, di
             amax(t)
             dt = float(t[0])
         out[name] = {"ms": dt * 1e3, "hypotheses_per_s": n_hyp / dt}
-    if cpu_sample > 0:
-        from oracle import port  # (bench.py cpu_baseline leg)
-        gp = port.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)
-        gp.set_max_truncation(cfg.max_truncation)
-        hp = HostSensor(cfg.sensor, port.invert3x3)
-        for pose2, r2 in scans[:3]:
-            hp.set_scan(r2)
-            hp.T = np.eye(3)
-            hp.rays = hp.rays_local.copy()
-            hp.ray_norm = 1.0
-            hp.transform(synth.pose_matrix(*pose2))
-            gp.push(hp.scan())
-        h = wl.hyps[:cpu_sample]
-        cpu = {}
-        t0 = time.perf_counter()
-        port.score_tsd(gp, h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, hs.pose, 0.25)
-        cpu["tsd"] = cpu_sample / (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        port.score_rnm(h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, wl.phi_control, wl.model_valid, wl.phi_valid,
-                       wl.theta_min, wl.theta_max, 1.0 / 0.15 ** 2, 0.33, wl.control.shape[1] // 3)
-        cpu["rnm"] = cpu_sample / (time.perf_counter() - t0)
-        t0 = time.perf_counter()
-        port.score_pdf(h, wl.M, wl.S, wl.phi_m, wl.phi_s, wl.phi_max, wl.control, wl.model_angles, wl.model_dists, wl.PDF_PARAMS)
-        cpu["pdf"] = cpu_sample / (time.perf_counter() - t0)
-        out["cpu_port_hypotheses_per_s"] = dict(cpu, sample=cpu_sample, cores=1)
+    if keep_inputs:
+        out["_inputs"] = {"workload": wl, "pose": hs.pose.copy(), "map_scans": scans[:3], "cfg": cfg}
     return out
 
 
