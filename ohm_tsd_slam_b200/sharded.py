@@ -168,6 +168,19 @@ class LocalBands:
         if sync:
             self.sync_halos()
 
+    def push_batch(self, scans, sync: bool = True):
+        """tsdg_push_batch on every band any of the scans can reach."""
+        boxes = [self.grids[0].scan_box(sc) for sc in scans]
+        self.pushed = [any(band_reached(bx, b, e) for bx in boxes) for (b, e) in self.rows]
+        for g, mine in zip(self.grids, self.pushed):
+            if mine:
+                g.push_batch_async(scans)
+        self.dirty = True
+        for bx in boxes:
+            self.dirty_cols.add(bx[0], bx[2])
+        if sync:
+            self.sync_halos()
+
     def sync_halos(self):
         if not getattr(self, "dirty", False):
             return
@@ -388,6 +401,15 @@ class DistBand:
         self.flags_dirty = True
         if self.note_scan(self._box(scan)):
             self.grid.push_async(scan)
+        if sync:
+            self.sync_halos()
+
+    def push_batch(self, scans, sync: bool = False):
+        """Every rank calls this with the same scans (tsdg_push_batch: the result of pushing them one by one)."""
+        self.flags_dirty = True
+        mine = [self.note_scan(self._box(sc)) for sc in scans]
+        if any(mine):
+            self.grid.push_batch_async(scans)
         if sync:
             self.sync_halos()
 

@@ -92,3 +92,23 @@ def test_scan_box_contains_every_touched_partition():
     assert len(touched) > 0
     assert (touched % parts_x >= px0).all() and (touched % parts_x <= px1).all()
     assert (touched // parts_x >= py0).all() and (touched // parts_x <= py1).all()
+
+
+def test_batched_pushes_on_bands():
+    """Two scans per launch pair (tsdg_push_batch) on a sharded grid == the same scans pushed one by one into the
+    unsharded grid."""
+    from ohm_tsd_slam_b200.workload import DoubleLaserWorkload
+    wl = DoubleLaserWorkload("C1", n_map=4, n_steps=2, invert=capi.invert3x3)
+    cfg = wl.cfg
+    whole = capi.Grid(cfg.cell_size, 5, cfg.layout_grid)
+    parts = LocalBands(cfg.cell_size, cfg.layout_grid, 3, peer=True)
+    whole.set_max_truncation(cfg.max_truncation)
+    parts.set_max_truncation(cfg.max_truncation)
+    scans = wl.map_scans + [sc for st in wl.step_scans for sc in st]
+    for k in range(0, len(scans), 2):
+        for sc in scans[k:k + 2]:
+            whole.push(sc)
+        parts.push_batch(scans[k:k + 2], sync=(k % 4 == 2))
+    parts.sync_halos()
+    ok, lines = compare_grids(whole, parts)
+    assert ok, lines
