@@ -181,6 +181,7 @@ __device__ __forceinline__ int back_project_edge(const ScanDev& s, const double2
 }
 
 #define CLASSIFY_THREADS 256
+#define CLASSIFY_MAX_BEAMS 2048  // scans up to this size are copied to shared memory by every classifier CTA
 
 // K1: TsdGridComponent::isInRange (TsdGridComponent.cpp:43-124) for every partition of the range box.  Four lanes
 // per partition (one per edge point), eight partitions per warp; the beam interval [minIdx, maxIdx] is scanned by
@@ -195,6 +196,22 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
 #pragma unroll
   for(int si = 0; si < NS; si++)
     fill_tables(pp, pp.scans[si], coltab + (size_t)si * 3 * pp.cells_x, rowtab + (size_t)si * 3 * pp.cells_y, gtid);
+  // The beam loops below walk ranges / mask with dependent loads; from global memory about half of them missed L1
+  // (a CTA touches the scan only briefly), so every CTA first copies the scans into shared memory (9.7 KB each).
+  __shared__ double s_ranges[NS][CLASSIFY_MAX_BEAMS];
+  __shared__ uint8_t s_mask[NS][CLASSIFY_MAX_BEAMS];
+  const bool stagedScan = pp.scans[0].n <= CLASSIFY_MAX_BEAMS;
+  if(stagedScan)
+  {
+#pragma unroll
+    for(int si = 0; si < NS; si++)
+      for(int i = threadIdx.x; i < pp.scans[si].n; i += CLASSIFY_THREADS)
+      {
+        s_ranges[si][i] = pp.scans[si].ranges[i];
+        s_mask[si][i] = pp.scans[si].mask[i];
+      }
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int sub = lane & 3;
   const int gshift = lane & ~3;
@@ -228,6 +245,8 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
   for(int si = 0; si < NS; si++)
   {
     const ScanDev& s = pp.scans[si];
+    const double* ranges = stagedScan ? s_ranges[si] : s.ranges;
+    const uint8_t* mask = stagedScan ? s_mask[si] : s.mask;
     wItem[si] = 0.0;
     bool alive = exists;
     const double trx = s.P[2], try_ = s.P[5];
@@ -278,8 +297,8 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
     {
       for(int j = minIdx + sub; j <= maxIdx; j += 4)
       {
-        const double d = s.ranges[j];
-        const bool m = s.mask[j] != 0;
+        const double d = ranges[j];
+        const bool m = mask[j] != 0;
         vis = vis || ((d > closest) && m);
         if(isinf(d)) empty = empty && (distance < s.low_refl);
         else empty = empty && (d > farthest) && m;
@@ -296,8 +315,8 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
       bool v = false, e = true;
       for(int j = lo + lane; j <= hi; j += 32)
       {
-        const double d = s.ranges[j];
-        const bool m = s.mask[j] != 0;
+        const double d = ranges[j];
+        const bool m = mask[j] != 0;
         v = v || ((d > cl) && m);
         if(isinf(d)) e = e && (di < s.low_refl);
         else e = e && (d > fa) && m;
