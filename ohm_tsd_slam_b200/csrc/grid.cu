@@ -102,6 +102,7 @@ struct PushParams
   double inv_max_trunc;  // 1.0 / maxTruncation (TsdGridPartition.cpp:94)
   int cells_x, cells_y, parts_x, parts_y, n_parts;
   int parts_shift;  // parts_x == 1 << parts_shift
+  int scan_cap;                     // padded size of a staged scan (ensure_scan_capacity)
   int cl_px0, cl_py0, cl_w, cl_h;  // partitions k_classify looks at: the scan's range box (scan_partition_box)
   int row_begin, row_end;
   int alloc_begin, alloc_end;
@@ -198,18 +199,20 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
     fill_tables(pp, pp.scans[si], coltab + (size_t)si * 3 * pp.cells_x, rowtab + (size_t)si * 3 * pp.cells_y, gtid);
   // The beam loops below walk ranges / mask with dependent loads; from global memory about half of them missed L1
   // (a CTA touches the scan only briefly), so every CTA first copies the scans into shared memory (9.7 KB each).
-  __shared__ double s_ranges[NS][CLASSIFY_MAX_BEAMS];
-  __shared__ uint8_t s_mask[NS][CLASSIFY_MAX_BEAMS];
-  const bool stagedScan = pp.scans[0].n <= CLASSIFY_MAX_BEAMS;
+  __shared__ __align__(16) double s_ranges[NS][CLASSIFY_MAX_BEAMS];
+  __shared__ __align__(16) uint8_t s_mask[NS][CLASSIFY_MAX_BEAMS];
+  const bool stagedScan = pp.scan_cap <= CLASSIFY_MAX_BEAMS;
   if(stagedScan)
   {
+    // 16-byte copies of the padded staging slots (scan_cap is a multiple of 64 and the slots are 64-byte aligned)
 #pragma unroll
     for(int si = 0; si < NS; si++)
-      for(int i = threadIdx.x; i < pp.scans[si].n; i += CLASSIFY_THREADS)
-      {
-        s_ranges[si][i] = pp.scans[si].ranges[i];
-        s_mask[si][i] = pp.scans[si].mask[i];
-      }
+    {
+      const double2* r2 = reinterpret_cast<const double2*>(pp.scans[si].ranges);
+      const uint4* m4 = reinterpret_cast<const uint4*>(pp.scans[si].mask);
+      for(int i = threadIdx.x; i < pp.scan_cap / 2; i += CLASSIFY_THREADS) reinterpret_cast<double2*>(s_ranges[si])[i] = r2[i];
+      for(int i = threadIdx.x; i < pp.scan_cap / 16; i += CLASSIFY_THREADS) reinterpret_cast<uint4*>(s_mask[si])[i] = m4[i];
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -1563,6 +1566,7 @@ int tsdg_push_staged(tsd_grid_t* g)
   PushParams pp = make_params(g);
   const int ns = g->staged_n;
   pp.nscan = ns;
+  pp.scan_cap = g->scan_cap;
   for(int i = 0; i < ns; i++) pp.scans[i] = g->staged[i];
   pp.dirs = g->d_dirs;
   g->stats_fresh = false;
