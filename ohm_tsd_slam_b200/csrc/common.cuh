@@ -233,10 +233,10 @@ struct tsd_grid
   uint32_t* d_active;  // bit 31: partition was initialised before this push
   uint32_t* d_kinds;   // per work-list entry: 2-bit outcome per scan of the launch
   double* d_active_w;  // 0.01 * partWeight per active item
-  uint32_t* d_emptied;
   uint32_t* d_newly;   // partitions allocated by the current push
   uint32_t* d_pending; // partitions initialised/modified outside push: borders refreshed by the next push
-  uint32_t* d_counters;   // [0] active [1] emptied [2] pending [3] refresh-all flag [4] newly initialised [5] slow cells
+  uint32_t* d_counters;   // [0] work-list entries [2] pending [3] refresh-all flag [4] newly allocated [5] slow-path cells
+                          // [6] emptied tiles [7] active tiles [8..15] snapshot of the last push [16..21] tickets, list sizes, update count
   unsigned long long* d_stats64;  // [0] cell updates
   double* d_coltab;    // 3 * cells_x : A (0.0 + Pi00*X), B (0.0 + Pi10*X), D ((X-tx)^2)
   double* d_rowtab;    // 3 * cells_y : A (Pi01*Y), B (Pi11*Y), D ((Y-ty)^2)

@@ -10,11 +10,13 @@
 // _initWeight) per partition.  The homogeneous cell-coordinate matrices the reference stores per partition
 // (24.6 KB each) are not stored: they are recomputed from the cell index.
 //
-// One push = 5 launches on the handle's stream:
-//   k_tables    per grid column / row: the pose-inverse products and squared offsets shared by all cells
-//   k_classify  warp per partition: TsdGridComponent::isInRange incl. the emptiness side effect (K1)
-//   k_update    persistent CTAs over the active + emptied lists: addTsd per cell / increaseEmptiness (K2, K3)
-//   k_borders   warp per touched partition: TsdGrid::propagateBorders restricted to what changed (K4)
+// One push (of one scan, or of two scans of the same sensor model: tsdg_push_batch) = 2 launches on the handle's stream:
+//   k_classify  4 lanes per partition of the scan's range box: TsdGridComponent::isInRange incl. the emptiness
+//               side effect, one work-list entry per touched partition (K1); also the per-column / per-row tables
+//   k_update    persistent CTAs over the work list: addTsd per cell / increaseEmptiness, border strips mirrored
+//               into the neighbours, and -- in the last CTA to finish -- the borders of newly allocated partitions
+//               and the per-push bookkeeping (K2, K3, most of K4)
+// plus k_borders after a fill / upload (full border refresh) and k_halo_sync / k_borders on sharded grids.
 #include <stdarg.h>
 #include <string.h>
 #include <cmath>
@@ -116,7 +118,6 @@ struct PushParams
   uint32_t* kinds;     // per list entry: 2 bits per scan (0 untouched, 1 increaseEmptiness, 2 active)
   double* active_w;    // per list entry and scan: partition weight (capacity n_owned per scan)
   int list_cap;        // n_owned
-  uint32_t* emptied;
   uint32_t* newly;    // partitions allocated by this push (count: counters[4], owned ones only in the list)
   uint32_t* pending;
   uint32_t* counters;
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
 }
 
 // K4: TsdGrid::propagateBorders (TsdGrid.cpp:372-427) restricted to the partitions whose cells changed
-// in this push (active, emptied) or since the last one (pending): a touched partition refreshes its own
+// in this push or since the last one (pending): a touched partition refreshes its own
 // right/top/corner border from its +x/+y/+xy neighbours, and the border of its -x/-y/-xy neighbours that
 // mirrors its first column / row / cell.  Untouched pairs keep the values of the previous push, which is
 // what the reference's full pass would rewrite them with.
@@ -1156,7 +1157,6 @@ static PushParams make_params(const tsd_grid* g)
   pp.active_w = g->d_active_w;
   pp.kinds = g->d_kinds;
   pp.list_cap = g->n_owned;
-  pp.emptied = g->d_emptied;
   pp.newly = g->d_newly;
   pp.pending = g->d_pending;
   pp.counters = g->d_counters;
@@ -1417,7 +1417,6 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMalloc(&g->d_initw, sizeof(double) * g->n_parts));
   TSD_CUDA(cudaMalloc(&g->d_active, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_active_w, sizeof(double) * g->n_owned * PUSH_MAX_SCANS));
-  TSD_CUDA(cudaMalloc(&g->d_emptied, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_newly, sizeof(uint32_t) * g->n_owned));
   TSD_CUDA(cudaMalloc(&g->d_signal, sizeof(uint32_t) * 8));
   TSD_CUDA(cudaMemset(g->d_signal, 0, sizeof(uint32_t) * 8));
@@ -1449,7 +1448,7 @@ int tsdg_destroy(tsd_grid_t* g)
   cudaSetDevice(g->device);
   if(g->stream) cudaStreamSynchronize(g->stream);
   cudaFree(g->d_tsd); cudaFree(g->d_weight); cudaFree(g->d_flags); cudaFree(g->d_initw); cudaFree(g->d_active);
-  cudaFree(g->d_active_w); cudaFree(g->d_emptied); cudaFree(g->d_newly); cudaFree(g->d_signal);
+  cudaFree(g->d_active_w); cudaFree(g->d_newly); cudaFree(g->d_signal);
   for(int b = 0; b < 2; b++)
     if(g->peer[b].connected && g->peer[b].ipc)
     {
@@ -1605,7 +1604,7 @@ int tsdg_push_staged(tsd_grid_t* g)
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[1], g->stream));
   const size_t smem = 0;
-  static const int ctasPerSm = []{ const char* e = getenv("TSD_UPDATE_CTAS"); const int v = e ? atoi(e) : UPDATE_CTAS_PER_SM; return (v == 3 || v == 4) ? v : UPDATE_CTAS_PER_SM; }();
+  const int ctasPerSm = UPDATE_CTAS_PER_SM;  // 3 x 256 threads x 80 registers; 4 (64 registers, spills) measured slower
   int ctas = g->sm_count * ctasPerSm;
   if(ctas > g->n_owned) ctas = g->n_owned;
   // nothing asked for a full border refresh: K4's remainder runs in k_update's last CTA.  (Sharded grids too: the
@@ -1614,13 +1613,11 @@ int tsdg_push_staged(tsd_grid_t* g)
   if(g->band) g->band_push_open = true;
   if(ns == 2)
   {
-    if(ctasPerSm == 3) k_update<3, 2><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
-    else k_update<4, 2><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+    k_update<UPDATE_CTAS_PER_SM, 2><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   }
   else
   {
-    if(ctasPerSm == 3) k_update<3, 1><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
-    else k_update<4, 1><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+    k_update<UPDATE_CTAS_PER_SM, 1><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   }
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[2], g->stream));
