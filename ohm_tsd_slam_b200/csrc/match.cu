@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
 struct PdfParams
 {
   int n_valid;
+  int sorted;  // model_angles strictly increasing (the usual case: model points come in beam order): binary search
   const double* model_angles;
   const double* model_dists;
   double p[12];
@@ -251,12 +252,44 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_pdf(HypCommon hc, Pd
       transform_control(T, s_ctrl[s], s_ctrl[hc.n_control + s], s_ctrl[2 * hc.n_control + s], &x, &y);
       const double angle = atan2(y, x);
       const double distance = sqrt(x * x + y * y);
+      // arg-min of |angle - modelAngle[k]|, first index on ties (PDFMatching.cpp:321-333 is a linear scan)
       double minAngleDiff = 2 * pi;
       int idxMin = 0;
-      for(int k = 0; k < pp.n_valid; k++)
+      if(pp.sorted)
       {
-        const double diff = fabs(angle - s_ang[k]);
-        if(diff < minAngleDiff) { minAngleDiff = diff; idxMin = k; }
+        // Sorted angles: the rounded differences are weakly V-shaped in k, so the scan's answer is the leftmost
+        // local minimum next to the insertion point of `angle`.
+        const int nv = pp.n_valid;
+        int lo = 0, hi = nv;
+        while(lo < hi)
+        {
+          const int mid = (lo + hi) >> 1;
+          if(s_ang[mid] < angle) lo = mid + 1;
+          else hi = mid;
+        }
+        int c = (lo < nv) ? lo : nv - 1;
+        double dc = fabs(angle - s_ang[c]);
+        while(c > 0)
+        {
+          const double d = fabs(angle - s_ang[c - 1]);
+          if(d <= dc) { c--; dc = d; }
+          else break;
+        }
+        while(c + 1 < nv)
+        {
+          const double d = fabs(angle - s_ang[c + 1]);
+          if(d < dc) { c++; dc = d; }
+          else break;
+        }
+        if(dc < minAngleDiff) { minAngleDiff = dc; idxMin = c; }
+      }
+      else
+      {
+        for(int k = 0; k < pp.n_valid; k++)
+        {
+          const double diff = fabs(angle - s_ang[k]);
+          if(diff < minAngleDiff) { minAngleDiff = diff; idxMin = k; }
+        }
       }
       if(minAngleDiff < angleThresh) fov++;
       prob *= probability_of_two_single_scans(pp.p, s_dst[idxMin], distance);
@@ -583,6 +616,9 @@ int match_score_pdf(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
   hc.control = a.put(control, 3 * (size_t)n_control + (n_control == 0 ? 1 : 0));
   PdfParams pp;
   pp.n_valid = n_valid;
+  pp.sorted = 1;
+  for(int k = 1; k < n_valid; k++)
+    if(!(model_angles[k - 1] < model_angles[k])) { pp.sorted = 0; break; }
   pp.model_angles = a.put(model_angles, n_valid);
   pp.model_dists = a.put(model_dists, n_valid);
   for(int i = 0; i < 12; i++) pp.p[i] = params[i];
