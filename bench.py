@@ -464,8 +464,15 @@ def run_reference(args):
     warmup = max(0, min(args.warmup, 20))
     b = cpu_baseline(args.workload, steps=steps, warmup=warmup, threads=None, budget_s=150.0)
     steps = b["steps"]  # (fewer than asked only if 150 s of pushes were not enough)
-    from ohm_tsd_slam_b200.workload import DoubleLaserWorkload
-    wl = DoubleLaserWorkload(args.workload, invert=lambda T: np.eye(3), n_map=0, n_steps=1)
+    from ohm_tsd_slam_b200.workload import DoubleLaserWorkload, MultiRobotWorkload
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # the CUDA arm's workload at N GPUs is N robots of this kind on one sharded grid; the reference has one grid in
+        # host memory and one process: its push rate per robot is what it is for one robot (sampled: robot 0)
+        wl = MultiRobotWorkload(world, args.workload, n_map=0, n_steps=1, invert=lambda T: np.eye(3))
+        b["sample"] += f"; robot 0 of the {world}-robot workload on its own {1 << wl.cfg.layout_grid}^2 grid"
+    else:
+        wl = DoubleLaserWorkload(args.workload, invert=lambda T: np.eye(3), n_map=0, n_steps=1)
     line = {
         "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps,
         "warmup": warmup, "ms_per_step": b["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
