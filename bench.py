@@ -126,11 +126,14 @@ def run_cuda(args):
     # A step = one scan cycle: the two lasers of every robot.  The two scans of a robot form one batch
     # (tsdg_stage_batch / tsdg_push_batch: the result of two TsdGrid::push calls, one classification + one update
     # launch for both; --no-batch pushes them one by one).
+    def make_batches(sc):
+        groups = [[s1] for s1 in sc] if args.no_batch else [list(sc[k:k + 2]) for k in range(0, len(sc), 2)]
+        return [capi.ScanBatch(gr) for gr in groups]  # the tsd_scan_t arrays are laid out once
+
+    step_batches = [make_batches(sc) for sc in wl.step_scans]
+
     def batches(i):
-        sc = wl.step_scans[i % n_steps]
-        if args.no_batch:
-            return [[s1] for s1 in sc]
-        return [list(sc[k:k + 2]) for k in range(0, len(sc), 2)]
+        return step_batches[i % n_steps]
 
     def resident_step(i, acc, samples=None):
         for b in batches(i):

@@ -147,6 +147,22 @@ def invert3x3(m) -> np.ndarray:
     return out
 
 
+class ScanBatch:
+    """Scans laid out as the contiguous tsd_scan_t array tsdg_push_batch takes (built once, reused every cycle)."""
+
+    def __init__(self, scans):
+        self.scans = list(scans)  # keeps the numpy buffers alive
+        self.array = (ScanStruct * len(self.scans))()
+        for i, sc in enumerate(self.scans):
+            self.array[i] = sc.struct
+
+    def __len__(self):
+        return len(self.scans)
+
+    def __iter__(self):
+        return iter(self.scans)
+
+
 class Grid:
     """obvious::TsdGrid on the device."""
 
@@ -215,23 +231,23 @@ class Grid:
 
     @staticmethod
     def _scan_array(scans):
+        if isinstance(scans, ScanBatch):
+            return scans.array
         arr = (ScanStruct * len(scans))()
         for i, sc in enumerate(scans):
             arr[i] = sc.struct
         return arr
 
     def push_batch(self, scans):
-        """The scans in order, as len(scans) pushes would; pairs of scans share their launches (tsdg_push_batch)."""
-        arr = self._scan_array(scans)
-        check(lib().tsdg_push_batch(self.h, arr, len(scans)))
+        """The scans in order, as len(scans) pushes would; pairs of scans share their launches (tsdg_push_batch).
+        `scans`: a list of Scan or a prepared ScanBatch."""
+        check(lib().tsdg_push_batch(self.h, self._scan_array(scans), len(scans)))
 
     def push_batch_async(self, scans):
-        arr = self._scan_array(scans)
-        check(lib().tsdg_push_batch_async(self.h, arr, len(scans)))
+        check(lib().tsdg_push_batch_async(self.h, self._scan_array(scans), len(scans)))
 
     def stage_batch(self, scans):
-        arr = self._scan_array(scans)
-        check(lib().tsdg_stage_batch(self.h, arr, len(scans)))
+        check(lib().tsdg_stage_batch(self.h, self._scan_array(scans), len(scans)))
 
     def stage_scan(self, scan: Scan):
         check(lib().tsdg_stage_scan(self.h, scan.byref()))
