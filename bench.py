@@ -127,7 +127,18 @@ def run_cuda(args):
     # (tsdg_stage_batch / tsdg_push_batch: the result of two TsdGrid::push calls, one classification + one update
     # launch for both; --no-batch pushes them one by one).
     def make_batches(sc):
-        groups = [[s1] for s1 in sc] if args.no_batch else [list(sc[k:k + 2]) for k in range(0, len(sc), 2)]
+        if band:  # only what reaches this rank's band; up to four scans (two robots) per launch pair
+            b, e = band.rows[band.rank]
+            from ohm_tsd_slam_b200.sharded import band_reached
+            sc = [s1 for s1 in sc if band_reached(band._box(s1), b, e)]
+        if args.no_batch:
+            groups = [[s1] for s1 in sc]
+        else:
+            groups, k = [], 0
+            while k < len(sc):
+                take = 4 if len(sc) - k >= 4 else (2 if len(sc) - k >= 2 else 1)
+                groups.append(list(sc[k:k + take]))
+                k += take
         return [capi.ScanBatch(gr) for gr in groups]  # the tsd_scan_t arrays are laid out once
 
     step_batches = [make_batches(sc) for sc in wl.step_scans]
@@ -135,13 +146,16 @@ def run_cuda(args):
     def batches(i):
         return step_batches[i % n_steps]
 
+    def note_step(i):
+        # every rank looks at every scan of the step: which band boundaries it dirties (replicated book-keeping)
+        for s1 in wl.step_scans[i % n_steps]:
+            band.note_scan(band._box(s1))
+        band.flags_dirty = True
+
     def resident_step(i, acc, samples=None):
+        if band:
+            note_step(i)
         for b in batches(i):
-            if band:
-                mine = [band.note_scan(band._box(s1)) for s1 in b]
-                band.flags_dirty = True
-                if not any(mine):
-                    continue
             grid.stage_batch(b)
             e0, e1 = ev_pair()
             e0.record(stream)
@@ -175,12 +189,9 @@ def run_cuda(args):
 
     # exact update count of one step on this rank, and of its heaviest push (the roofline launch)
     def host_step(i, count=None):
+        if band:
+            note_step(i)
         for b in batches(i):
-            if band:
-                mine = [band.note_scan(band._box(s1)) for s1 in b]
-                band.flags_dirty = True
-                if not any(mine):
-                    continue
             grid.push_batch(b)  # blocking: H2D of the scans, kernels, D2H of the statistics, synchronise
             if count is not None:
                 count.append(grid.last_push_stats()["cell_updates"])

@@ -157,10 +157,10 @@ int tsdg_stage_scan(tsd_grid_t* grid, const tsd_scan_t* scan);
 int tsdg_push_staged(tsd_grid_t* grid);
 /* n scans in the order given, with the result of n TsdGrid::push calls (ThreadMapping::eventLoop drains its queue
  * of sensors one push after the other, ThreadMapping.cpp:43-62).  Consecutive scans of the same sensor model are
- * taken two at a time: one classification and one update launch for both, partitions seen by both scans (the two
- * lasers of a robot) are read and written once.  tsdg_push_batch blocks like tsdg_push; the statistics reported
- * afterwards are those of the last launch (both scans of a pair together).  tsdg_stage_batch (n <= 2, same sensor
- * model) + tsdg_push_staged is the device-resident variant. */
+ * taken four or two at a time: one classification and one update launch for all of them, partitions seen by several
+ * scans (the two lasers of a robot) are read and written once.  tsdg_push_batch blocks like tsdg_push; the statistics
+ * reported afterwards are those of the last launch (its scans together).  tsdg_stage_batch (n = 1, 2 or 4, same
+ * sensor model) + tsdg_push_staged is the device-resident variant. */
 int tsdg_push_batch(tsd_grid_t* grid, const tsd_scan_t* scans, int32_t n);
 int tsdg_push_batch_async(tsd_grid_t* grid, const tsd_scan_t* scans, int32_t n);
 int tsdg_stage_batch(tsd_grid_t* grid, const tsd_scan_t* scans, int32_t n);

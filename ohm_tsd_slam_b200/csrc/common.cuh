@@ -274,7 +274,7 @@ struct tsd_grid
   unsigned long long* h_stats64;
   tsd_push_stats_t last_stats;
   int sm_count;
-  tsd::ScanDev staged[2];  // scans staged by tsdg_stage_scan / tsdg_stage_batch (device pointers + scalars)
+  tsd::ScanDev staged[4];  // scans staged by tsdg_stage_scan / tsdg_stage_batch (device pointers + scalars)
   int staged_n;
   // halo synchronisation over peer memory (bands only): [0] = the band below, [1] = the band above
   uint32_t* d_signal;        // [0]/[1] data-ready from below/above, [2]/[3] ack from below/above, [4] CTA ticket

@@ -93,7 +93,7 @@ using namespace tsd;
 // kernels
 // ------------------------------------------------------------------------------------------------
 
-#define PUSH_MAX_SCANS 2  // scans one push launch integrates (tsdg_push_batch)
+#define PUSH_MAX_SCANS 4  // scans one push launch integrates (tsdg_push_batch); launches are built for 1, 2 and 4
 
 struct PushParams
 {
@@ -183,7 +183,7 @@ __device__ __forceinline__ int back_project_edge(const ScanDev& s, const double2
 }
 
 #define CLASSIFY_THREADS 256
-#define CLASSIFY_MAX_BEAMS 2048  // scans up to this size are copied to shared memory by every classifier CTA
+#define CLASSIFY_MAX_BEAMS 1152  // scans up to this (padded) size are copied to shared memory by every classifier CTA
 
 // K1: TsdGridComponent::isInRange (TsdGridComponent.cpp:43-124) for every partition of the range box.  Four lanes
 // per partition (one per edge point), eight partitions per warp; the beam interval [minIdx, maxIdx] is scanned by
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
           tv[j] = s_cells[stage][0][j * UPDATE_THREADS + t];
           wv[j] = s_cells[stage][1][j * UPDATE_THREADS + t];
         }
-        if(myStrip && (kinds & 0x5u))  // some scan runs increaseEmptiness over the border cells too
+        if(myStrip && (kinds & 0x55u))  // some scan runs increaseEmptiness over the border cells too
         {
           bt = T[TSD_BORDER_OFF + t];
           bw = W[TSD_BORDER_OFF + t];
@@ -1187,8 +1187,8 @@ int grid_ensure_scratch(tsd_grid* g, size_t bytes)
 }
 
 // One device block and one pinned mirror hold everything a scan brings with it, so that staging is a single
-// H2D copy:  [ ranges: cap doubles | mask: cap bytes | ranges of a second scan | its mask | rays: 2*cap doubles ]
-// (a push copies the first two or four parts, a ray cast everything).  The ray-caster's results come
+// H2D copy:  [ ranges: cap doubles | mask: cap bytes | rays: 2*cap doubles | (ranges | mask) of scans 1..3 of a batch ]
+// (a push of one scan or a ray cast copies a prefix; a batch copies through its last scan).  The ray-caster's results come
 // back in one D2H copy of  [ out: 4*cap doubles | keys: cap u64 | steps: 2 u64 ].
 static int ensure_scan_capacity(tsd_grid* g, int n)
 {
@@ -1197,7 +1197,7 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
   cudaFree(g->d_in); cudaFree(g->d_dirs); cudaFree(g->d_rc);
   cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc);
   const int cap = ((n + 63) / 64) * 64 + 64;
-  g->in_bytes = 2 * (sizeof(double) * cap + cap) + sizeof(double) * 2 * cap;
+  g->in_bytes = PUSH_MAX_SCANS * (sizeof(double) * cap + cap) + sizeof(double) * 2 * cap;
   g->rc_bytes = sizeof(double) * 4 * cap + sizeof(unsigned long long) * cap + sizeof(unsigned long long) * 2;
   TSD_CUDA(cudaMalloc(&g->d_in, g->in_bytes));
   TSD_CUDA(cudaMalloc(&g->d_rc, g->rc_bytes));
@@ -1208,10 +1208,10 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
   memset(g->h_rc, 0, g->rc_bytes);
   g->d_ranges = reinterpret_cast<double*>(g->d_in);
   g->d_mask = g->d_in + sizeof(double) * cap;
-  g->d_rays = reinterpret_cast<double*>(g->d_in + 2 * (sizeof(double) * cap + cap));
+  g->d_rays = reinterpret_cast<double*>(g->d_in + sizeof(double) * cap + cap);
   g->h_ranges = reinterpret_cast<double*>(g->h_in);
   g->h_mask = g->h_in + sizeof(double) * cap;
-  g->h_rays = reinterpret_cast<double*>(g->h_in + 2 * (sizeof(double) * cap + cap));
+  g->h_rays = reinterpret_cast<double*>(g->h_in + sizeof(double) * cap + cap);
   g->d_rc_out = reinterpret_cast<double*>(g->d_rc);
   g->d_rc_keys = reinterpret_cast<unsigned long long*>(g->d_rc + sizeof(double) * 4 * cap);
   g->d_rc_steps = g->d_rc_keys + cap;
@@ -1236,29 +1236,35 @@ int grid_stage_scans(tsd_grid* g, const tsd_scan_t* scans, int n, ScanDev* sd, c
   for(int i = 0; i < n; i++)
     if(scans[i].n < 1 || !scans[i].ranges || !scans[i].mask) { set_error("invalid scan"); return TSD_E_INVALID; }
   const tsd_scan_t* scan = &scans[0];
-  if(n == 2 && (scans[1].n != scan->n || scans[1].phi_min != scan->phi_min || scans[1].angular_res != scan->angular_res))
-  {
-    set_error("the scans of a batch must come from the same sensor model");
-    return TSD_E_INVALID;
-  }
+  for(int i = 1; i < n; i++)
+    if(scans[i].n != scan->n || scans[i].phi_min != scan->phi_min || scans[i].angular_res != scan->angular_res)
+    {
+      set_error("the scans of a batch must come from the same sensor model");
+      return TSD_E_INVALID;
+    }
+  if(n == 3) { set_error("a launch takes 1, 2 or 4 scans"); return TSD_E_INVALID; }
   int rc = ensure_scan_capacity(g, scan->n);
   if(rc) return rc;
   // the previous call's async copy out of the pinned staging block must have drained
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   const size_t slotBytes = sizeof(double) * g->scan_cap + g->scan_cap;
+  const size_t raysBytes = sizeof(double) * 2 * g->scan_cap;
+  size_t bytes = 0;
   for(int i = 0; i < n; i++)
   {
+    const size_t off = (i == 0) ? 0 : slotBytes + raysBytes + (size_t)(i - 1) * slotBytes;
     fill_scan_dev(&scans[i], &sd[i]);
-    memcpy(g->h_in + i * slotBytes, scans[i].ranges, sizeof(double) * scans[i].n);
-    memcpy(g->h_in + i * slotBytes + sizeof(double) * g->scan_cap, scans[i].mask, scans[i].n);
-    sd[i].ranges = reinterpret_cast<double*>(g->d_in + i * slotBytes);
-    sd[i].mask = g->d_in + i * slotBytes + sizeof(double) * g->scan_cap;
+    memcpy(g->h_in + off, scans[i].ranges, sizeof(double) * scans[i].n);
+    memcpy(g->h_in + off + sizeof(double) * g->scan_cap, scans[i].mask, scans[i].n);
+    sd[i].ranges = reinterpret_cast<double*>(g->d_in + off);
+    sd[i].mask = g->d_in + off + sizeof(double) * g->scan_cap;
+    bytes = off + sizeof(double) * g->scan_cap + scans[i].n;
   }
-  size_t bytes = (n - 1) * slotBytes + sizeof(double) * g->scan_cap + scan->n;
   if(rays_world)
   {
     memcpy(g->h_rays, rays_world, sizeof(double) * 2 * scan->n);
-    bytes = 2 * slotBytes + sizeof(double) * 2 * scan->n;
+    const size_t withRays = slotBytes + sizeof(double) * 2 * scan->n;
+    bytes = bytes > withRays ? bytes : withRays;
   }
   TSD_CUDA(cudaMemcpyAsync(g->d_in, g->h_in, bytes, cudaMemcpyHostToDevice, g->stream));
   if(g->dirs_n != scan->n || g->dirs_phi_min != scan->phi_min || g->dirs_res != scan->angular_res)
@@ -1599,7 +1605,8 @@ int tsdg_push_staged(tsd_grid_t* g)
   const int nthreads = (4 * pp.cl_w * pp.cl_h > nmax) ? 4 * pp.cl_w * pp.cl_h : nmax;
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[0], g->stream));
   const int cctas = (nthreads + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS;
-  if(ns == 2) k_classify<2><<<cctas, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
+  if(ns == 4) k_classify<4><<<cctas, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
+  else if(ns == 2) k_classify<2><<<cctas, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
   else k_classify<1><<<cctas, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[1], g->stream));
@@ -1611,7 +1618,11 @@ int tsdg_push_staged(tsd_grid_t* g)
   // strips that depend on the halo row above the band are refreshed after the exchange, tsdg_band_push_finish.)
   pp.fused_tail = g->refresh_all_pending ? 0 : 1;
   if(g->band) g->band_push_open = true;
-  if(ns == 2)
+  if(ns == 4)
+  {
+    k_update<UPDATE_CTAS_PER_SM, 4><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+  }
+  else if(ns == 2)
   {
     k_update<UPDATE_CTAS_PER_SM, 2><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   }
@@ -1659,10 +1670,13 @@ int tsdg_push_batch_async(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
   int i = 0;
   while(i < n)
   {
+    auto same = [&](int a, int b)
+    {
+      return scans[a].n == scans[b].n && scans[a].phi_min == scans[b].phi_min && scans[a].angular_res == scans[b].angular_res;
+    };
     int take = 1;
-    if(i + 1 < n && scans[i + 1].n == scans[i].n && scans[i + 1].phi_min == scans[i].phi_min &&
-       scans[i + 1].angular_res == scans[i].angular_res)
-      take = 2;
+    if(i + 3 < n && same(i, i + 1) && same(i, i + 2) && same(i, i + 3)) take = 4;
+    else if(i + 1 < n && same(i, i + 1)) take = 2;
     int rc = tsdg_stage_batch(g, scans + i, take);
     if(rc) return rc;
     rc = tsdg_push_staged(g);
