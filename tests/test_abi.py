@@ -59,3 +59,25 @@ def test_argument_validation():
     assert capi.lib().tsdg_create(0.025, 5, 20, 0, C.byref(h)) in (-1, -2)
     assert capi.lib().tsdg_push(None, None) == -1
     assert capi.lib().tsdg_destroy(None) == 0
+
+
+def test_argument_validation_of_the_wider_surface(tmp_path):
+    """NULL handles / buffers are refused before anything touches CUDA (runs without a GPU)."""
+    L = capi.lib()
+    n = C.c_uint32()
+    assert L.tsdg_push_batch(None, None, 2) == -1
+    assert L.tsdg_push_batch_async(None, None, 0) == -1
+    assert L.tsdg_stage_batch(None, None, 1) == -1
+    assert L.tsdg_axis_aligned_map(None, None, 0, None, C.byref(n), None) == -1
+    assert L.tsdg_color_image(None, None, 4, 4) == -1
+    assert L.tsdg_store(None, b"x") == -1
+    h = C.c_void_p()
+    assert L.tsdg_load(None, 0, C.byref(h)) == -1
+    assert L.tsdg_load(str(tmp_path / "missing.txt").encode(), 0, C.byref(h)) == -1 and not h.value
+    assert b"cannot open" in L.tsd_last_error()
+    assert L.tsdg_band_halo_sync(None, 0, -1, 0, -1) == -1
+    assert L.tsdg_band_push_finish(None) == -1
+    assert L.tsdg_band_export(None, None) == -1
+    assert L.tsdg_band_connect(None, 0, None) == -1
+    box = (C.c_int32 * 4)()
+    assert L.tsdg_scan_box(None, None, box) == -1
