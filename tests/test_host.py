@@ -46,3 +46,16 @@ def test_host_sensor_scene_and_rays():
     assert n == int(mask.sum()) and np.allclose(np.hypot(*coords[mask > 0].T), hs.data[mask > 0], rtol=1e-12)
     sc = hs.scan()
     assert np.allclose(sc.pose_inv @ sc.pose, np.eye(3), atol=1e-12)
+
+
+def test_build_stamp_follows_the_sources_not_their_mtimes(monkeypatch):
+    """The library is rebuilt when the content hash of its sources differs from the stamp written at build time
+    (a snapshot copied to another box does not keep the order of modification times)."""
+    from ohm_tsd_slam_b200 import _build, capi
+    capi.lib()  # built and stamped
+    assert not _build.needs_build()
+    import os
+    os.utime(_build.sources()[0])  # a newer mtime alone changes nothing
+    assert not _build.needs_build()
+    monkeypatch.setattr(_build, "source_hash", lambda: "something else")
+    assert _build.needs_build()
