@@ -172,6 +172,10 @@ int tsdg_stream_order(tsd_grid_t* grid, void* other_stream, int direction);
 /* Measurement aid: with timing enabled every push records CUDA events around its kernels on the handle's
  * stream; ms = {tables + classify, update (K2+K3), borders (K4), whole push} of the last completed push. */
 int tsdg_set_timing(tsd_grid_t* grid, int enable);
+/* Measurement aid (bench.py's K2-only / K3-only roofline rows): the update kernel of the following pushes skips the
+ * addTsd work of active partitions (mask bit 0) and / or the increaseEmptiness work of emptied partitions (bit 1).
+ * The map is then NOT what the reference would compute; 0 restores the normal behaviour. */
+int tsdg_set_update_filter(tsd_grid_t* grid, unsigned mask);
 int tsdg_last_push_kernel_ms(tsd_grid_t* grid, float ms[4]);
 
 /* Counters of the most recent completed push. */

@@ -28,7 +28,7 @@ EXPORTS = [
     "tsdg_create", "tsdg_create_band", "tsdg_band_push_finish", "tsdg_band_export", "tsdg_band_connect", "tsdg_band_connect_local", "tsdg_band_halo_sync",
     "tsdg_band_flags", "tsdg_scan_box", "tsdg_band_row", "tsdg_destroy", "tsdg_set_max_truncation", "tsdg_get_geometry",
     "tsdg_free_footprint", "tsdg_push", "tsdg_push_async", "tsdg_sync", "tsdg_stage_scan", "tsdg_push_staged", "tsdg_push_batch", "tsdg_push_batch_async", "tsdg_stage_batch",
-    "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
+    "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_set_update_filter", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
     "tsdg_axis_aligned_map", "tsdg_color_image", "tsdg_store", "tsdg_load",
@@ -87,6 +87,7 @@ def lib():
     L.tsdg_stream.argtypes = [C.c_void_p]
     L.tsdg_stream_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.tsdg_set_timing.argtypes = [C.c_void_p, C.c_int]
+    L.tsdg_set_update_filter.argtypes = [C.c_void_p, C.c_uint]
     L.tsdg_last_push_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tsdg_last_push_stats.argtypes = [C.c_void_p, C.POINTER(PushStats)]
     L.tsdg_interpolate_bilinear.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
@@ -272,6 +273,10 @@ class Grid:
 
     def set_timing(self, enable: bool = True):
         check(lib().tsdg_set_timing(self.h, 1 if enable else 0))
+
+    def set_update_filter(self, mask: int):
+        """Measurement aid: bit 0 = the update kernel skips K2 (addTsd) work, bit 1 = K3 (increaseEmptiness) work."""
+        check(lib().tsdg_set_update_filter(self.h, mask))
 
     def last_push_kernel_ms(self):
         ms = (C.c_float * 4)()

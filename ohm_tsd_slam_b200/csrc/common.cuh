@@ -71,6 +71,11 @@ struct ScanDev
   double Pi[9];    // pose inverse
   double max_range, min_range, low_refl;
   BeamModel bm;
+  // single-precision front end of k_update (grid.cu "fast path"): sensor position as the pose INVERSE implies it
+  // (Pi * [txp typ 1]' = [0 0 1]'), and the scaled-angle parameters s = fma(phi, rinv_f, off_f), a cell's beam is
+  // round(s) for certain iff |s - round(s)| < half_m (half_m < 0: never, every cell takes the exact route)
+  double txp, typ;
+  float rinv_f, off_f, half_m;
 };
 
 #ifdef __CUDACC__
@@ -240,6 +245,12 @@ struct tsd_grid
   unsigned long long* d_stats64;  // [0] cell updates
   double* d_coltab;    // 3 * cells_x : A (0.0 + Pi00*X), B (0.0 + Pi10*X), D ((X-tx)^2)
   double* d_rowtab;    // 3 * cells_y : A (Pi01*Y), B (Pi11*Y), D ((Y-ty)^2)
+  unsigned long long* d_prof;  // UPDATE_PROFILE builds only
+  tsd::ScanDev* d_scans;  // the scans of the current push launch, for out-of-line device code
+  float4* d_col4;      // per scan cells_x x {Pi00*(X-tx'), Pi10*(X-tx')} as float2, then cells_x x (X-tx)^2 as float (k_update fast path)
+  float4* d_row4;      // cells_y per scan: {Pi01*(Y-ty'), Pi11*(Y-ty'), (Y-ty)^2, 0}
+  float2* d_gate;      // scan_cap per scan: per beam the squared distances below / above which a cell is free space for
+                       // certain / not rewritten for certain (grid.cu fill_gate)
   // sensor model tables
   double2* d_dirs;
   int dirs_n;
@@ -288,6 +299,7 @@ struct tsd_grid
   } peer[2];
   uint32_t halo_seq[2];      // synchronisations done per boundary (both sides count alike)
   bool has_staged;
+  unsigned update_filter;  // measurement aid: k_update skips K2 (bit 0) / K3 (bit 1) work (tsdg_set_update_filter)
   bool timing;          // record CUDA events around the push kernels (bench.py's live roofline)
   cudaEvent_t ev[4];
   cudaEvent_t ev_order;

@@ -64,6 +64,13 @@ int fill_scan_dev(const tsd_scan_t* s, ScanDev* o)
                 s->phi_upper > s->phi_lower && s->n >= 1)
                    ? 1
                    : 0;
+  FastModel fm;
+  tsd_fast_model(o->Pi, s->phi_min, s->angular_res, s->phi_lower, s->phi_upper, s->n, &fm);  // beam_index.cuh
+  o->txp = fm.txp;
+  o->typ = fm.typ;
+  o->rinv_f = fm.rinv_f;
+  o->off_f = fm.off_f;
+  o->half_m = fm.half_m;
   return TSD_OK;
 }
 
@@ -125,12 +132,21 @@ struct PushParams
   const double* coltab;  // per scan: 3 * cells_x
   const double* rowtab;  // per scan: 3 * cells_y
   const double2* dirs;
+  float2* colxy;         // per scan: cells_x   (single-precision tables of the fast path, fill_tables)
+  float* cold;           // per scan: cells_x
+  float2* rowxy;         // per scan: cells_y
+  float* rowd;           // per scan: cells_y
+  float2* gate;          // per scan: scan_cap  (fill_gate)
+  ScanDev* scans_dev;    // copy of scans[] in global memory (written by k_classify) for out-of-line code
+  unsigned update_filter;  // measurement aid (tsdg_set_update_filter): bit 0 = skip K2 work, bit 1 = skip K3 work
+  unsigned long long* prof;  // UPDATE_PROFILE builds: 8 cycle counters per CTA of k_update
 };
 
 // Per grid column X = ((double)ix + 0.5) * cellSize (TsdGridPartition.cpp:127): the two products of
 // SensorPolar2D.cpp:125 that depend on X only, with gslcblas' accumulation order (temp = 0; temp += a*b ...),
 // and the squared offset of TsdGrid.cpp:262.  Same per grid row.  Runs inside k_classify (first threads).
-__device__ __forceinline__ void fill_tables(const PushParams& pp, const ScanDev& sc, double* coltab, double* rowtab, int i0)
+__device__ __forceinline__ void fill_tables(const PushParams& pp, const ScanDev& sc, double* coltab, double* rowtab, float2* colxy,
+                                            float* cold, float2* rowxy, float* rowd, int i0)
 {
   const double* Pi = sc.Pi;
   if(i0 < pp.cl_w * TSD_TILE)
@@ -145,6 +161,9 @@ __device__ __forceinline__ void fill_tables(const PushParams& pp, const ScanDev&
     coltab[i] = a;
     coltab[pp.cells_x + i] = b;
     coltab[2 * pp.cells_x + i] = d * d;
+    const double dp = X - sc.txp;
+    colxy[i] = make_float2((float)(Pi[0] * dp), (float)(Pi[3] * dp));
+    cold[i] = (float)(d * d);
   }
   if(i0 < pp.cl_h * TSD_TILE)
   {
@@ -154,7 +173,19 @@ __device__ __forceinline__ void fill_tables(const PushParams& pp, const ScanDev&
     rowtab[i] = Pi[1] * Y;
     rowtab[pp.cells_y + i] = Pi[4] * Y;
     rowtab[2 * pp.cells_y + i] = d * d;
+    const double dp = Y - sc.typ;
+    rowxy[i] = make_float2((float)(Pi[1] * dp), (float)(Pi[4] * dp));
+    rowd[i] = (float)(d * d);
   }
+}
+
+// Per beam: the squared-distance gates of the single-precision front end (tsd_gate_entry, beam_index.cuh).
+__device__ __forceinline__ void fill_gate(const PushParams& pp, const ScanDev& sc, float2* gate, int i)
+{
+  if(i >= sc.n) return;
+  float lo2, hi2;
+  tsd_gate_entry(sc.ranges[i], sc.mask[i] != 0, pp.max_trunc, sc.low_refl, &lo2, &hi2);
+  gate[i] = make_float2(lo2, hi2);
 }
 
 // SensorPolar2D::backProject for one homogeneous point, complete (sign of zero included), for the 4 edge
@@ -195,9 +226,15 @@ template <int NS>
 __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, double* coltab, double* rowtab)
 {
   const int gtid = blockIdx.x * CLASSIFY_THREADS + threadIdx.x;
+  if(gtid < NS) pp.scans_dev[gtid] = pp.scans[gtid];
 #pragma unroll
   for(int si = 0; si < NS; si++)
-    fill_tables(pp, pp.scans[si], coltab + (size_t)si * 3 * pp.cells_x, rowtab + (size_t)si * 3 * pp.cells_y, gtid);
+  {
+    fill_tables(pp, pp.scans[si], coltab + (size_t)si * 3 * pp.cells_x, rowtab + (size_t)si * 3 * pp.cells_y,
+                pp.colxy + (size_t)si * pp.cells_x, pp.cold + (size_t)si * pp.cells_x, pp.rowxy + (size_t)si * pp.cells_y,
+                pp.rowd + (size_t)si * pp.cells_y, gtid);
+    fill_gate(pp, pp.scans[si], pp.gate + (size_t)si * pp.scan_cap, gtid);
+  }
   // The beam loops below walk ranges / mask with dependent loads; from global memory about half of them missed L1
   // (a CTA touches the scan only briefly), so every CTA first copies the scans into shared memory (9.7 KB each).
   __shared__ __align__(16) double s_ranges[NS][CLASSIFY_MAX_BEAMS];
@@ -389,11 +426,16 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
   if(nActive) atomicAdd(&pp.counters[7], nActive);
 }
 
-#define UPDATE_THREADS 256
-#define ITEM_CHUNK 32  // items whose metadata k_update fetches at a time
+#define UPDATE_CONSUMERS 256                        // threads that update cells: 8 warps, 4 cells each per partition
+#define UPDATE_THREADS (UPDATE_CONSUMERS + 32)      // + one producer warp (work list, metadata, bulk copies)
+#ifndef UPDATE_STAGES
+#define UPDATE_STAGES 3
+#endif
 #ifndef UPDATE_CTAS_PER_SM
 #define UPDATE_CTAS_PER_SM 3
 #endif
+#define TILE_BYTES (TSD_TILE_STRIDE * 8)            // one partition of one array: 8832 B = 69 x 128 B, borders included
+#define STAGE_BYTES (2 * TILE_BYTES)                // tsd + weight
 #define BEAM_UNDECIDED (-3)
 
 // Beam index of the slow path (the reference formula verbatim), kept out of line: ~0.1 % of the cells.
@@ -443,44 +485,93 @@ __device__ __forceinline__ int beam_index_fast(const BeamModel& bm, const double
   return confirmed ? k : (below ? -2 : (above ? -1 : BEAM_UNDECIDED));
 }
 
-// Two horizontally adjacent cells of TsdGrid.cpp:250-274 + TsdGridPartition::addTsd (TsdGridPartition.h:170-212),
-// written straight-line so that the two dependency chains interleave; only the division is skipped when neither
-// cell is rewritten.  Returns the number of cells rewritten (0..2).
-__device__ __forceinline__ unsigned update_pair(const PushParams& pp, const ScanDev& s, const double2 cA, const double2 cB,
-                                                const double2 cD, double rA, double rB, double rD, double wTile, double2& tv,
-                                                double2& wv)
+// ---- K2, single-precision front end: tsd_classify_cell / tsd_gate_entry / tsd_fast_model in beam_index.cuh -------------
+__device__ __forceinline__ int classify_cell(const ScanDev& s, const float2* __restrict__ gate, float xf, float yf, float d2f,
+                                             int& kOut)
 {
-  const double x0 = (cA.x + rA) + s.Pi[2] * 1.0;
-  const double y0 = (cB.x + rB) + s.Pi[5] * 1.0;
-  const double x1 = (cA.y + rA) + s.Pi[2] * 1.0;
-  const double y1 = (cB.y + rB) + s.Pi[5] * 1.0;
-  int i0, i1;
-  if(s.bm.fast_ok)
+  return tsd_classify_cell(s.rinv_f, s.off_f, s.half_m, s.n, gate, xf, yf, d2f, kOut);
+}
+
+// The reference's own expressions for one cell (classes 2 and 3).  Out of line (~0.3 % of the cells), and reading
+// the sensor model from the copy k_classify left in global memory: a reference to the kernel's parameter block would
+// make the compiler copy all of it to the stack of every thread.
+__device__ __noinline__ int beam_of_point_exact(const ScanDev* __restrict__ sg, const double2* __restrict__ dirs, uint32_t* counter,
+                                                double x, double y)
+{
+  const BeamModel bm = sg->bm;
+  int i = bm.fast_ok ? beam_index_fast(bm, dirs, x, y) : BEAM_UNDECIDED;
+  if(i == BEAM_UNDECIDED) i = beam_index_slow(counter, bm.phi_min, bm.res_inv, bm.phi_lower, bm.phi_upper, x, y);
+  return i;
+}
+
+__device__ __forceinline__ void exact_cell(const PushParams& pp, const ScanDev& s, int si, const double* ct, const double* rt, int ix,
+                                           int iy, double rD, int cls, int k, bool& ok, double& n)
+{
+  int idx = k;
+  if(cls == 3)
   {
-    i0 = beam_index_fast(s.bm, pp.dirs, x0, y0);
-    i1 = beam_index_fast(s.bm, pp.dirs, x1, y1);
+    const double x = (ct[ix] + rt[iy]) + s.Pi[2] * 1.0;  // SensorPolar2D.cpp:125 with gslcblas' accumulation order
+    const double y = (ct[pp.cells_x + ix] + rt[pp.cells_y + iy]) + s.Pi[5] * 1.0;
+    idx = beam_of_point_exact(pp.scans_dev + si, pp.dirs, pp.counters + 5, x, y);
   }
-  else i0 = i1 = BEAM_UNDECIDED;
-  if(i0 == BEAM_UNDECIDED) i0 = beam_index_slow(pp.counters + 5, s.bm.phi_min, s.bm.res_inv, s.bm.phi_lower, s.bm.phi_upper, x0, y0);
-  if(i1 == BEAM_UNDECIDED) i1 = beam_index_slow(pp.counters + 5, s.bm.phi_min, s.bm.res_inv, s.bm.phi_lower, s.bm.phi_upper, x1, y1);
-  const int last = s.n - 1;
-  const int j0 = min(max(i0, 0), last), j1 = min(max(i1, 0), last);
-  const unsigned m0 = __ldg(s.mask + j0), m1 = __ldg(s.mask + j1);
-  const double r0 = __ldg(s.ranges + j0), r1 = __ldg(s.ranges + j1);
-  const double dist0 = sqrt(cD.x + rD), dist1 = sqrt(cD.y + rD);
-  const bool inf0 = isinf(r0), inf1 = isinf(r1);
-  const double sd0 = inf0 ? pp.max_trunc : r0 - dist0;
-  const double sd1 = inf1 ? pp.max_trunc : r1 - dist1;
-  const bool ok0 = (i0 >= 0) && (m0 != 0) && (!inf0 || dist0 < s.low_refl) && (sd0 >= -pp.max_trunc);
-  const bool ok1 = (i1 >= 0) && (m1 != 0) && (!inf1 || dist1 < s.low_refl) && (sd1 >= -pp.max_trunc);
+  ok = false;
+  if(idx >= 0)
+  {
+    idx = min(idx, s.n - 1);
+    const unsigned m = __ldg(s.mask + idx);
+    const double r = __ldg(s.ranges + idx);
+    const double dist = sqrt(ct[2 * pp.cells_x + ix] + rD);  // TsdGrid.cpp:262
+    const bool inf = isinf(r);
+    const double sd = inf ? pp.max_trunc : r - dist;
+    ok = (m != 0) && (!inf || dist < s.low_refl) && (sd >= -pp.max_trunc);
+    n = fmin(sd * pp.inv_max_trunc, 1.0);  // == obvious::min(a, 1.0): the constant is never NaN
+  }
+}
+
+// Two horizontally adjacent cells of TsdGrid.cpp:250-274 + TsdGridPartition::addTsd (TsdGridPartition.h:170-212).
+// cxy / cd / rxy / rd: the single-precision table entries of the two columns and of the row; returns the number of
+// cells rewritten (0..2).
+__device__ __forceinline__ unsigned update_pair(const PushParams& pp, const ScanDev& s, int si, int cls0, int cls1, int k0, int k1,
+                                                int gx, int gy, double wTile, double2& tv, double2& wv)
+{
+  const double den0 = wv.x + wTile, den1 = wv.y + wTile;
+  // The common pair: each cell is either not rewritten (class 0) or free space seen again -- class 1 (tsd_new == 1.0)
+  // on a cell whose tsd is 1.0.  Then (1.0 * w + 1.0 * wTile) / (w + wTile) has exact products, numerator and
+  // denominator are the same rounded sum, and x / x == 1.0 for every finite non-zero x: tsd stays 1.0 without a
+  // division, weight = min(w + wTile, 32).  Decided with integer tests on the high words (den a positive normal
+  // number: then also min(den, 32) is a comparison of high words).
+  const int dh0 = __double2hiint(den0), dh1 = __double2hiint(den1);
+  const bool unit0 = (__double2hiint(tv.x) == 0x3ff00000) && (__double2loint(tv.x) == 0);
+  const bool unit1 = (__double2hiint(tv.y) == 0x3ff00000) && (__double2loint(tv.y) == 0);
+  const bool easy0 = (cls0 == 0) || (cls0 == 1 && unit0 && (unsigned)(dh0 - 0x00100000) < 0x7fe00000u);
+  const bool easy1 = (cls1 == 0) || (cls1 == 1 && unit1 && (unsigned)(dh1 - 0x00100000) < 0x7fe00000u);
+  if(easy0 && easy1)
+  {
+    if(cls0 == 1) wv.x = (dh0 >= 0x40400000) ? TSD_MAXWEIGHT : den0;
+    if(cls1 == 1) wv.y = (dh1 >= 0x40400000) ? TSD_MAXWEIGHT : den1;
+    return (unsigned)(cls0 + cls1);
+  }
+  bool ok0 = (cls0 == 1), ok1 = (cls1 == 1);
+  double n0 = 1.0, n1 = 1.0;
+  if((cls0 | cls1) & 2)
+  {
+    const double* ct = pp.coltab + (size_t)si * 3 * pp.cells_x;
+    const double* rt = pp.rowtab + (size_t)si * 3 * pp.cells_y;
+    const double rD = rt[2 * pp.cells_y + gy];
+    if(cls0 & 2) exact_cell(pp, s, si, ct, rt, gx, gy, rD, cls0, k0, ok0, n0);
+    if(cls1 & 2) exact_cell(pp, s, si, ct, rt, gx + 1, gy, rD, cls1, k1, ok1, n1);
+  }
   if(ok0 || ok1)
   {
-    const double n0 = fmin(sd0 * pp.inv_max_trunc, 1.0);  // == obvious::min(a, 1.0): the constant is never NaN
-    const double n1 = fmin(sd1 * pp.inv_max_trunc, 1.0);
-    const double den0 = wv.x + wTile, den1 = wv.y + wTile;
-    const double q0 = (tv.x * wv.x + n0 * wTile) / den0;
-    const double q1 = (tv.y * wv.y + n1 * wTile) / den1;
     const bool f0 = isnan(tv.x), f1 = isnan(tv.y);  // first measurement of the cell
+    const bool one0 = (tv.x == 1.0) && (n0 == 1.0) && (den0 != 0.0) && (fabs(den0) < __longlong_as_double(0x7ff0000000000000LL));
+    const bool one1 = (tv.y == 1.0) && (n1 == 1.0) && (den1 != 0.0) && (fabs(den1) < __longlong_as_double(0x7ff0000000000000LL));
+    double q0 = 1.0, q1 = 1.0;
+    if((ok0 && !f0 && !one0) || (ok1 && !f1 && !one1))
+    {
+      q0 = (tv.x * wv.x + n0 * wTile) / den0;
+      q1 = (tv.y * wv.y + n1 * wTile) / den1;
+    }
     if(ok0)
     {
       tv.x = f0 ? n0 : q0;
@@ -539,7 +630,7 @@ __device__ __forceinline__ void empty_pair(double2& tv, double2& wv)
 // rewrites stores its own first column / row / cell into the strips of its -x, -y, -xy neighbours that mirror
 // them.  What is left for k_borders is to *pull* the strips of partitions that became initialised outside this
 // mechanism (allocated by this push, by freeFootprint or by an upload).
-// Which neighbours exist and are allocated comes as a bit mask per item (k_update's chunk prologue): bits 0-2 the
+// Which neighbours exist and are allocated comes as a bit mask per item (the producer warp of k_update): bits 0-2 the
 // mirror targets -x / -y / -xy (inside this grid or band), bits 3-5 the border sources +x / +y / +xy.
 // thread (xp, y) holds the final values of cells (y, xp) and (y, xp + 1) of the partition at `base`
 __device__ __forceinline__ void mirror_to_neighbours(const PushParams& pp, unsigned nb, size_t base, int xp, int y,
@@ -568,73 +659,167 @@ __device__ __forceinline__ void mirror_to_neighbours(const PushParams& pp, unsig
 __device__ __forceinline__ void pull_pass(const PushParams& pp, int warp, int nwarps, int lane);
 __device__ __forceinline__ void push_tail(const PushParams& pp);
 
-// K2 + K3.  Persistent CTAs with a two-stage cp.async pipeline over their partitions.
-// Thread t of 256 owns the cell pair x = 2*(t%16), 2*(t%16)+1 in rows t/16 and t/16 + 16: a warp reads two
-// adjacent 256-B rows (512 contiguous bytes) per 16-byte vector load.
-// A work-list entry carries the outcome of every scan of the launch for its partition (k_classify); the scans are
-// applied one after the other to the cells while they sit in registers, so a partition seen by both lasers of a
-// robot is read and written once.
-template <int CTAS_PER_SM, int NS>
-__global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushParams pp)
+// ---- mbarrier / bulk-copy (TMA) primitives of the k_update pipeline --------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-  // the scans (8.6 KB + 1 KB each) and the beam-boundary table (17 KB) are read through L1 (read-only path): they
-  // stay resident per SM for the whole launch, with no per-CTA staging pass
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint elapses)
+// instead of returning after its short default limit -- a waiting warp issues almost nothing
+__device__ __forceinline__ bool mbar_try_wait_parked(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  if(mbar_try_wait(bar, parity)) return;
+  while(!mbar_try_wait_parked(bar, parity)) {}
+}
+// global -> shared bulk copy (TMA unit, no register staging); completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// Per item in flight: what the consumers need to know about the partition besides its cells.  The producer also
+// stages the item's slices of the single-precision per-column / per-row tables here (32 entries each per scan), so
+// that a consumer's chain starts with shared-memory loads instead of L2 round trips.
+template <int NS>
+struct UpdMeta
+{
+  uint32_t entry;  // work-list entry: partition | bit 31 = its cells existed before this push (and are in the stage);
+                   // 0xffffffff = no more work
+  uint32_t nbm;    // bits 0-5 neighbour masks, bits 8.. the 2-bit outcomes of the scans
+  int gx, gy;      // grid coordinates of the partition's first cell
+  size_t base;     // offset of the partition's cells in the tsd / weight arrays
+  double initw;    // TsdGridPartition::_initWeight (only read for a partition this push allocates)
+  double wt[NS];
+  alignas(16) float2 cxy[NS][TSD_TILE];  // fill_tables: Pi00*(X-tx'), Pi10*(X-tx') of the partition's 32 columns (read in pairs)
+  float2 rxy[NS][TSD_TILE];  //              Pi01*(Y-ty'), Pi11*(Y-ty') of its 32 rows
+  float cd[NS][TSD_TILE];    //              (X-tx)^2
+  float rd[NS][TSD_TILE];    //              (Y-ty)^2
+};
+// The metadata ring has one slot more than the stage ring: a consumer warp releases a stage as soon as it holds the
+// cells in registers but keeps reading the item's metadata while it computes.  The producer writes slot i % (S + 1) for
+// item i after every consumer warp released the stage of item i - S, which a warp does after it finished item
+// i - S - 1 -- the previous user of that slot -- entirely.
+#define UPDATE_META_SLOTS (UPDATE_STAGES + 1)
+template <int NS>
+constexpr size_t update_smem_bytes()
+{
+  return UPDATE_STAGES * STAGE_BYTES + UPDATE_META_SLOTS * sizeof(UpdMeta<NS>) + 2 * UPDATE_STAGES * 8;
+}
+
+// K2 + K3.  Persistent CTAs over the work list (one entry per touched partition), UPDATE_CTAS_PER_SM per SM.
+// Warp 8 is the PRODUCER.  It draws chunks of consecutive list entries from a global ticket counter -- guided
+// self-scheduling: a chunk is 1/(4 #CTAs) of what is left, so that the CTAs finish together although partitions cost
+// between a few hundred (free space) and several thousand cycles (a surface in it, two lasers) -- one entry per lane: the
+// entry, the scans' outcomes and partition weights, the allocation flags of the six neighbours that the border logic needs;
+// the next chunk is fetched while the current one is fed to the pipeline.  Feeding one partition: its table slices are
+// loaded (a lane per column / row), the stage is waited for (mbarrier `empty`), metadata and tables are stored, and
+// the TMA unit copies the partition's 8832 B of tsd and 8832 B of weight (interior + border strips, contiguous) into
+// the stage with two cp.async.bulk whose bytes complete the stage's `full` mbarrier.  No thread computes an address
+// per cell, no register stages the data, and the copies of UPDATE_STAGES - 1 partitions are in flight while one is
+// computed.
+// Warps 0-7 are the CONSUMERS: thread t of 256 owns the cell pair x = 2*(t%16), 2*(t%16)+1 in rows t/16 and
+// t/16 + 16 (16-byte shared loads, a warp reads two adjacent 256-B rows).  They wait on `full`, take their
+// cells (and the border cell they look after) into registers, release the stage (one arrive per warp), apply
+// the scans of the launch one after the other (a partition seen by both lasers of a robot is read and written
+// once), and store what changed with 16-byte stores.
+template <int NS>
+__global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(PushParams pp)
+{
+  extern __shared__ __align__(128) unsigned char smem[];
+  UpdMeta<NS>* s_meta = reinterpret_cast<UpdMeta<NS>*>(smem + UPDATE_STAGES * STAGE_BYTES);
+  const uint32_t bar0 = smem_u32(smem + UPDATE_STAGES * STAGE_BYTES + UPDATE_META_SLOTS * sizeof(UpdMeta<NS>));  // full[s], then empty[s]
   const uint32_t nItems = pp.counters[0];
-  const int t = threadIdx.x;
-  const int xp = (t & 15) * 2;
-  const int yb = t >> 4;
-  const bool edge = (xp == 0) || (yb == 0);
-  unsigned updates = 0;
-  unsigned long long updatesWide = 0;
-
-  // list entry of item `it`: partition index, bit 31 = its cells existed before this push (so they are read)
-  auto entry = [&](uint32_t it) -> uint32_t { return (it < nItems) ? pp.active[it] : 0xffffffffu; };
-
-  // Two-stage pipeline over the CTA's partitions: the 16 KB of cell state of partition i+1 are copied into
-  // shared memory with cp.async (LDGSTS, L1 bypass) while partition i is computed.  Every thread copies exactly
-  // the four 16-byte pieces it will read itself, so the only synchronisation is its own cp.async.wait_group.
-  __shared__ __align__(16) double2 s_cells[2][2][2 * UPDATE_THREADS];  // [stage][tsd|weight][row j * 256 + t]
-  auto stage_in = [&](uint32_t e, int stage)
-  {
-    if(e != 0xffffffffu && (e & 0x80000000u))
-    {
-      const size_t nb = (size_t)((e & 0x7fffffffu) - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
-#pragma unroll
-      for(int j = 0; j < 2; j++)
-      {
-        const int ci = (yb + 16 * j) * TSD_TILE + xp;
-        const unsigned dT = (unsigned)__cvta_generic_to_shared(&s_cells[stage][0][j * UPDATE_THREADS + t]);
-        const unsigned dW = (unsigned)__cvta_generic_to_shared(&s_cells[stage][1][j * UPDATE_THREADS + t]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dT), "l"(pp.tsd + nb + ci));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dW), "l"(pp.weight + nb + ci));
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::);
-  };
-
-  // Static striding over the item list (a ticket counter with one __syncthreads per item was measured slower:
-  // 55 us vs 48 us on C2).  The per-item metadata -- list entry, scan outcomes, partition weights, which neighbours
-  // are allocated (mirror targets -x/-y/-xy, border sources +x/+y/+xy) -- is fetched for 32 items at a time by the
-  // first warps and parked in shared memory: one memory round trip and two barriers per 32 items instead of
-  // dependent global loads in front of every item (on maps beyond L2 those were half of all stall samples).
   const uint32_t G = gridDim.x;
-  __shared__ uint32_t s_ent[ITEM_CHUNK + 1];
-  __shared__ uint32_t s_nbm[ITEM_CHUNK];   // bits 0-5 neighbour masks, bits 8.. the 2-bit outcomes of the scans
-  __shared__ double s_wt[NS][ITEM_CHUNK];
-  int stage = 0;
-  for(uint32_t chunk0 = blockIdx.x; chunk0 < nItems; chunk0 += ITEM_CHUNK * G)
+  const int t = threadIdx.x;
+  const int lane = t & 31;
+  if(t == 0)
   {
-    __syncthreads();  // the previous chunk is consumed
-    if(t <= ITEM_CHUNK)
+    for(int s = 0; s < UPDATE_STAGES; s++)
     {
-      const uint32_t it = chunk0 + (uint32_t)t * G;
-      const uint32_t e = entry(it);
-      s_ent[t] = e;
-      if(t < ITEM_CHUNK && e != 0xffffffffu)
+      mbar_init(bar0 + 8 * s, 1);                                         // the producer's arrive (+ the copies' bytes)
+      mbar_init(bar0 + 8 * (UPDATE_STAGES + s), UPDATE_CONSUMERS / 32);   // one arrive per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  unsigned updates = 0, emptied = 0;
+
+  if(t >= UPDATE_CONSUMERS)
+  {
+    // ------------------------------------------------------------------------------------------ producer warp
+    int s = 0, ms = 0;
+    uint32_t round = 0;
+    // one chunk of the work list in registers, a lane per entry
+    struct Chunk
+    {
+      uint32_t start, cnt, e, m;
+      double wt[NS];
+    };
+    auto grab = [&](uint32_t seen) -> Chunk  // seen: entries known to be handed out already
+    {
+      Chunk c;
+      uint32_t start = 0, want = 0;
+      if(lane == 0)
       {
+        const uint32_t left = nItems > seen ? nItems - seen : 0u;
+        want = min(32u, max(1u, left / (4 * G)));
+        start = atomicAdd(&pp.counters[19], want);
+      }
+      start = __shfl_sync(0xffffffffu, start, 0);
+      want = __shfl_sync(0xffffffffu, want, 0);
+      c.start = start;
+      c.cnt = start < nItems ? min(want, nItems - start) : 0u;
+      c.e = 0xffffffffu;
+      c.m = 0;
 #pragma unroll
-        for(int si = 0; si < NS; si++) s_wt[si][t] = pp.active_w[(size_t)si * pp.list_cap + it];
-        const int p = (int)(e & 0x7fffffffu);
+      for(int si = 0; si < NS; si++) c.wt[si] = 0.0;
+      if((uint32_t)lane < c.cnt)
+      {
+        const uint32_t it = start + (uint32_t)lane;
+        c.e = pp.active[it];
+#pragma unroll
+        for(int si = 0; si < NS; si++) c.wt[si] = pp.active_w[(size_t)si * pp.list_cap + it];
+        const int p = (int)(c.e & 0x7fffffffu);
         const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
         const bool hasL = px > 0, hasD = py > pp.row_begin;
         const bool hasR = px < pp.parts_x - 1, hasU = py < pp.parts_y - 1;
@@ -645,118 +830,243 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
         if(hasR && pp.flags[p + 1]) m |= 8u;
         if(hasU && pp.flags[p + pp.parts_x]) m |= 16u;
         if(hasR && hasU && pp.flags[p + pp.parts_x + 1]) m |= 32u;
-        s_nbm[t] = m;
+        c.m = m;
       }
-    }
-    __syncthreads();
-    if(chunk0 == blockIdx.x) stage_in(s_ent[0], 0);
-    for(int k = 0; k < ITEM_CHUNK; k++, stage ^= 1)
+      return c;
+    };
+#ifdef UPDATE_PROFILE
+    long long pr_t0 = clock64(), pr_wait = 0, pr_grab = 0, pr_items = 0;
+#endif
+    Chunk cur = grab(0);
+#ifdef UPDATE_PROFILE
+    pr_grab += clock64() - pr_t0;
+#endif
+    while(true)
     {
-      const uint32_t item = chunk0 + (uint32_t)k * G;
-      if(item >= nItems) break;
-      const uint32_t eCur = s_ent[k];
-      stage_in(s_ent[k + 1], stage ^ 1);
-      const unsigned nbm = s_nbm[k];
-      const unsigned nb = edge ? (nbm & 7u) : 0u;
+      // the next chunk's ticket and metadata are on their way while this one is fed (cur.cnt == 0: the sentinel)
+      Chunk nxt;
+      nxt.cnt = 0;
+#ifdef UPDATE_PROFILE
+      long long g0 = clock64();
+#endif
+      if(cur.cnt) nxt = grab(cur.start + cur.cnt);
+#ifdef UPDATE_PROFILE
+      pr_grab += clock64() - g0;
+      pr_items += cur.cnt;
+#endif
+      const int cnt = cur.cnt ? (int)cur.cnt : 1;
+      for(int j = 0; j < cnt; j++)
+      {
+        const uint32_t ej = __shfl_sync(0xffffffffu, cur.e, j);
+        const uint32_t mj = __shfl_sync(0xffffffffu, cur.m, j);
+        double wj[NS];
+#pragma unroll
+        for(int si = 0; si < NS; si++) wj[si] = __shfl_sync(0xffffffffu, cur.wt[si], j);
+        // this lane's column / row of the partition: table slices of every scan (consumed after the wait below)
+        float2 cxy[NS], rxy[NS];
+        float cd[NS], rd[NS];
+        if(ej != 0xffffffffu)
+        {
+          const uint32_t p = ej & 0x7fffffffu;
+          const int gx = (int)(p & (uint32_t)(pp.parts_x - 1)) * TSD_TILE + lane;
+          const int gy = (int)(p >> pp.parts_shift) * TSD_TILE + lane;
+#pragma unroll
+          for(int si = 0; si < NS; si++)
+          {
+            cxy[si] = __ldg(pp.colxy + (size_t)si * pp.cells_x + gx);
+            cd[si] = __ldg(pp.cold + (size_t)si * pp.cells_x + gx);
+            rxy[si] = __ldg(pp.rowxy + (size_t)si * pp.cells_y + gy);
+            rd[si] = __ldg(pp.rowd + (size_t)si * pp.cells_y + gy);
+          }
+        }
+        const uint32_t full = bar0 + 8 * s, empty = bar0 + 8 * (UPDATE_STAGES + s);
+#ifdef UPDATE_PROFILE
+        long long w0 = clock64();
+#endif
+        if(lane == 0) mbar_wait(empty, (round & 1u) ^ 1u);  // (passes at once the first time round)
+#ifdef UPDATE_PROFILE
+        pr_wait += clock64() - w0;
+#endif
+        __syncwarp();
+        UpdMeta<NS>& meta = s_meta[ms];
+        if(ej != 0xffffffffu)
+        {
+#pragma unroll
+          for(int si = 0; si < NS; si++)
+          {
+            meta.cxy[si][lane] = cxy[si];
+            meta.cd[si][lane] = cd[si];
+            meta.rxy[si][lane] = rxy[si];
+            meta.rd[si][lane] = rd[si];
+          }
+        }
+        if(lane == 0)
+        {
+          meta.entry = ej;
+          meta.nbm = mj;
+          if(ej != 0xffffffffu)
+          {
+            const uint32_t p = ej & 0x7fffffffu;
+            meta.gx = (int)(p & (uint32_t)(pp.parts_x - 1)) * TSD_TILE;
+            meta.gy = (int)(p >> pp.parts_shift) * TSD_TILE;
+            meta.base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
+            meta.initw = (ej & 0x80000000u) ? 0.0 : pp.initw[p];
+          }
+#pragma unroll
+          for(int si = 0; si < NS; si++) meta.wt[si] = wj[si];
+        }
+        __syncwarp();  // every lane's stores are ordered before lane 0's arrive (release)
+        if(lane == 0)
+        {
+          if(ej != 0xffffffffu && (ej & 0x80000000u))
+          {
+            const size_t nb = (size_t)((ej & 0x7fffffffu) - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
+            const uint32_t dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
+            mbar_arrive_expect_tx(full, STAGE_BYTES);
+            bulk_g2s(dst, pp.tsd + nb, TILE_BYTES, full);
+            bulk_g2s(dst + TILE_BYTES, pp.weight + nb, TILE_BYTES, full);
+          }
+          else
+            mbar_arrive(full);  // a partition this push allocates (nothing to read), or the end of the list
+        }
+        if(++s == UPDATE_STAGES) { s = 0; round++; }
+        if(++ms == UPDATE_META_SLOTS) ms = 0;
+      }
+      if(cur.cnt == 0) break;
+      cur = nxt;
+    }
+#ifdef UPDATE_PROFILE
+    if(lane == 0 && pp.prof)
+    {
+      pp.prof[blockIdx.x * 8 + 0] = clock64() - pr_t0;
+      pp.prof[blockIdx.x * 8 + 1] = pr_wait;
+      pp.prof[blockIdx.x * 8 + 2] = pr_grab;
+      pp.prof[blockIdx.x * 8 + 3] = pr_items;
+    }
+#endif
+  }
+  else
+  {
+    // ------------------------------------------------------------------------------------------ consumer warps
+    const int xp = (t & 15) * 2;
+    const int yb = t >> 4;
+    const bool edge = (xp == 0) || (yb == 0);
+    const int ci0 = yb * TSD_TILE + xp, ci1 = ci0 + 16 * TSD_TILE;  // this thread's cell pairs: rows yb and yb + 16
+    int s = 0, ms = 0;
+    uint32_t par = 0;
+#ifdef UPDATE_PROFILE
+    long long co_t0 = clock64(), co_wait = 0, co_first = 0;
+#endif
+    while(true)
+    {
+      const uint32_t full = bar0 + 8 * s, empty = bar0 + 8 * (UPDATE_STAGES + s);
+#ifdef UPDATE_PROFILE
+      long long w0 = clock64();
+#endif
+      mbar_wait(full, par);
+#ifdef UPDATE_PROFILE
+      { long long w1 = clock64(); if(co_first == 0) co_first = w1 - co_t0; else co_wait += w1 - w0; }
+#endif
+      const double* st = reinterpret_cast<const double*>(smem + (size_t)s * STAGE_BYTES);
+      const UpdMeta<NS>& meta = s_meta[ms];
+      const uint32_t eCur = meta.entry;
+      if(eCur == 0xffffffffu) break;
+      const unsigned nbm = meta.nbm;
+      if(++s == UPDATE_STAGES) { s = 0; par ^= 1u; }
+      if(++ms == UPDATE_META_SLOTS) ms = 0;
       const unsigned kinds = nbm >> 8;
-      const uint32_t p = eCur & 0x7fffffffu;
       const bool wasInit = (eCur & 0x80000000u) != 0;
-      const int px = p & (pp.parts_x - 1), py = p >> pp.parts_shift;
-      const size_t base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
-      double* T = pp.tsd + base;
-      double* W = pp.weight + base;
       // the border cell this thread looks after (t < 65): only strips WITHOUT an allocated source neighbour are
       // the partition's own business (the others mirror the neighbour, which keeps them current)
       const bool myStrip = t < 65 && !((nbm >> (t < 32 ? 3 : (t < 64 ? 4 : 5))) & 1u);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-      double2 tv[2], wv[2];
-      double bt = 0.0, bw = 0.0;
-      bool alloc = wasInit, dirty[2] = {false, false}, stripDirty = false;
+      // a partition this push allocates starts from TsdGridPartition::init (TsdGridPartition.cpp:98-119): in the list
+      // because some scan found it active, and no scan before that one did anything to it
+      double2 tv0, wv0, tv1, wv1;
+      double bt, bw;
       if(wasInit)
       {
-#pragma unroll
-        for(int j = 0; j < 2; j++)
-        {
-          tv[j] = s_cells[stage][0][j * UPDATE_THREADS + t];
-          wv[j] = s_cells[stage][1][j * UPDATE_THREADS + t];
-        }
+        tv0 = *reinterpret_cast<const double2*>(st + ci0);
+        wv0 = *reinterpret_cast<const double2*>(st + TSD_TILE_STRIDE + ci0);
+        tv1 = *reinterpret_cast<const double2*>(st + ci1);
+        wv1 = *reinterpret_cast<const double2*>(st + TSD_TILE_STRIDE + ci1);
+        bt = bw = 0.0;
         if(myStrip && (kinds & 0x55u))  // some scan runs increaseEmptiness over the border cells too
         {
-          bt = T[TSD_BORDER_OFF + t];
-          bw = W[TSD_BORDER_OFF + t];
+          bt = st[TSD_BORDER_OFF + t];
+          bw = st[TSD_TILE_STRIDE + TSD_BORDER_OFF + t];
         }
       }
-#pragma unroll
+      else
+      {
+        const double initW = meta.initw;
+        const double initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
+        tv0 = tv1 = make_double2(initT, initT);
+        wv0 = wv1 = make_double2(initW, initW);
+        bt = initT;
+        bw = initW;
+      }
+      __syncwarp();
+      if(lane == 0) mbar_arrive(empty);  // this warp has taken everything it needs out of the stage
+      bool dirty0 = !wasInit, dirty1 = !wasInit, stripDirty = !wasInit;
+      // The scans one after the other, rolled (the body unrolled NS times is beyond the instruction cache: measured,
+      // 39 % of all stall samples "no instruction"); the two cell pairs of a thread side by side.
+#pragma unroll 1
       for(int si = 0; si < NS; si++)
       {
         const unsigned kind = (kinds >> (2 * si)) & 3u;
-        if(kind == 2u)
+        if(kind == 2u && !(pp.update_filter & 1u))
         {
+          const float4 cxy = *reinterpret_cast<const float4*>(&meta.cxy[si][xp]);
+          const float2 cd = *reinterpret_cast<const float2*>(&meta.cd[si][xp]);
+          const float2 rxy0 = meta.rxy[si][yb], rxy1 = meta.rxy[si][yb + 16];
+          const float rd0 = meta.rd[si][yb], rd1 = meta.rd[si][yb + 16];
+          const double wTile = meta.wt[si];
+          const float2* gate = pp.gate + (size_t)si * pp.scan_cap;
           const ScanDev& sc = pp.scans[si];
-          const double* ct = pp.coltab + (size_t)si * 3 * pp.cells_x;
-          const double* rt = pp.rowtab + (size_t)si * 3 * pp.cells_y;
-          const double wTile = s_wt[si][k];
-          const int gx = px * TSD_TILE + xp;
-          const int gy = py * TSD_TILE + yb;
-          const double2 cA = *reinterpret_cast<const double2*>(ct + gx);
-          const double2 cB = *reinterpret_cast<const double2*>(ct + pp.cells_x + gx);
-          const double2 cD = *reinterpret_cast<const double2*>(ct + 2 * pp.cells_x + gx);
-          if(!alloc)
-          {
-            // TsdGridPartition::init (TsdGridPartition.cpp:98-119)
-            const double initW = pp.initw[p];
-            const double initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-            for(int j = 0; j < 2; j++)
-            {
-              tv[j] = make_double2(initT, initT);
-              wv[j] = make_double2(initW, initW);
-              dirty[j] = true;
-            }
-            bt = initT;
-            bw = initW;
-            stripDirty = true;
-            alloc = true;
-          }
-#pragma unroll
-          for(int j = 0; j < 2; j++)
-          {
-            const double rA = rt[gy + 16 * j];
-            const double rB = rt[pp.cells_y + gy + 16 * j];
-            const double rD = rt[2 * pp.cells_y + gy + 16 * j];
-            const unsigned u = update_pair(pp, sc, cA, cB, cD, rA, rB, rD, wTile, tv[j], wv[j]);
-            updates += u;
-            dirty[j] = dirty[j] || (u != 0u);
-          }
+          // the four cells are classified side by side (four independent dependency chains in straight-line code),
+          // then the two pairs are updated
+          int k00, k01, k10, k11;
+          const int c00 = classify_cell(sc, gate, cxy.x + rxy0.x, cxy.y + rxy0.y, cd.x + rd0, k00);
+          const int c01 = classify_cell(sc, gate, cxy.z + rxy0.x, cxy.w + rxy0.y, cd.y + rd0, k01);
+          const int c10 = classify_cell(sc, gate, cxy.x + rxy1.x, cxy.y + rxy1.y, cd.x + rd1, k10);
+          const int c11 = classify_cell(sc, gate, cxy.z + rxy1.x, cxy.w + rxy1.y, cd.y + rd1, k11);
+          const unsigned u0 = update_pair(pp, sc, si, c00, c01, k00, k01, meta.gx + xp, meta.gy + yb, wTile, tv0, wv0);
+          const unsigned u1 = update_pair(pp, sc, si, c10, c11, k10, k11, meta.gx + xp, meta.gy + yb + 16, wTile, tv1, wv1);
+          updates += u0 + u1;
+          dirty0 = dirty0 || (u0 != 0u);
+          dirty1 = dirty1 || (u1 != 0u);
         }
-        else if(kind == 1u)
+        else if(kind == 1u && !(pp.update_filter & 2u))
         {
           // K3: increaseEmptiness on an allocated partition, all 33x33 cells
-#pragma unroll
-          for(int j = 0; j < 2; j++)
-          {
-            empty_pair(tv[j], wv[j]);
-            dirty[j] = true;
-          }
+          empty_pair(tv0, wv0);
+          empty_pair(tv1, wv1);
+          dirty0 = dirty1 = true;
           if(myStrip)
           {
             empty_cell(bt, bw);
             stripDirty = true;
           }
-          if(t == 0) updatesWide += 33 * 33;
+          if(t == 0) emptied++;
         }
       }
-#pragma unroll
-      for(int j = 0; j < 2; j++)
+      const size_t base = meta.base;
+      double* T = pp.tsd + base;
+      double* W = pp.weight + base;
+      if(dirty0)
       {
-        const int y = yb + 16 * j;
-        const int ci = y * TSD_TILE + xp;
-        if(dirty[j])
-        {
-          *reinterpret_cast<double2*>(T + ci) = tv[j];
-          *reinterpret_cast<double2*>(W + ci) = wv[j];
-        }
-        if(nb) mirror_to_neighbours(pp, nb, base, xp, y, tv[j], wv[j]);
+        *reinterpret_cast<double2*>(T + ci0) = tv0;
+        *reinterpret_cast<double2*>(W + ci0) = wv0;
+      }
+      if(dirty1)
+      {
+        *reinterpret_cast<double2*>(T + ci1) = tv1;
+        *reinterpret_cast<double2*>(W + ci1) = wv1;
+      }
+      if(edge && (nbm & 7u))
+      {
+        mirror_to_neighbours(pp, nbm & 7u, base, xp, yb, tv0, wv0);
+        mirror_to_neighbours(pp, nbm & 7u, base, xp, yb + 16, tv1, wv1);
       }
       if(myStrip && stripDirty)
       {
@@ -764,14 +1074,24 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
         W[TSD_BORDER_OFF + t] = bw;
       }
     }
+#ifdef UPDATE_PROFILE
+    if(t == 0 && pp.prof)
+    {
+      pp.prof[blockIdx.x * 8 + 4] = clock64() - co_t0;
+      pp.prof[blockIdx.x * 8 + 5] = co_wait;
+      pp.prof[blockIdx.x * 8 + 6] = co_first;
+      unsigned smid;
+      asm("mov.u32 %0, %%smid;" : "=r"(smid));
+      pp.prof[blockIdx.x * 8 + 7] = smid;
+    }
+#endif
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
 
   // one atomic per CTA
   __shared__ unsigned long long s_upd[UPDATE_THREADS / 32];
 #pragma unroll
   for(int o = 16; o > 0; o >>= 1) updates += __shfl_xor_sync(0xffffffffu, updates, o);
-  if((t & 31) == 0) s_upd[t >> 5] = (unsigned long long)updates + updatesWide;
+  if(lane == 0) s_upd[t >> 5] = (unsigned long long)updates + (unsigned long long)emptied * (33 * 33);
   __syncthreads();
   if(t == 0)
   {
@@ -793,7 +1113,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
     if(s_last)
     {
       __threadfence();
-      pull_pass(pp, t >> 5, UPDATE_THREADS / 32, t & 31);
+      pull_pass(pp, t >> 5, UPDATE_THREADS / 32, lane);
       __syncthreads();
       if(t == 0)
       {
@@ -804,6 +1124,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, CTAS_PER_SM) k_update(PushPara
     }
   }
 }
+
 
 // K4: TsdGrid::propagateBorders (TsdGrid.cpp:372-427) restricted to the partitions whose cells changed
 // in this push or since the last one (pending): a touched partition refreshes its own
@@ -900,6 +1221,7 @@ __device__ __forceinline__ void push_tail(const PushParams& pp)
   pp.counters[21] = (uint32_t)(pp.stats64[0] >> 32);
   for(int i = 0; i < 8; i++) pp.counters[i] = 0;
   pp.counters[18] = 0;
+  pp.counters[19] = 0;  // k_update's work ticket
   pp.stats64[0] = 0;
 }
 
@@ -1164,6 +1486,15 @@ static PushParams make_params(const tsd_grid* g)
   pp.coltab = g->d_coltab;
   pp.rowtab = g->d_rowtab;
   pp.dirs = g->d_dirs;
+  pp.colxy = reinterpret_cast<float2*>(g->d_col4);  // one allocation: cells_x float2 per scan, then cells_x float per scan
+  pp.cold = reinterpret_cast<float*>(g->d_col4) + (size_t)2 * g->cells_x * PUSH_MAX_SCANS;
+  pp.rowxy = reinterpret_cast<float2*>(g->d_row4);
+  pp.rowd = reinterpret_cast<float*>(g->d_row4) + (size_t)2 * g->cells_y * PUSH_MAX_SCANS;
+  pp.gate = g->d_gate;
+  pp.scan_cap = g->scan_cap;
+  pp.update_filter = g->update_filter;
+  pp.scans_dev = g->d_scans;
+  pp.prof = g->d_prof;
   return pp;
 }
 
@@ -1194,14 +1525,17 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
 {
   if(n <= g->scan_cap) return TSD_OK;
   TSD_CUDA(cudaStreamSynchronize(g->stream));
-  cudaFree(g->d_in); cudaFree(g->d_dirs); cudaFree(g->d_rc);
+  cudaFree(g->d_in); cudaFree(g->d_dirs); cudaFree(g->d_rc); cudaFree(g->d_gate);
   cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc);
+  g->d_in = g->d_rc = nullptr; g->d_dirs = nullptr; g->d_gate = nullptr; g->h_in = g->h_rc = nullptr;
+  g->scan_cap = 0;
   const int cap = ((n + 63) / 64) * 64 + 64;
   g->in_bytes = PUSH_MAX_SCANS * (sizeof(double) * cap + cap) + sizeof(double) * 2 * cap;
   g->rc_bytes = sizeof(double) * 4 * cap + sizeof(unsigned long long) * cap + sizeof(unsigned long long) * 2;
   TSD_CUDA(cudaMalloc(&g->d_in, g->in_bytes));
   TSD_CUDA(cudaMalloc(&g->d_rc, g->rc_bytes));
   TSD_CUDA(cudaMalloc(&g->d_dirs, sizeof(double2) * (cap + 1)));
+  TSD_CUDA(cudaMalloc(&g->d_gate, sizeof(float2) * (size_t)cap * PUSH_MAX_SCANS));
   TSD_CUDA(cudaMallocHost(&g->h_in, g->in_bytes));
   TSD_CUDA(cudaMallocHost(&g->h_rc, g->rc_bytes));
   TSD_CUDA(cudaMemsetAsync(g->d_rc, 0, g->rc_bytes, g->stream));
@@ -1432,6 +1766,13 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaMalloc(&g->d_coltab, sizeof(double) * 3 * g->cells_x * PUSH_MAX_SCANS));
   TSD_CUDA(cudaMalloc(&g->d_rowtab, sizeof(double) * 3 * g->cells_y * PUSH_MAX_SCANS));
   TSD_CUDA(cudaMalloc(&g->d_kinds, sizeof(uint32_t) * g->n_owned));
+  TSD_CUDA(cudaMalloc(&g->d_scans, sizeof(tsd::ScanDev) * PUSH_MAX_SCANS));
+#ifdef UPDATE_PROFILE
+  TSD_CUDA(cudaMalloc(&g->d_prof, sizeof(unsigned long long) * 8 * g->sm_count * UPDATE_CTAS_PER_SM));
+  TSD_CUDA(cudaMemset(g->d_prof, 0, sizeof(unsigned long long) * 8 * g->sm_count * UPDATE_CTAS_PER_SM));
+#endif
+  TSD_CUDA(cudaMalloc(&g->d_col4, sizeof(float4) * g->cells_x * PUSH_MAX_SCANS));
+  TSD_CUDA(cudaMalloc(&g->d_row4, sizeof(float4) * g->cells_y * PUSH_MAX_SCANS));
   TSD_CUDA(cudaMallocHost(&g->h_counters, sizeof(uint32_t) * 32));
   TSD_CUDA(cudaMallocHost(&g->h_stats64, sizeof(unsigned long long) * 4));
   TSD_CUDA(cudaMemsetAsync(g->d_flags, 0, g->n_parts, g->stream));
@@ -1461,7 +1802,7 @@ int tsdg_destroy(tsd_grid_t* g)
       cudaIpcCloseMemHandle(g->peer[b].tsd); cudaIpcCloseMemHandle(g->peer[b].weight); cudaIpcCloseMemHandle(g->peer[b].signal);
     }
   cudaFree(g->d_pending); cudaFree(g->d_counters);
-  cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_kinds); cudaFree(g->d_dirs); cudaFree(g->d_in);
+  cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_col4); cudaFree(g->d_row4); cudaFree(g->d_scans); cudaFree(g->d_prof); cudaFree(g->d_gate); cudaFree(g->d_kinds); cudaFree(g->d_dirs); cudaFree(g->d_in);
   cudaFree(g->d_rc); cudaFree(g->d_scratch);
   cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters);
   cudaFreeHost(g->h_stats64);
@@ -1601,7 +1942,8 @@ int tsdg_push_staged(tsd_grid_t* g)
   pp.cl_py0 = box[1];
   pp.cl_w = box[2] - box[0] + 1;
   pp.cl_h = box[3] - box[1] + 1;
-  const int nmax = TSD_TILE * (pp.cl_w > pp.cl_h ? pp.cl_w : pp.cl_h);
+  int nmax = TSD_TILE * (pp.cl_w > pp.cl_h ? pp.cl_w : pp.cl_h);  // the first threads also fill the per-push tables
+  if(nmax < pp.scans[0].n) nmax = pp.scans[0].n;
   const int nthreads = (4 * pp.cl_w * pp.cl_h > nmax) ? 4 * pp.cl_w * pp.cl_h : nmax;
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[0], g->stream));
   const int cctas = (nthreads + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS;
@@ -1610,9 +1952,21 @@ int tsdg_push_staged(tsd_grid_t* g)
   else k_classify<1><<<cctas, CLASSIFY_THREADS, 0, g->stream>>>(pp, g->d_coltab, g->d_rowtab);
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[1], g->stream));
-  const size_t smem = 0;
-  const int ctasPerSm = UPDATE_CTAS_PER_SM;  // 3 x 256 threads x 80 registers; 4 (64 registers, spills) measured slower
-  int ctas = g->sm_count * ctasPerSm;
+  const size_t smem = ns == 4 ? update_smem_bytes<4>() : (ns == 2 ? update_smem_bytes<2>() : update_smem_bytes<1>());
+  {
+    // the pipeline stages live in dynamic shared memory beyond the 48 KB default: opt in once per device
+    static std::mutex mtx;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mtx);
+    if(!done[g->device & 63])
+    {
+      TSD_CUDA(cudaFuncSetAttribute(k_update<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<1>()));
+      TSD_CUDA(cudaFuncSetAttribute(k_update<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<2>()));
+      TSD_CUDA(cudaFuncSetAttribute(k_update<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<4>()));
+      done[g->device & 63] = true;
+    }
+  }
+  int ctas = g->sm_count * UPDATE_CTAS_PER_SM;
   if(ctas > g->n_owned) ctas = g->n_owned;
   // nothing asked for a full border refresh: K4's remainder runs in k_update's last CTA.  (Sharded grids too: the
   // strips that depend on the halo row above the band are refreshed after the exchange, tsdg_band_push_finish.)
@@ -1620,15 +1974,15 @@ int tsdg_push_staged(tsd_grid_t* g)
   if(g->band) g->band_push_open = true;
   if(ns == 4)
   {
-    k_update<UPDATE_CTAS_PER_SM, 4><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+    k_update<4><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   }
   else if(ns == 2)
   {
-    k_update<UPDATE_CTAS_PER_SM, 2><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+    k_update<2><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   }
   else
   {
-    k_update<UPDATE_CTAS_PER_SM, 1><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
+    k_update<1><<<ctas, UPDATE_THREADS, smem, g->stream>>>(pp);
   }
   TSD_LAUNCHED();
   if(g->timing) TSD_CUDA(cudaEventRecord(g->ev[2], g->stream));
@@ -1894,6 +2248,27 @@ int tsdg_band_row(tsd_grid_t* g, int which, double** tsd, double** weight, uint6
   *tsd = g->d_tsd + off;
   *weight = g->d_weight + off;
   *count = (uint64_t)g->parts_x * TSD_TILE_STRIDE;
+  return TSD_OK;
+}
+
+// UPDATE_PROFILE builds: cycle counters of the last k_update launch, 8 per CTA: producer {total, waiting for a free
+// stage, fetching work, items}, consumer warp 0 {total, waiting for data after the first item, until the first item, SM}
+int tsdg_debug_profile(tsd_grid_t* g, unsigned long long* out, int max_ctas)
+{
+  if(!g || !out) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  if(!g->d_prof) return TSD_E_INVALID;
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  int n = g->sm_count * UPDATE_CTAS_PER_SM;
+  if(n > max_ctas) n = max_ctas;
+  TSD_CUDA(cudaMemcpy(out, g->d_prof, sizeof(unsigned long long) * 8 * n, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int tsdg_set_update_filter(tsd_grid_t* g, unsigned mask)
+{
+  if(!g) return TSD_E_INVALID;
+  g->update_filter = mask & 3u;
   return TSD_OK;
 }
 

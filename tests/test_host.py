@@ -1,9 +1,13 @@
 """Host-side pieces: synthetic data generator determinism, the host sensor mirror, gslcblas-order gemm."""
+import os
+
 import numpy as np
 
 from ohm_tsd_slam_b200 import synth
 from ohm_tsd_slam_b200.scan import HostSensor, gemm_nn, standard_mask
 from oracle import port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_synth_is_deterministic_and_hokuyo_like():
@@ -59,3 +63,21 @@ def test_build_stamp_follows_the_sources_not_their_mtimes(monkeypatch):
     assert not _build.needs_build()
     monkeypatch.setattr(_build, "source_hash", lambda: "something else")
     assert _build.needs_build()
+
+
+def test_fast_path_front_end_is_exact_where_it_is_certain(tmp_path):
+    """k_update's single-precision front end (csrc/beam_index.cuh: tsd_fast_model / tsd_gate_entry / tsd_classify_cell,
+    host/device code) against the reference's double-precision expressions (SensorPolar2D.cpp:117-135, TsdGrid.cpp:250-274,
+    TsdGridPartition.h:174-191) on the CPU: every cell the front end decides must be decided as the reference decides
+    it -- random and adversarial cells (next to beam boundaries, next to the truncation band, on the cut of atan2),
+    approximate reciprocal perturbed by up to +-2 ulp.  tests/cpp/fastpath_check.cpp."""
+    import subprocess
+    exe = str(tmp_path / "fastpath_check")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", os.path.join(ROOT, "tests", "cpp", "fastpath_check.cpp"),
+                    "-o", exe], check=True)
+    out = subprocess.run([exe, "1500000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "violations 0" in out.stdout
+    # the front end must decide almost everything, or it is not a fast path
+    certain = float(out.stdout.split("certain ")[1].split("%")[0])
+    assert certain > 99.0, out.stdout
