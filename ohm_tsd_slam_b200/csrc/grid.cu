@@ -429,7 +429,8 @@ __global__ void __launch_bounds__(CLASSIFY_THREADS) k_classify(PushParams pp, do
 #define UPDATE_CONSUMERS 256                        // threads that update cells: 8 warps, 4 cells each per partition
 #define UPDATE_THREADS (UPDATE_CONSUMERS + 32)      // + one producer warp (work list, metadata, bulk copies)
 #ifndef UPDATE_STAGES
-#define UPDATE_STAGES 3
+#define UPDATE_STAGES 2   // measured on C2: 2 stages 76.8 us, 3 stages 85.2 us (the shared memory a third stage takes is L1 the
+                          // kernel's table look-ups and register spills live in); the copies saturate HBM with 2 x 3 CTAs/SM
 #endif
 #ifndef UPDATE_CTAS_PER_SM
 #define UPDATE_CTAS_PER_SM 3
@@ -795,18 +796,29 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
       uint32_t start, cnt, e, m;
       double wt[NS];
     };
-    auto grab = [&](uint32_t seen) -> Chunk  // seen: entries known to be handed out already
+    // The first chunk of every CTA is static (entries [blockIdx * first, +first)): no ticket, no contention of all CTAs
+    // on one counter at the start of the launch; the tickets hand out what follows.
+    const uint32_t first = min(32u, nItems / (4 * G));
+    auto grab = [&](uint32_t seen, bool initial) -> Chunk  // seen: entries known to be handed out already
     {
       Chunk c;
       uint32_t start = 0, want = 0;
-      if(lane == 0)
+      if(initial && first > 0)
       {
-        const uint32_t left = nItems > seen ? nItems - seen : 0u;
-        want = min(32u, max(1u, left / (4 * G)));
-        start = atomicAdd(&pp.counters[19], want);
+        start = blockIdx.x * first;
+        want = first;
       }
-      start = __shfl_sync(0xffffffffu, start, 0);
-      want = __shfl_sync(0xffffffffu, want, 0);
+      else
+      {
+        if(lane == 0)
+        {
+          const uint32_t left = nItems > seen ? nItems - seen : 0u;
+          want = min(32u, max(1u, left / (6 * G)));
+          start = atomicAdd(&pp.counters[19], want) + G * first;
+        }
+        start = __shfl_sync(0xffffffffu, start, 0);
+        want = __shfl_sync(0xffffffffu, want, 0);
+      }
       c.start = start;
       c.cnt = start < nItems ? min(want, nItems - start) : 0u;
       c.e = 0xffffffffu;
@@ -837,7 +849,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
 #ifdef UPDATE_PROFILE
     long long pr_t0 = clock64(), pr_wait = 0, pr_grab = 0, pr_items = 0;
 #endif
-    Chunk cur = grab(0);
+    Chunk cur = grab(G * first, true);
 #ifdef UPDATE_PROFILE
     pr_grab += clock64() - pr_t0;
 #endif
@@ -849,7 +861,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
 #ifdef UPDATE_PROFILE
       long long g0 = clock64();
 #endif
-      if(cur.cnt) nxt = grab(cur.start + cur.cnt);
+      if(cur.cnt) nxt = grab(max(cur.start + cur.cnt, G * first), false);
 #ifdef UPDATE_PROFILE
       pr_grab += clock64() - g0;
       pr_items += cur.cnt;
@@ -862,23 +874,6 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
         double wj[NS];
 #pragma unroll
         for(int si = 0; si < NS; si++) wj[si] = __shfl_sync(0xffffffffu, cur.wt[si], j);
-        // this lane's column / row of the partition: table slices of every scan (consumed after the wait below)
-        float2 cxy[NS], rxy[NS];
-        float cd[NS], rd[NS];
-        if(ej != 0xffffffffu)
-        {
-          const uint32_t p = ej & 0x7fffffffu;
-          const int gx = (int)(p & (uint32_t)(pp.parts_x - 1)) * TSD_TILE + lane;
-          const int gy = (int)(p >> pp.parts_shift) * TSD_TILE + lane;
-#pragma unroll
-          for(int si = 0; si < NS; si++)
-          {
-            cxy[si] = __ldg(pp.colxy + (size_t)si * pp.cells_x + gx);
-            cd[si] = __ldg(pp.cold + (size_t)si * pp.cells_x + gx);
-            rxy[si] = __ldg(pp.rowxy + (size_t)si * pp.cells_y + gy);
-            rd[si] = __ldg(pp.rowd + (size_t)si * pp.cells_y + gy);
-          }
-        }
         const uint32_t full = bar0 + 8 * s, empty = bar0 + 8 * (UPDATE_STAGES + s);
 #ifdef UPDATE_PROFILE
         long long w0 = clock64();
@@ -887,47 +882,56 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
 #ifdef UPDATE_PROFILE
         pr_wait += clock64() - w0;
 #endif
-        __syncwarp();
         UpdMeta<NS>& meta = s_meta[ms];
-        if(ej != 0xffffffffu)
-        {
-#pragma unroll
-          for(int si = 0; si < NS; si++)
-          {
-            meta.cxy[si][lane] = cxy[si];
-            meta.cd[si][lane] = cd[si];
-            meta.rxy[si][lane] = rxy[si];
-            meta.rd[si][lane] = rd[si];
-          }
-        }
+        const bool item = ej != 0xffffffffu;
+        const bool cells = item && (ej & 0x80000000u);
+        const uint32_t p = ej & 0x7fffffffu;
+        const int gx = (int)(p & (uint32_t)(pp.parts_x - 1)) * TSD_TILE;
+        const int gy = (int)(p >> pp.parts_shift) * TSD_TILE;
+        const size_t nb = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
         if(lane == 0)
         {
           meta.entry = ej;
           meta.nbm = mj;
-          if(ej != 0xffffffffu)
+          if(item)
           {
-            const uint32_t p = ej & 0x7fffffffu;
-            meta.gx = (int)(p & (uint32_t)(pp.parts_x - 1)) * TSD_TILE;
-            meta.gy = (int)(p >> pp.parts_shift) * TSD_TILE;
-            meta.base = (size_t)(p - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
-            meta.initw = (ej & 0x80000000u) ? 0.0 : pp.initw[p];
+            meta.gx = gx;
+            meta.gy = gy;
+            meta.base = nb;
+            meta.initw = cells ? 0.0 : pp.initw[p];
           }
 #pragma unroll
           for(int si = 0; si < NS; si++) meta.wt[si] = wj[si];
+          // one arrival for the metadata just written + the bytes the copies below will deliver
+          if(item) mbar_arrive_expect_tx(full, (cells ? (uint32_t)STAGE_BYTES : 0u) + (uint32_t)(NS * 6 * 128));
+          else mbar_arrive(full);  // the end of the list
         }
-        __syncwarp();  // every lane's stores are ordered before lane 0's arrive (release)
-        if(lane == 0)
+        __syncwarp();
+        // Everything else comes by bulk copy, one copy per lane: the partition's tsd and weight (lanes 0, 1) and, per
+        // scan, its 32-entry slices of the four single-precision tables (256 + 256 + 128 + 128 B, 16-byte aligned:
+        // gx and gy are multiples of 32).  Nothing passes through this warp's registers, nothing is waited for here.
+        if(item)
         {
-          if(ej != 0xffffffffu && (ej & 0x80000000u))
+          const void* src = nullptr;
+          uint32_t dst = 0, bytes = 0;
+          if(lane < 2)
           {
-            const size_t nb = (size_t)((ej & 0x7fffffffu) - pp.alloc_begin * pp.parts_x) * TSD_TILE_STRIDE;
-            const uint32_t dst = smem_u32(smem + (size_t)s * STAGE_BYTES);
-            mbar_arrive_expect_tx(full, STAGE_BYTES);
-            bulk_g2s(dst, pp.tsd + nb, TILE_BYTES, full);
-            bulk_g2s(dst + TILE_BYTES, pp.weight + nb, TILE_BYTES, full);
+            if(cells)
+            {
+              src = (lane == 0 ? pp.tsd : pp.weight) + nb;
+              dst = smem_u32(smem + (size_t)s * STAGE_BYTES) + (uint32_t)lane * TILE_BYTES;
+              bytes = TILE_BYTES;
+            }
           }
-          else
-            mbar_arrive(full);  // a partition this push allocates (nothing to read), or the end of the list
+          else if(lane < 2 + 4 * NS)
+          {
+            const int si = (lane - 2) >> 2, which = (lane - 2) & 3;
+            if(which == 0) { src = pp.colxy + (size_t)si * pp.cells_x + gx; dst = smem_u32(&meta.cxy[si][0]); bytes = 256; }
+            else if(which == 1) { src = pp.rowxy + (size_t)si * pp.cells_y + gy; dst = smem_u32(&meta.rxy[si][0]); bytes = 256; }
+            else if(which == 2) { src = pp.cold + (size_t)si * pp.cells_x + gx; dst = smem_u32(&meta.cd[si][0]); bytes = 128; }
+            else { src = pp.rowd + (size_t)si * pp.cells_y + gy; dst = smem_u32(&meta.rd[si][0]); bytes = 128; }
+          }
+          if(bytes) bulk_g2s(dst, src, bytes, full);
         }
         if(++s == UPDATE_STAGES) { s = 0; round++; }
         if(++ms == UPDATE_META_SLOTS) ms = 0;
@@ -981,20 +985,16 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
       const bool myStrip = t < 65 && !((nbm >> (t < 32 ? 3 : (t < 64 ? 4 : 5))) & 1u);
       // a partition this push allocates starts from TsdGridPartition::init (TsdGridPartition.cpp:98-119): in the list
       // because some scan found it active, and no scan before that one did anything to it
+      const size_t base = meta.base;
+      double* T = pp.tsd + base;
+      double* W = pp.weight + base;
       double2 tv0, wv0, tv1, wv1;
-      double bt, bw;
       if(wasInit)
       {
         tv0 = *reinterpret_cast<const double2*>(st + ci0);
         wv0 = *reinterpret_cast<const double2*>(st + TSD_TILE_STRIDE + ci0);
         tv1 = *reinterpret_cast<const double2*>(st + ci1);
         wv1 = *reinterpret_cast<const double2*>(st + TSD_TILE_STRIDE + ci1);
-        bt = bw = 0.0;
-        if(myStrip && (kinds & 0x55u))  // some scan runs increaseEmptiness over the border cells too
-        {
-          bt = st[TSD_BORDER_OFF + t];
-          bw = st[TSD_TILE_STRIDE + TSD_BORDER_OFF + t];
-        }
       }
       else
       {
@@ -1002,12 +1002,31 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
         const double initT = (initW > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
         tv0 = tv1 = make_double2(initT, initT);
         wv0 = wv1 = make_double2(initW, initW);
-        bt = initT;
-        bw = initW;
+      }
+      // The border cell this thread looks after is finished first (it only sees the partition's initialisation and
+      // the increaseEmptiness scans, never addTsd), so that it does not occupy registers during the cell update.
+      if(myStrip && (!wasInit || (kinds & 0x55u)))
+      {
+        double bt, bw;
+        if(wasInit)
+        {
+          bt = st[TSD_BORDER_OFF + t];
+          bw = st[TSD_TILE_STRIDE + TSD_BORDER_OFF + t];
+        }
+        else
+        {
+          bw = meta.initw;
+          bt = (bw > 0.0) ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
+        }
+        if(!(pp.update_filter & 2u))
+          for(unsigned k = kinds; k; k >>= 2)
+            if((k & 3u) == 1u) empty_cell(bt, bw);
+        T[TSD_BORDER_OFF + t] = bt;
+        W[TSD_BORDER_OFF + t] = bw;
       }
       __syncwarp();
       if(lane == 0) mbar_arrive(empty);  // this warp has taken everything it needs out of the stage
-      bool dirty0 = !wasInit, dirty1 = !wasInit, stripDirty = !wasInit;
+      bool dirty0 = !wasInit, dirty1 = !wasInit;
       // The scans one after the other, rolled (the body unrolled NS times is beyond the instruction cache: measured,
       // 39 % of all stall samples "no instruction"); the two cell pairs of a thread side by side.
 #pragma unroll 1
@@ -1042,17 +1061,9 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
           empty_pair(tv0, wv0);
           empty_pair(tv1, wv1);
           dirty0 = dirty1 = true;
-          if(myStrip)
-          {
-            empty_cell(bt, bw);
-            stripDirty = true;
-          }
           if(t == 0) emptied++;
         }
       }
-      const size_t base = meta.base;
-      double* T = pp.tsd + base;
-      double* W = pp.weight + base;
       if(dirty0)
       {
         *reinterpret_cast<double2*>(T + ci0) = tv0;
@@ -1067,11 +1078,6 @@ __global__ void __launch_bounds__(UPDATE_THREADS, UPDATE_CTAS_PER_SM) k_update(P
       {
         mirror_to_neighbours(pp, nbm & 7u, base, xp, yb, tv0, wv0);
         mirror_to_neighbours(pp, nbm & 7u, base, xp, yb + 16, tv1, wv1);
-      }
-      if(myStrip && stripDirty)
-      {
-        T[TSD_BORDER_OFF + t] = bt;
-        W[TSD_BORDER_OFF + t] = bw;
       }
     }
 #ifdef UPDATE_PROFILE

@@ -294,6 +294,10 @@ class DistBand:
         self._flags = None
         self._views = None
         self.transport = transport
+        # gloo (the CPU backend; also what the one-GPU multi-process parity test uses) reduces host tensors only
+        self._host_collectives = dist.get_backend() != "nccl"
+        if self._host_collectives and transport != "peer":
+            raise ValueError("the NCCL halo transport needs the nccl backend; use transport='peer'")
         if transport == "peer" and self.world > 1:
             blobs = [None] * self.world
             dist.all_gather_object(blobs, self.grid.band_export())
@@ -302,6 +306,15 @@ class DistBand:
             if self.rank + 1 < self.world:
                 self.grid.band_connect(1, blobs[self.rank + 1])
             dist.barrier()
+
+    def _all_reduce(self, t: torch.Tensor, op):
+        """All-reduce of a device tensor on the current stream (NCCL), or through the host (gloo)."""
+        if self._host_collectives:
+            h = t.cpu()
+            self.dist.all_reduce(h, op=op)
+            t.copy_(h)
+        else:
+            self.dist.all_reduce(t, op=op)
 
     def _row_views(self):
         if self._views is None:
@@ -382,7 +395,7 @@ class DistBand:
             self._flags = device_tensor(ptr, n, "|u1", self.device)
         cur = torch.cuda.current_stream(self.device)
         self.grid.stream_order(cur.cuda_stream, 0)
-        self.dist.all_reduce(self._flags, op=self.dist.ReduceOp.MAX)
+        self._all_reduce(self._flags, self.dist.ReduceOp.MAX)
         self.grid.stream_order(cur.cuda_stream, 1)
         self.flags_dirty = False
 
@@ -432,8 +445,8 @@ class DistBand:
         kp, pp = self.grid.raycast_band_keys(scan, rays_world)
         keys = device_tensor(kp, n, "<i8", self.device)
         payload = device_tensor(pp, 4 * n, "<f8", self.device).view(n, 4)
-        mask, out, _ = merge_first_events(keys, payload, lambda t: dist.all_reduce(t, op=dist.ReduceOp.MIN),
-                                          lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
+        mask, out, _ = merge_first_events(keys, payload, lambda t: self._all_reduce(t, dist.ReduceOp.MIN),
+                                          lambda t: self._all_reduce(t, dist.ReduceOp.SUM))
         mask = mask.cpu().numpy().astype(np.uint8)
         out = out.cpu().numpy()
         return out[:, :2], out[:, 2:], mask, int(mask.sum())

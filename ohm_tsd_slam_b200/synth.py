@@ -44,7 +44,9 @@ class World:
 
     @staticmethod
     def room_with_obstacles(cx: float, cy: float, width: float, height: float, n_obstacles: int, seed: int,
-                            keep_clear: float = 1.0) -> "World":
+                            keep_clear: float = 1.0, obstacle_scale: float | None = None) -> "World":
+        """obstacle_scale: circumradius of the obstacles in units of 0.15 .. 0.6 m; default: grows with the room
+        (1 for rooms up to 20 m)."""
         rng = np.random.default_rng(seed)
         x0, x1 = cx - width / 2, cx + width / 2
         y0, y1 = cy - height / 2, cy + height / 2
@@ -53,7 +55,7 @@ class World:
         tries = 0
         while made < n_obstacles and tries < 100 * max(n_obstacles, 1):
             tries += 1
-            r = rng.uniform(0.15, 0.6) * max(1.0, min(width, height) / 20.0)
+            r = rng.uniform(0.15, 0.6) * (max(1.0, min(width, height) / 20.0) if obstacle_scale is None else obstacle_scale)
             ox = rng.uniform(x0 + r, x1 - r)
             oy = rng.uniform(y0 + r, y1 - r)
             if math.hypot(ox - cx, oy - cy) < keep_clear + r + 0.5:
@@ -122,6 +124,7 @@ class Config:
     seed: int = BASE_SEED
     n_scans: int = 200
     twist: tuple = (0.03, 0.0, 0.005)  # forward, lateral, yaw per scan
+    obstacle_scale: float | None = None
 
     @property
     def cells(self) -> int:
@@ -137,7 +140,8 @@ class Config:
 
     def world(self) -> World:
         c = self.side / 2.0
-        return World.room_with_obstacles(c, c, self.room[0], self.room[1], self.n_obstacles, self.seed)
+        return World.room_with_obstacles(c, c, self.room[0], self.room[1], self.n_obstacles, self.seed,
+                                         obstacle_scale=self.obstacle_scale)
 
     def trajectory(self, n: int | None = None) -> np.ndarray:
         """(n, 3) ground-truth x, y, theta: start at the grid centre (ThreadLocalize.cpp:466-471), constant twist."""
@@ -167,8 +171,12 @@ def config(which: str) -> Config:
         return Config("C2", 12, seed=BASE_SEED + 2, room=(90.0, 67.5), n_obstacles=64,
                       sensor=SensorSpec(max_range=80.0))
     if which == "C3":
+        # 1024 obstacles of the size of C1's (pillars, vehicles: 0.15 .. 0.6 m circumradius) in a 360 x 270 m hall: the
+        # sensor sees most of the hall through them, every obstacle casts a shadow wedge, and most partitions in range
+        # are "active" (addTsd per cell) rather than "empty" -- the addTsd-dominated regime of the large map.  (With
+        # obstacles that grow with the room, 2 .. 8 m, the view ends after 30 m and a push touches 0.35 M cells.)
         return Config("C3", 14, seed=BASE_SEED + 3, room=(360.0, 270.0), n_obstacles=1024,
-                      sensor=SensorSpec(max_range=250.0), n_scans=8)
+                      sensor=SensorSpec(max_range=250.0), n_scans=8, obstacle_scale=1.0)
     if which == "C5":
         return Config("C5", 16, seed=BASE_SEED + 5, room=(1500.0, 1200.0), n_obstacles=1024,
                       sensor=SensorSpec(max_range=800.0), n_scans=4)

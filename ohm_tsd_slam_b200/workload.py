@@ -27,7 +27,7 @@ class DoubleLaserWorkload:
             self.world = cfg.world()
         else:
             self.world = synth.World.room_with_obstacles(origin[0], origin[1], cfg.room[0], cfg.room[1], cfg.n_obstacles,
-                                                         cfg.seed + seed_offset)
+                                                         cfg.seed + seed_offset, obstacle_scale=cfg.obstacle_scale)
             traj = traj + np.array([origin[0] - cfg.side / 2.0, origin[1] - cfg.side / 2.0, 0.0])
         self.sensors = [HostSensor(cfg.sensor, invert) for _ in self.offsets]
         self.map_scans = []    # list of Scan (alternating lasers)

@@ -1,6 +1,9 @@
-"""A grid sharded over REAL GPUs (one rank each, halo rows over CUDA IPC / NVLink or NCCL) equals the unsharded
-grid bit for bit.  Not a pytest test (the GPU test tier has one GPU):
-  torchrun --nproc-per-node 2 tests/gpu_shard_parity.py [peer|nccl]"""
+"""A grid sharded over several PROCESSES (one band per rank, halo rows over CUDA IPC peer stores or NCCL) equals the
+unsharded grid bit for bit: every partition after pushes, every ray cast (min-merge of the bands' crossings).
+  torchrun --nproc-per-node 2 tests/gpu_shard_parity.py [peer|nccl]             # one GPU per rank, NCCL plumbing
+  torchrun --nproc-per-node 2 tests/gpu_shard_parity.py peer --one-device      # all ranks on GPU 0, gloo plumbing:
+                                                                                  # what tests/test_sharded_multiproc.py runs
+                                                                                  # under pytest -m gpu on a one-GPU box"""
 import os
 import sys
 
@@ -14,10 +17,14 @@ from ohm_tsd_slam_b200.scan import HostSensor
 from ohm_tsd_slam_b200.sharded import DistBand
 from tests.harness import same
 
-transport = sys.argv[1] if len(sys.argv) > 1 else "peer"
-world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+transport = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "peer"
+one_device = "--one-device" in sys.argv
+world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = 0 if one_device else int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if one_device:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 cfg = synth.config("C1")
 whole = capi.Grid(cfg.cell_size, 5, cfg.layout_grid, device=local)      # every rank keeps its own unsharded copy
 band = DistBand(cfg.cell_size, cfg.layout_grid, local, transport=transport)
@@ -55,7 +62,7 @@ for k, (pose, r) in enumerate(cfg.scans(10)):
                 bad += 1
                 if bad < 4:
                     print(f"rank {rank} scan {k}: partition {p} differs", flush=True)
-t = torch.tensor([bad, checked], device="cuda")
+t = torch.tensor([bad, checked], device="cpu" if one_device else "cuda")
 dist.all_reduce(t)
 if rank == 0:
     print(f"transport {transport}, {world} GPUs: {int(t[1])} partition comparisons, {int(t[0])} mismatches -> {'OK' if int(t[0]) == 0 else 'FAIL'}")
