@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""bench.py -- TsdGrid::push throughput (+ raycast + ICP) of the B200-native hot path on BASELINE.json
-configs[1] (double-laser, 4096^2 grid), dense regime.  One JSON line on stdout (rank 0).
+"""bench.py -- TsdGrid::push throughput (+ raycast + ICP) of the B200-native hot path.  N = 1: BASELINE.json
+configs[2], the largest single-GPU configuration (16384^2 map, dense regime, the double-laser robot of configs[1] in a
+360 x 270 m hall with 1024 obstacles: addTsd-dominated); configs[1] (4096^2) rides along as `c2_double_laser`.
+N > 1: N robots on one (8192 N)^2 grid sharded in bands (configs[4]).  One JSON line on stdout (rank 0).
 
   python bench.py --gpus 1 --steps 50 --warmup 5            # CUDA arm (the product, through its C ABI)
   python bench.py --impl reference --steps 3 --warmup 1     # the reference's own CPU code (oracle/_ref)
@@ -279,14 +281,50 @@ def run_cuda(args):
     # ---------------- hypothesis scoring (BASELINE.json configs[3]: 10^5 hypotheses per scan; split over the ranks)
     from ohm_tsd_slam_b200.workload import hypothesis_benchmark
     want_cpu = not (args.no_cpu_baseline or world > 1)
-    hyp = hypothesis_benchmark(device=local, n_hyp=100000, reps=2, dist=dist if world > 1 else None, keep_inputs=want_cpu)
+    hyp = hypothesis_benchmark(device=local, n_hyp=100000, reps=20, dist=dist if world > 1 else None, keep_inputs=want_cpu)
     hyp_inputs = hyp.pop("_inputs", None)
+
+    # ---------------- ray-cast sweep (BASELINE.json configs[2] "push + raycast throughput sweep"): one 1081-beam cast per
+    # map size through the C ABI (host buffers), rays/s and march steps/s; L2 hit rates come from the ncu capture
+    c2 = None
+    rc_sweep = None
+    if world == 1 and not args.no_sweep:
+        from ohm_tsd_slam_b200.workload import raycast_sweep, secondary_push_benchmark
+        rc_sweep = raycast_sweep(device=local, main=(args.workload, grid, wl))
+        if args.workload != "C2":
+            c2 = secondary_push_benchmark("C2", device=local, steps=min(args.steps, 200), peak_gbs=measured_peak()[0])
 
     # ---------------- large-map push sweep (BASELINE.json configs[2]): the bandwidth regime of the push
     sweep = None
     if world == 1 and not args.no_sweep:
         from ohm_tsd_slam_b200.workload import large_grid_sweep
         sweep = large_grid_sweep(device=local, layout_grid=14, peak_gbs=measured_peak()[0])
+
+    # ---------------- K2-only / K3-only: the same launches with one kind of work switched off in the update kernel
+    # (tsdg_set_update_filter): which part of the roofline fraction is addTsd (K2) and
+    # which is increaseEmptiness streaming (K3)
+    split = None
+    if world == 1:
+        split = {}
+        for name, mask in (("k2_addTsd_only", 2), ("k3_increaseEmptiness_only", 1)):
+            rows = []
+            for i in range(n_steps):
+                for b in batches(i):
+                    grid.set_update_filter(mask)
+                    grid.push_batch(b)
+                    upd = grid.last_push_stats()["cell_updates"]
+                    grid.stage_batch(b)
+                    ts = []
+                    for _ in range(5):
+                        grid.push_staged()
+                        ts.append(grid.last_push_kernel_ms()["update"])
+                    rows.append((upd, float(np.median(ts))))
+            grid.set_update_filter(0)
+            u = float(np.mean([r[0] for r in rows]))
+            t = float(np.mean([r[1] for r in rows]))
+            split[name] = {"cell_updates_per_launch": u, "k_update_ms": t, "algorithmic_gbs": ALG_BYTES_PER_UPDATE * u / t / 1e6,
+                           "frac_of_hbm_peak": ALG_BYTES_PER_UPDATE * u / t / 1e6 / measured_peak()[0]}
+        # (the filtered pushes leave a map the reference would not have computed: this leg runs last on this grid)
 
     launches = capi.kernel_launches() - launches0
 
@@ -301,7 +339,9 @@ def run_cuda(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        traffic, traffic_src = profiled_traffic("k_update")
+        # DRAM traffic of the roofline kernel: only from an ncu capture of THIS workload (profiles/rNN_metrics.json keys
+        # "k_update@<workload>"); none for the sharded runs
+        traffic, traffic_src = profiled_traffic(f"k_update@{args.workload}") if world == 1 else (None, None)
         upd_ms = float(np.mean([k["update"] for k in kms]))
         achieved = ALG_BYTES_PER_UPDATE * upd_avg_per_push / (upd_ms * 1e-3) / 1e9
         value = work_dev / (dev_ms_max * 1e-3) / 1e9
@@ -313,7 +353,8 @@ def run_cuda(args):
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "cuda",
             "config": dict(wl.describe(), parallelism=(f"one band of partition rows per GPU ({world} bands), scans replicated, pushes without "
-                                                       f"communication, boundary rows to the neighbours once per step (NCCL P2P)"
+                                                       f"communication, boundary rows stored into the neighbours' halo rows once per step by one "
+                                                       f"kernel over CUDA-IPC peer mappings (NVLink P2P stores; no NCCL on the data path)"
                                                        if world > 1 else "single GPU"),
                            cell_updates_per_step=upd_per_step_all, push_launch_pairs_per_step_rank0=pushes_per_step,
                            batched=not args.no_batch),
@@ -323,7 +364,8 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_update (TsdGrid::push cell update, K2+K3)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel_ms": upd_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE * upd_avg_per_push},
+                         "kernel_ms": upd_ms, "algorithmic_bytes_per_launch": ALG_BYTES_PER_UPDATE * upd_avg_per_push,
+                         "split": split},
             "push_kernel_ms": {k: float(np.mean([x[k] for x in kms])) for k in kms[0]},
             "raycast_icp": {"raycast_ms": rc_ms, "icp_ms": icp_ms, "raycast_hits": int(cnt),
                             "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
@@ -331,7 +373,9 @@ def run_cuda(args):
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
             "map_publication": pub,
             "hypothesis_scoring": hyp,
-            "large_grid_sweep": sweep,
+            "raycast_sweep": rc_sweep,
+            "c2_double_laser": c2,
+            "k3_streaming_sweep": sweep,
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall,
         }
@@ -502,15 +546,17 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default=None, help="C3 (default at 1 GPU) or C2; N > 1 always uses C2 robots")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch", action="store_true", help="push the two lasers of a robot one by one (two launch pairs)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 16384^2 push sweep (4.6 GB of HBM, a few seconds)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.workload is None:
+        args.workload = "C3" if int(os.environ.get("WORLD_SIZE", "1")) == 1 and args.gpus <= 1 else "C2"
     if args.impl == "reference":
         run_reference(args)
     else:

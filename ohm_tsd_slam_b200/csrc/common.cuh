@@ -9,6 +9,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/tsdslam_b200.h"
@@ -216,6 +217,10 @@ int fill_scan_dev(const tsd_scan_t* scan, ScanDev* out);  // scalars only (point
 // the grid handle is shared between grid.cu, raycast.cu and match.cu
 struct tsd_grid
 {
+  // One handle may be used from several host threads (the node's mapper pushes while its localisers ray-cast and
+  // its grid thread publishes, ThreadMapping.cpp:46-61, ThreadLocalize.cpp:353, ThreadGrid.cpp:84): every entry point
+  // holds this lock from staging through launch, read-back and synchronisation.  (Recursive: entry points call each other.)
+  std::recursive_mutex* mtx;
   int device;
   cudaStream_t stream;
   int layout_grid;
@@ -259,7 +264,11 @@ struct tsd_grid
   int scan_cap;
   size_t in_bytes, rc_bytes;
   unsigned char* d_in;
-  unsigned char* h_in;   // pinned
+  unsigned char* h_in;   // pinned; = h_in2[in_next ^ 1] after a staging call
+  unsigned char* h_in2[2];  // two pinned blocks take turns, so that staging a scan does not wait for the previous push
+  cudaEvent_t ev_in[2];     // recorded after the H2D copy out of block i
+  bool ev_in_used[2];
+  int in_next;
   unsigned char* d_rc;
   unsigned char* h_rc;   // pinned
   unsigned long long rc_steps_prev[2];
@@ -304,6 +313,10 @@ struct tsd_grid
   cudaEvent_t ev[4];
   cudaEvent_t ev_order;
 };
+
+#define TSD_LOCK(g)                                      \
+  std::unique_lock<std::recursive_mutex> tsd_lock__;     \
+  if(g) tsd_lock__ = std::unique_lock<std::recursive_mutex>(*(g)->mtx)
 
 namespace tsd
 {

@@ -1532,8 +1532,9 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
   if(n <= g->scan_cap) return TSD_OK;
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   cudaFree(g->d_in); cudaFree(g->d_dirs); cudaFree(g->d_rc); cudaFree(g->d_gate);
-  cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc);
-  g->d_in = g->d_rc = nullptr; g->d_dirs = nullptr; g->d_gate = nullptr; g->h_in = g->h_rc = nullptr;
+  cudaFreeHost(g->h_in2[0]); cudaFreeHost(g->h_in2[1]); cudaFreeHost(g->h_rc);
+  g->d_in = g->d_rc = nullptr; g->d_dirs = nullptr; g->d_gate = nullptr; g->h_in = g->h_in2[0] = g->h_in2[1] = g->h_rc = nullptr;
+  g->ev_in_used[0] = g->ev_in_used[1] = false;
   g->scan_cap = 0;
   const int cap = ((n + 63) / 64) * 64 + 64;
   g->in_bytes = PUSH_MAX_SCANS * (sizeof(double) * cap + cap) + sizeof(double) * 2 * cap;
@@ -1542,7 +1543,13 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
   TSD_CUDA(cudaMalloc(&g->d_rc, g->rc_bytes));
   TSD_CUDA(cudaMalloc(&g->d_dirs, sizeof(double2) * (cap + 1)));
   TSD_CUDA(cudaMalloc(&g->d_gate, sizeof(float2) * (size_t)cap * PUSH_MAX_SCANS));
-  TSD_CUDA(cudaMallocHost(&g->h_in, g->in_bytes));
+  for(int i = 0; i < 2; i++)
+  {
+    TSD_CUDA(cudaMallocHost(&g->h_in2[i], g->in_bytes));
+    if(!g->ev_in[i]) TSD_CUDA(cudaEventCreateWithFlags(&g->ev_in[i], cudaEventDisableTiming));
+  }
+  g->h_in = g->h_in2[0];
+  g->in_next = 0;
   TSD_CUDA(cudaMallocHost(&g->h_rc, g->rc_bytes));
   TSD_CUDA(cudaMemsetAsync(g->d_rc, 0, g->rc_bytes, g->stream));
   memset(g->h_rc, 0, g->rc_bytes);
@@ -1585,8 +1592,15 @@ int grid_stage_scans(tsd_grid* g, const tsd_scan_t* scans, int n, ScanDev* sd, c
   if(n == 3) { set_error("a launch takes 1, 2 or 4 scans"); return TSD_E_INVALID; }
   int rc = ensure_scan_capacity(g, scan->n);
   if(rc) return rc;
-  // the previous call's async copy out of the pinned staging block must have drained
-  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  // Two pinned blocks take turns: only the copy out of THIS block (two staging calls ago) must have drained, not the
+  // kernels of the previous push -- tsdg_push_async returns while the previous push is still running.
+  const int blk = g->in_next;
+  g->in_next ^= 1;
+  if(g->ev_in_used[blk]) TSD_CUDA(cudaEventSynchronize(g->ev_in[blk]));
+  g->h_in = g->h_in2[blk];
+  g->h_ranges = reinterpret_cast<double*>(g->h_in);
+  g->h_mask = g->h_in + sizeof(double) * g->scan_cap;
+  g->h_rays = reinterpret_cast<double*>(g->h_in + sizeof(double) * g->scan_cap + g->scan_cap);
   const size_t slotBytes = sizeof(double) * g->scan_cap + g->scan_cap;
   const size_t raysBytes = sizeof(double) * 2 * g->scan_cap;
   size_t bytes = 0;
@@ -1607,6 +1621,8 @@ int grid_stage_scans(tsd_grid* g, const tsd_scan_t* scans, int n, ScanDev* sd, c
     bytes = bytes > withRays ? bytes : withRays;
   }
   TSD_CUDA(cudaMemcpyAsync(g->d_in, g->h_in, bytes, cudaMemcpyHostToDevice, g->stream));
+  TSD_CUDA(cudaEventRecord(g->ev_in[blk], g->stream));
+  g->ev_in_used[blk] = true;
   if(g->dirs_n != scan->n || g->dirs_phi_min != scan->phi_min || g->dirs_res != scan->angular_res)
   {
     // directions of the half-beam boundaries B_k = phiMin + (k - 1/2) res, k = 0..n (beam_index.cuh)
@@ -1720,6 +1736,7 @@ int tsdg_create_band(double cell_size, int layout_partition, int layout_grid, in
   TSD_CUDA(cudaSetDevice(device));
   tsd_grid* g = new tsd_grid();
   memset(g, 0, sizeof(*g));
+  g->mtx = new std::recursive_mutex();
   g->device = device;
   g->layout_grid = layout_grid;
   g->cell_size = cell_size;
@@ -1810,18 +1827,21 @@ int tsdg_destroy(tsd_grid_t* g)
   cudaFree(g->d_pending); cudaFree(g->d_counters);
   cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_col4); cudaFree(g->d_row4); cudaFree(g->d_scans); cudaFree(g->d_prof); cudaFree(g->d_gate); cudaFree(g->d_kinds); cudaFree(g->d_dirs); cudaFree(g->d_in);
   cudaFree(g->d_rc); cudaFree(g->d_scratch);
-  cudaFreeHost(g->h_in); cudaFreeHost(g->h_rc); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters);
+  cudaFreeHost(g->h_in2[0]); cudaFreeHost(g->h_in2[1]); cudaFreeHost(g->h_rc); cudaFreeHost(g->h_scratch); cudaFreeHost(g->h_counters);
+  for(int i = 0; i < 2; i++) if(g->ev_in[i]) cudaEventDestroy(g->ev_in[i]);
   cudaFreeHost(g->h_stats64);
   for(int i = 0; i < 4; i++) if(g->ev[i]) cudaEventDestroy(g->ev[i]);
   if(g->ev_order) cudaEventDestroy(g->ev_order);
   if(g->stream) cudaStreamDestroy(g->stream);
   cudaGetLastError();
+  delete g->mtx;
   delete g;
   return TSD_OK;
 }
 
 int tsdg_set_max_truncation(tsd_grid_t* g, double val)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   if(val < 2 * g->cell_size) val = 2 * g->cell_size;  // TsdGrid.cpp:208-212
   g->max_truncation = val;
@@ -1832,6 +1852,7 @@ int tsdg_get_geometry(const tsd_grid_t* g, int32_t* cells_x, int32_t* cells_y, i
                       double* cell_size, double* min_x, double* max_x, double* min_y, double* max_y,
                       double* max_truncation)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   if(cells_x) *cells_x = g->cells_x;
   if(cells_y) *cells_y = g->cells_y;
@@ -1847,6 +1868,7 @@ int tsdg_get_geometry(const tsd_grid_t* g, int32_t* cells_x, int32_t* cells_y, i
 
 int tsdg_free_footprint(tsd_grid_t* g, double cx, double cy, double width, double height)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   // TsdGrid.cpp:611-622
@@ -1902,6 +1924,7 @@ int tsdg_stage_scan(tsd_grid_t* g, const tsd_scan_t* scan) { return tsdg_stage_b
 
 int tsdg_stage_batch(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   int rc = grid_stage_scans(g, scans, n, g->staged, nullptr);
@@ -1913,6 +1936,7 @@ int tsdg_stage_batch(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
 
 int tsdg_push_staged(tsd_grid_t* g)
 {
+  TSD_LOCK(g);
   if(!g || !g->has_staged) { set_error("no staged scan"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));
   PushParams pp = make_params(g);
@@ -2016,6 +2040,7 @@ static int push_finish(tsd_grid* g, const PushParams& pp)
 
 int tsdg_push_async(tsd_grid_t* g, const tsd_scan_t* scan)
 {
+  TSD_LOCK(g);
   int rc = tsdg_stage_scan(g, scan);
   if(rc) return rc;
   return tsdg_push_staged(g);
@@ -2026,6 +2051,7 @@ int tsdg_push_async(tsd_grid_t* g, const tsd_scan_t* scan)
 // one classify + one update launch: partitions both scans touch are read and written once.
 int tsdg_push_batch_async(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
 {
+  TSD_LOCK(g);
   if(!g || !scans || n < 1) return TSD_E_INVALID;
   int i = 0;
   while(i < n)
@@ -2048,6 +2074,7 @@ int tsdg_push_batch_async(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
 
 int tsdg_push_batch(tsd_grid_t* g, const tsd_scan_t* scans, int32_t n)
 {
+  TSD_LOCK(g);
   int rc = tsdg_push_batch_async(g, scans, n);
   if(rc) return rc;
   // statistics of the LAST launch of the batch (both scans of a pair together) come back with the synchronisation
@@ -2064,6 +2091,7 @@ void* tsdg_stream(tsd_grid_t* g) { return g ? (void*)g->stream : nullptr; }
 // direction 1 makes the handle's stream wait for everything queued on `other`.
 int tsdg_stream_order(tsd_grid_t* g, void* other, int direction)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   if(!g->ev_order) TSD_CUDA(cudaEventCreateWithFlags(&g->ev_order, cudaEventDisableTiming));
@@ -2083,6 +2111,7 @@ int tsdg_stream_order(tsd_grid_t* g, void* other, int direction)
 
 int tsdg_band_push_finish(tsd_grid_t* g)
 {
+  TSD_LOCK(g);
   if(!g || !g->band) { set_error("not a sharded grid"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));
   PushParams pp = make_params(g);
@@ -2105,6 +2134,7 @@ static_assert(sizeof(BandExport) <= TSD_BAND_EXPORT_BYTES, "tsd_band_export_t to
 
 int tsdg_band_export(tsd_grid_t* g, void* blob)
 {
+  TSD_LOCK(g);
   if(!g || !blob || !g->band) { set_error("not a sharded grid"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));
   BandExport e;
@@ -2131,6 +2161,7 @@ static int check_neighbour(const tsd_grid* g, int side, int nb_row_begin, int nb
 
 int tsdg_band_connect(tsd_grid_t* g, int side, const void* blob)
 {
+  TSD_LOCK(g);
   if(!g || !blob || !g->band || side < 0 || side > 1) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   BandExport e;
@@ -2154,6 +2185,7 @@ int tsdg_band_connect(tsd_grid_t* g, int side, const void* blob)
 
 int tsdg_band_connect_local(tsd_grid_t* g, int side, tsd_grid_t* nb)
 {
+  TSD_LOCK(g);
   if(!g || !nb || !g->band || !nb->band || side < 0 || side > 1) return TSD_E_INVALID;
   int rc = check_neighbour(g, side, nb->row_begin, nb->row_end, nb->parts_x);
   if(rc) return rc;
@@ -2180,6 +2212,7 @@ int tsdg_band_connect_local(tsd_grid_t* g, int side, tsd_grid_t* nb)
 
 int tsdg_band_halo_sync(tsd_grid_t* g, int lo_px0, int lo_px1, int hi_px0, int hi_px1)
 {
+  TSD_LOCK(g);
   if(!g || !g->band) { set_error("not a sharded grid"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));
   HaloParams hp;
@@ -2221,6 +2254,7 @@ int tsdg_band_halo_sync(tsd_grid_t* g, int lo_px0, int lo_px1, int hi_px0, int h
 
 int tsdg_band_flags(tsd_grid_t* g, uint8_t** flags, uint64_t* count)
 {
+  TSD_LOCK(g);
   if(!g || !flags || !count) return TSD_E_INVALID;
   *flags = g->d_flags;
   *count = (uint64_t)g->n_parts;
@@ -2229,6 +2263,7 @@ int tsdg_band_flags(tsd_grid_t* g, uint8_t** flags, uint64_t* count)
 
 int tsdg_scan_box(const tsd_grid_t* g, const tsd_scan_t* scan, int32_t box[4])
 {
+  TSD_LOCK(g);
   if(!g || !scan || !box) return TSD_E_INVALID;
   int b[4];
   scan_partition_box(g, scan->pose[2], scan->pose[5], scan->max_range, b);
@@ -2241,6 +2276,7 @@ int tsdg_scan_box(const tsd_grid_t* g, const tsd_scan_t* scan, int32_t box[4])
 //        3 = halo slot above my band (filled from the upper neighbour's lowest row).
 int tsdg_band_row(tsd_grid_t* g, int which, double** tsd, double** weight, uint64_t* count)
 {
+  TSD_LOCK(g);
   if(!g || !tsd || !weight || !count || which < 0 || which > 3) return TSD_E_INVALID;
   int row;
   if(which == 0) row = g->row_begin;
@@ -2261,6 +2297,7 @@ int tsdg_band_row(tsd_grid_t* g, int which, double** tsd, double** weight, uint6
 // stage, fetching work, items}, consumer warp 0 {total, waiting for data after the first item, until the first item, SM}
 int tsdg_debug_profile(tsd_grid_t* g, unsigned long long* out, int max_ctas)
 {
+  TSD_LOCK(g);
   if(!g || !out) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   if(!g->d_prof) return TSD_E_INVALID;
@@ -2273,6 +2310,7 @@ int tsdg_debug_profile(tsd_grid_t* g, unsigned long long* out, int max_ctas)
 
 int tsdg_set_update_filter(tsd_grid_t* g, unsigned mask)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   g->update_filter = mask & 3u;
   return TSD_OK;
@@ -2280,6 +2318,7 @@ int tsdg_set_update_filter(tsd_grid_t* g, unsigned mask)
 
 int tsdg_set_timing(tsd_grid_t* g, int enable)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   if(enable && !g->ev[0])
@@ -2290,6 +2329,7 @@ int tsdg_set_timing(tsd_grid_t* g, int enable)
 
 int tsdg_last_push_kernel_ms(tsd_grid_t* g, float ms[4])
 {
+  TSD_LOCK(g);
   if(!g || !ms || !g->timing || !g->pushed_once) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
@@ -2302,6 +2342,7 @@ int tsdg_last_push_kernel_ms(tsd_grid_t* g, float ms[4])
 
 int tsdg_sync(tsd_grid_t* g)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
@@ -2310,6 +2351,7 @@ int tsdg_sync(tsd_grid_t* g)
 
 int tsdg_push(tsd_grid_t* g, const tsd_scan_t* scan)
 {
+  TSD_LOCK(g);
   int rc = tsdg_push_async(g, scan);
   if(rc) return rc;
   // the blocking call brings the push statistics back with its one synchronisation
@@ -2321,6 +2363,7 @@ int tsdg_push(tsd_grid_t* g, const tsd_scan_t* scan)
 
 int tsdg_last_push_stats(tsd_grid_t* g, tsd_push_stats_t* out)
 {
+  TSD_LOCK(g);
   if(!g || !out) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   if(!g->stats_fresh)
@@ -2339,6 +2382,7 @@ int tsdg_last_push_stats(tsd_grid_t* g, tsd_push_stats_t* out)
 
 int tsdg_interpolate_bilinear(tsd_grid_t* g, int32_t n, const double* xy, double* tsd, int32_t* status)
 {
+  TSD_LOCK(g);
   if(!g || n < 0 || (n > 0 && (!xy || !tsd || !status))) return TSD_E_INVALID;
   if(n == 0) return TSD_OK;
   TSD_CUDA(cudaSetDevice(g->device));
@@ -2363,6 +2407,7 @@ int tsdg_interpolate_bilinear(tsd_grid_t* g, int32_t n, const double* xy, double
 
 int tsdg_interpolate_normal(tsd_grid_t* g, int32_t n, const double* xy, double* normals, int32_t* ok)
 {
+  TSD_LOCK(g);
   if(!g || n < 0 || (n > 0 && (!xy || !normals || !ok))) return TSD_E_INVALID;
   if(n == 0) return TSD_OK;
   TSD_CUDA(cudaSetDevice(g->device));
@@ -2387,6 +2432,7 @@ int tsdg_interpolate_normal(tsd_grid_t* g, int32_t n, const double* xy, double* 
 
 int tsdg_num_partitions(const tsd_grid_t* g, int32_t* n)
 {
+  TSD_LOCK(g);
   if(!g || !n) return TSD_E_INVALID;
   *n = g->n_parts;
   return TSD_OK;
@@ -2394,6 +2440,7 @@ int tsdg_num_partitions(const tsd_grid_t* g, int32_t* n)
 
 int tsdg_partition_states(tsd_grid_t* g, int32_t* state, double* init_weight)
 {
+  TSD_LOCK(g);
   if(!g || !state) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
@@ -2435,6 +2482,7 @@ static void tile_from_33(const double* in33, double* tile)
 
 int tsdg_download_partition(tsd_grid_t* g, int32_t p, double* tsd, double* weight)
 {
+  TSD_LOCK(g);
   if(!g || p < 0 || p >= g->n_parts || !tsd || !weight) return TSD_E_INVALID;
   const int py = p / g->parts_x;
   if(py < g->row_begin || py >= g->row_end) { set_error("partition %d is not owned by this band", p); return TSD_E_INVALID; }
@@ -2454,6 +2502,7 @@ int tsdg_download_partition(tsd_grid_t* g, int32_t p, double* tsd, double* weigh
 
 int tsdg_upload_partition(tsd_grid_t* g, int32_t p, const double* tsd, const double* weight)
 {
+  TSD_LOCK(g);
   if(!g || p < 0 || p >= g->n_parts || !tsd || !weight) return TSD_E_INVALID;
   const int py = p / g->parts_x;
   if(py < g->row_begin || py >= g->row_end) { set_error("partition %d is not owned by this band", p); return TSD_E_INVALID; }
@@ -2475,6 +2524,7 @@ int tsdg_upload_partition(tsd_grid_t* g, int32_t p, const double* tsd, const dou
 
 int tsdg_fill(tsd_grid_t* g, double tsd, double weight, int only_uninitialized)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   PushParams pp = make_params(g);

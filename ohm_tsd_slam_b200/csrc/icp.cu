@@ -68,6 +68,7 @@ struct IcpParams
 
 struct tsd_icp
 {
+  std::recursive_mutex* mtx;  // one registration at a time per handle (each localiser thread owns one in the node)
   int device;
   cudaStream_t stream;
   IcpParams p;
@@ -669,6 +670,7 @@ int icp_create(uint32_t max_iterations, double dist_max, double dist_min, uint32
   TSD_CUDA(cudaSetDevice(device));
   tsd_icp* h = new tsd_icp();
   memset(h, 0, sizeof(*h));
+  h->mtx = new std::recursive_mutex();
   h->device = device;
   IcpParams& p = h->p;
   p.max_iterations = (int)max_iterations;  // ThreadLocalize.cpp:224
@@ -721,6 +723,7 @@ int icp_destroy(tsd_icp_t* h)
   cudaFreeHost(h->h_stage); cudaFreeHost(h->h_result);
   if(h->stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
+  delete h->mtx;
   delete h;
   return TSD_OK;
 }
@@ -729,6 +732,7 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
             int32_t n_scene, const double pose[9], const double* t_init, double t_out[9], double* mse,
             uint32_t* pairs, uint32_t* iterations, int32_t* state)
 {
+  TSD_LOCK(h);
   (void)normals;  // ClosedFormEstimator2D ignores normals (ClosedFormEstimator2D.cpp:26-34)
   if(!h || !pose || !t_out || !mse || !pairs || !iterations || !state) return TSD_E_INVALID;
   for(int i = 0; i < 9; i++) t_out[i] = (i % 4 == 0) ? 1.0 : 0.0;
@@ -781,6 +785,7 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
 
 int icp_set_termination(tsd_icp_t* h, double max_rms, uint32_t convergence_counter)
 {
+  TSD_LOCK(h);
   if(!h) return TSD_E_INVALID;
   h->p.max_rms = max_rms;
   h->p.conv_cnt = convergence_counter;
@@ -789,6 +794,7 @@ int icp_set_termination(tsd_icp_t* h, double max_rms, uint32_t convergence_count
 
 int icp_set_max_iterations(tsd_icp_t* h, uint32_t max_iterations)
 {
+  TSD_LOCK(h);
   if(!h || max_iterations > (uint32_t)h->trace_cap_it) { set_error("icp_set_max_iterations: beyond the capacity given to icp_create"); return TSD_E_INVALID; }
   h->p.max_iterations = (int)max_iterations;
   return TSD_OK;
@@ -796,6 +802,7 @@ int icp_set_max_iterations(tsd_icp_t* h, uint32_t max_iterations)
 
 int icp_set_trace(tsd_icp_t* h, int enable)
 {
+  TSD_LOCK(h);
   if(!h) return TSD_E_INVALID;
   h->trace = enable != 0;
   return TSD_OK;
@@ -804,6 +811,7 @@ int icp_set_trace(tsd_icp_t* h, int enable)
 int icp_get_trace(tsd_icp_t* h, int32_t max_it, int32_t cap, uint32_t* pair_model, uint32_t* pair_scene,
                   int32_t* pair_count, double* mse, double* t_final16, int32_t* n_it)
 {
+  TSD_LOCK(h);
   if(!h || !pair_model || !pair_scene || !pair_count || !mse || !t_final16 || !n_it) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(h->device));
   TSD_CUDA(cudaStreamSynchronize(h->stream));

@@ -18,6 +18,7 @@ using namespace tsd;
 
 struct tsd_matcher
 {
+  std::recursive_mutex* mtx;
   int device;
   cudaStream_t stream;
   size_t cap;
@@ -424,6 +425,7 @@ int match_create(int device, tsd_matcher_t** out)
   TSD_CUDA(cudaSetDevice(device));
   tsd_matcher* m = new tsd_matcher();
   memset(m, 0, sizeof(*m));
+  m->mtx = new std::recursive_mutex();
   m->device = device;
   TSD_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   *out = m;
@@ -439,6 +441,7 @@ int match_destroy(tsd_matcher_t* m)
   cudaFreeHost(m->h_buf);
   if(m->stream) cudaStreamDestroy(m->stream);
   cudaGetLastError();
+  delete m->mtx;
   delete m;
   return TSD_OK;
 }
@@ -448,6 +451,9 @@ int match_score_tsd(tsd_matcher_t* m, tsd_grid_t* grid, int32_t n_hyp, const tsd
                     double phi_max, int32_t n_control, const double* control, const double t_sensor[9],
                     double zrand, double* score, int32_t* best, double t_best[9])
 {
+  TSD_LOCK(m);
+  std::unique_lock<std::recursive_mutex> grid_lock__;
+  if(grid) grid_lock__ = std::unique_lock<std::recursive_mutex>(*grid->mtx);
   if(!m || !grid || n_hyp < 0 || n <= 0 || !hyps || !model || !scene || !phi_m || !phi_s || n_control < 0 ||
      (n_control > 0 && !control) || !t_sensor || !best || !t_best)
     return TSD_E_INVALID;
@@ -504,6 +510,7 @@ int match_score_rnm(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
                     double scale_distance, double scale_orientation, uint32_t cnt_match_thresh, int32_t* cnt_match,
                     int32_t* max_cnt_match, double* err_sum, int32_t* best, double t_best[9])
 {
+  TSD_LOCK(m);
   if(!m || n_hyp < 0 || n <= 0 || !hyps || !model || !scene || !phi_m || !phi_s || n_control < 0 ||
      (n_control > 0 && (!control || !phi_control)) || n_valid < 0 || (n_valid > 0 && (!model_valid || !phi_valid)) ||
      !best || !t_best)
@@ -590,6 +597,7 @@ int match_score_pdf(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
                     const double* model_dists, const double params[12], double* prob, int32_t* fov_count,
                     int32_t* best, double t_best[9])
 {
+  TSD_LOCK(m);
   if(!m || n_hyp < 0 || n <= 0 || !hyps || !model || !scene || !phi_m || !phi_s || n_control < 0 ||
      (n_control > 0 && !control) || n_valid <= 0 || !model_angles || !model_dists || !params || !best || !t_best)
     return TSD_E_INVALID;

@@ -216,6 +216,7 @@ extern "C" {
 int tsdg_axis_aligned_map(tsd_grid_t* g, double* coords, uint32_t cap_points, double* normals, uint32_t* count,
                           int8_t* occupied)
 {
+  TSD_LOCK(g);
   if(!g || !count || (cap_points > 0 && !coords)) return TSD_E_INVALID;
   if(g->band) { set_error("map publication works on an unsharded grid"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));
@@ -301,6 +302,7 @@ int tsdg_axis_aligned_map(tsd_grid_t* g, double* coords, uint32_t cap_points, do
 
 int tsdg_color_image(tsd_grid_t* g, uint8_t* image, uint32_t width, uint32_t height)
 {
+  TSD_LOCK(g);
   if(!g || !image || width == 0 || height == 0) return TSD_E_INVALID;
   if(g->band) { set_error("map publication works on an unsharded grid"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));

@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
 
 static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, bool download = true)
 {
+  TSD_LOCK(g);
   if(!g || !scan || !rays_world) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   RayParams rp;
@@ -279,6 +280,7 @@ extern "C" {
 int tsdg_raycast_mask(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, double* coords,
                       double* normals, uint8_t* mask, uint32_t* count)
 {
+  TSD_LOCK(g);
   if(!coords || !normals || !mask) return TSD_E_INVALID;
   int rc = raycast_launch(g, scan, rays_world);
   if(rc) return rc;
@@ -304,6 +306,7 @@ int tsdg_raycast_mask(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_
 int tsdg_raycast(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, double* coords, double* normals,
                  uint32_t* count)
 {
+  TSD_LOCK(g);
   if(!coords || !normals || !count) return TSD_E_INVALID;
   int rc = raycast_launch(g, scan, rays_world);
   if(rc) return rc;
@@ -325,6 +328,7 @@ int tsdg_raycast(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world
 
 int tsdg_last_raycast_steps(tsd_grid_t* g, uint64_t* fine_steps, uint64_t* coarse_steps)
 {
+  TSD_LOCK(g);
   if(!g) return TSD_E_INVALID;
   if(!g->h_rc_steps) return TSD_E_INVALID;
   if(fine_steps) *fine_steps = g->h_rc_steps[0] - g->rc_steps_prev[0];
@@ -335,6 +339,7 @@ int tsdg_last_raycast_steps(tsd_grid_t* g, uint64_t* fine_steps, uint64_t* coars
 int tsdg_raycast_band_keys(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, uint64_t** dev_keys,
                            double** dev_payload)
 {
+  TSD_LOCK(g);
   if(!dev_keys || !dev_payload) return TSD_E_INVALID;
   int rc = raycast_launch(g, scan, rays_world, false);
   if(rc) return rc;

@@ -40,6 +40,7 @@ extern "C" {
 
 int tsdg_store(tsd_grid_t* g, const char* path)
 {
+  TSD_LOCK(g);
   if(!g || !path || !path[0]) { set_error("tsdg_store: invalid path"); return TSD_E_INVALID; }
   if(g->band) { set_error("tsdg_store works on an unsharded grid"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));

@@ -75,3 +75,31 @@ def test_slam_loop_with_tsd_matcher():
     a = run("tiny", 0)[:-1]
     b = run("tiny", 3)[:-1]
     assert a.shape == b.shape and np.max(np.abs(a[:, 1:3] - b[:, 1:3])) < 0.05 and np.max(np.abs(a[:, 3] - b[:, 3])) < 0.02
+
+
+THREADS_EXE = os.path.join(ROOT, "tests", "cpp", "threads_b200")
+
+
+def build_threads_exe():
+    _build.build()
+    src = os.path.join(ROOT, "tests", "cpp", "threads.cpp")
+    if os.path.exists(THREADS_EXE) and os.path.getmtime(THREADS_EXE) > max(os.path.getmtime(src), os.path.getmtime(_build.LIB)):
+        return THREADS_EXE
+    libdir = os.path.join(ROOT, "ohm_tsd_slam_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-pthread", src, "-o", THREADS_EXE, "-L" + libdir,
+                    "-ltsdslam_b200", "-Wl,-rpath," + libdir], check=True)
+    return THREADS_EXE
+
+
+def test_thread_test_compiles():
+    assert os.path.exists(build_threads_exe())
+
+
+@pytest.mark.gpu
+def test_one_handle_from_three_threads_equals_the_serial_run():
+    """The node's threading (1 mapper + 2 localisers on one TsdGrid, no lock in the reference: ThreadMapping.cpp:46-61,
+    SlamNode.cpp:104-121) against the C ABI: 500 iterations of push / push_async on one thread and ray casts + samples
+    on two more, results and final map bit-identical to the single-threaded run (tests/cpp/threads.cpp)."""
+    out = subprocess.run([build_threads_exe(), "500"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "identical to the single-threaded run" in out.stdout
