@@ -137,6 +137,7 @@ def stall_table(rep, kernel, out, top=14):
 
 def main():
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[2] if len(sys.argv) > 2 else ""
     go = os.path.join(ROOT, "gpurun_out")
     import glob
     launches = os.path.join(go, f"{rnd}_launches.csv")
@@ -145,7 +146,7 @@ def main():
     if os.path.exists(launches):
         shutil.copy(launches, os.path.join(ROOT, "profiles", f"{rnd}_launches.csv"))
         out.append("## Launch list\n")
-        out.append("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sweep`"
+        out.append("`ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sweep`"
                    " (the whole bench: map build, pushes, ray casts, ICP, map publication, 10^5-hypothesis scoring)."
                    " Per-launch times are cold-cache and serialised: compare shares, not absolutes. Full list: `" + f"{rnd}_launches.csv`.\n")
         launch_table(launches, out)
@@ -154,9 +155,11 @@ def main():
         out.append(f"\n## ncu --set full, {os.path.basename(rep)} (per launch, mean over the captured launches)\n")
         m = raw_tables(rep, out)
         for k in m:
-            if k.split("<")[0] in ("k_update", "k_raycast", "k_icp", "k_classify"):
+            if k.split("<")[0] in ("k_update", "k_raycast", "k_icp", "k_classify", "k_score_tsd", "k_score_rnm", "k_score_pdf"):
                 stall_table(rep, k.split("<")[0], out)
         metrics.update({k.split("<")[0]: v for k, v in m.items()})
+        if tag:  # the workload the captured bench ran (bench.py's roofline.traffic looks up "k_update@<workload>")
+            metrics.update({k.split("<")[0] + "@" + tag: v for k, v in m.items()})
     if metrics:
         json.dump(metrics, open(os.path.join(ROOT, "profiles", f"{rnd}_metrics.json"), "w"), indent=1)
     extra = os.path.join(ROOT, "profiles", f"{rnd}_notes.md")
