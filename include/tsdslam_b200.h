@@ -232,6 +232,20 @@ int tsdg_raycast_band_keys(tsd_grid_t* grid, const tsd_scan_t* scan, const doubl
 int tsdg_last_raycast_steps(tsd_grid_t* grid, uint64_t* fine_steps, uint64_t* coarse_steps);
 
 /* ------------------------------------------------------------------------------------------------
+ * Scan pre-processing on the device (what ThreadLocalize does to a LaserScan before the hot path starts):
+ *   Sensor::setRealMeasurementData(vector<float>, scale)  (reconstruct/Sensor.cpp:136-145): data[i] = (double)(ranges[i] * scale)
+ *   SensorPolar2D::setStandardMask (reconstruct/grid/SensorPolar2D.cpp:59-98; Sensor.cpp:246-272): zero depth, ranges beyond
+ *       max_range -> inf, NaN -> inf + masked, depth discontinuities of less than 3 degrees masked
+ *   Sensor::dataToCartesianVectorMask (Sensor.cpp:168-190): scene[i] = rays_local[:, i] * data[i] where valid (n x 2)
+ *   ThreadLocalize::maskMatrix (src/ThreadLocalize.cpp:738-755): the valid scene points compacted, beam order (n_valid x 2)
+ * rays_local: 2 x n row-major, SensorPolar2D::_raysLocal.  scene / scene_mask / scene_valid / n_valid may be NULL.  The
+ * grid handle supplies device, stream and staging memory; the map is not touched.
+ * ---------------------------------------------------------------------------------------------- */
+int tsds_prepare_scan(tsd_grid_t* grid, int32_t n, const float* ranges, float scale, double max_range, double angular_res,
+                      const double* rays_local, double* data, uint8_t* mask, double* scene, uint8_t* scene_mask,
+                      double* scene_valid, uint32_t* n_valid);
+
+/* ------------------------------------------------------------------------------------------------
  * Map publication (ThreadGrid.cpp:84,125), on the device: the map never travels to the host.
  * ------------------------------------------------------------------------------------------------ */
 /* RayCastAxisAligned2D::calcCoords (RayCastAxisAligned2D.cpp:13-105): zero crossings of the TSD along the cell rows

@@ -75,7 +75,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             # the image exports CXX=/opt/gcc/bin/g++ whose wrapper cannot find libgomp; nvcc wants the system g++
             env.pop("CXX", None)
             env.pop("CC", None)
-            r = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"], capture_output=True, text=True, env=env)
+            # host compiler: TSD_CCBIN if set, else the system g++ where it exists, else nvcc's own default
+            ccbin = os.environ.get("TSD_CCBIN") or ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None)
+            r = subprocess.run(cmd + (["-ccbin", ccbin] if ccbin else []), capture_output=True, text=True, env=env)
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)
             if r.returncode != 0:

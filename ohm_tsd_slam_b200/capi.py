@@ -31,7 +31,7 @@ EXPORTS = [
     "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_set_update_filter", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
-    "tsdg_axis_aligned_map", "tsdg_color_image", "tsdg_store", "tsdg_load",
+    "tsdg_axis_aligned_map", "tsdg_color_image", "tsdg_store", "tsdg_load", "tsds_prepare_scan",
     "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
@@ -88,6 +88,8 @@ def lib():
     L.tsdg_stream_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.tsdg_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.tsdg_set_update_filter.argtypes = [C.c_void_p, C.c_uint]
+    L.tsds_prepare_scan.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_float, C.c_double, C.c_double, _dp, _dp, _bp, _dp,
+                                    _bp, _dp, _up]
     L.tsdg_last_push_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.tsdg_last_push_stats.argtypes = [C.c_void_p, C.POINTER(PushStats)]
     L.tsdg_interpolate_bilinear.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
@@ -273,6 +275,23 @@ class Grid:
 
     def set_timing(self, enable: bool = True):
         check(lib().tsdg_set_timing(self.h, 1 if enable else 0))
+
+    def prepare_scan(self, ranges_f32, spec, rays_local, scale: float = 1.0, scene=None):
+        """Scan pre-processing on the device (tsds_prepare_scan): returns data, mask, scene (n x 2), scene mask and
+        the compacted valid scene points."""
+        r = np.ascontiguousarray(ranges_f32, dtype=np.float32)
+        n = len(r)
+        rays = _f64(rays_local)
+        data = np.empty(n)
+        mask = np.empty(n, dtype=np.uint8)
+        scene = np.zeros((n, 2)) if scene is None else scene
+        smask = np.empty(n, dtype=np.uint8)
+        valid = np.empty((n, 2))
+        cnt = C.c_uint32()
+        check(lib().tsds_prepare_scan(self.h, n, r.ctypes.data_as(C.POINTER(C.c_float)), scale, spec.max_range, spec.angular_res,
+                                      _d(rays), _d(data), mask.ctypes.data_as(_bp), _d(scene), smask.ctypes.data_as(_bp),
+                                      _d(valid), C.byref(cnt)))
+        return data, mask, scene, smask, valid[:cnt.value].copy()
 
     def set_update_filter(self, mask: int):
         """Measurement aid: bit 0 = the update kernel skips K2 (addTsd) work, bit 1 = K3 (increaseEmptiness) work."""

@@ -297,7 +297,7 @@ struct tsd_grid
   tsd::ScanDev staged[4];  // scans staged by tsdg_stage_scan / tsdg_stage_batch (device pointers + scalars)
   int staged_n;
   // halo synchronisation over peer memory (bands only): [0] = the band below, [1] = the band above
-  uint32_t* d_signal;        // [0]/[1] data-ready from below/above, [2]/[3] ack from below/above, [4] CTA ticket
+  uint32_t* d_signal;        // [0]/[1] data-ready from below/above, [2]/[3] ack from below/above, [4] CTA ticket, [5] timeout flag
   struct Peer
   {
     bool connected, ipc;
@@ -307,6 +307,7 @@ struct tsd_grid
     int alloc_begin;         // the neighbour's first allocated partition row
   } peer[2];
   uint32_t halo_seq[2];      // synchronisations done per boundary (both sides count alike)
+  bool halo_used;            // k_halo_sync ran: tsdg_sync looks at its timeout flag (d_signal[5])
   bool has_staged;
   unsigned update_filter;  // measurement aid: k_update skips K2 (bit 0) / K3 (bit 1) work (tsdg_set_update_filter)
   bool timing;          // record CUDA events around the push kernels (bench.py's live roofline)

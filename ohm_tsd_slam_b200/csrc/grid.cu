@@ -1281,14 +1281,20 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// sequence numbers wrap: compare as a signed distance
-__device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq)
+// sequence numbers wrap: compare as a signed distance.  A neighbour that never calls (the C ABI asks both sides of a
+// boundary to call equally often) must not hang the GPU, and must not take the CUDA context -- and the map -- down
+// either: after ~10 s the wait gives up and raises an error flag that the host reports (TSD_E_CUDA) at the next
+// synchronisation; the kernel finishes with whatever arrived.
+__device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq, uint32_t* err)
 {
-  // a neighbour that never calls would hang the GPU: give up (and fail loudly) after a few seconds
   for(unsigned spins = 0; (int32_t)(ld_acquire_sys(p) - seq) < 0; spins++)
   {
-    __nanosleep(128);
-    if(spins > (1u << 25)) __trap();
+    __nanosleep(256);
+    if(spins > (1u << 25))
+    {
+      atomicExch(err, 1u);
+      return;
+    }
   }
 }
 
@@ -1298,7 +1304,7 @@ __global__ void __launch_bounds__(256) k_halo_sync(HaloParams hp)
   // A: my signal slots at the neighbour: [1]/[3] at the band below (I am its upper neighbour), [0]/[2] above
   if(blockIdx.x == 0 && t < 2 && hp.active[t]) st_release_sys(hp.peer_sig[t] + (t == 0 ? 3 : 2), hp.seq[t]);
   // B
-  if(t < 2 && hp.active[t]) wait_seq(hp.my_sig + 2 + t, hp.seq[t]);
+  if(t < 2 && hp.active[t]) wait_seq(hp.my_sig + 2 + t, hp.seq[t], hp.my_sig + 5);
   __syncthreads();
   // C: 16-byte stores; a partition is 8832 B = 552 x 16 B, so every column offset is aligned
   for(int b = 0; b < 2; b++)
@@ -1330,7 +1336,7 @@ __global__ void __launch_bounds__(256) k_halo_sync(HaloParams hp)
     }
   }
   // E
-  if(t < 2 && hp.active[t]) wait_seq(hp.my_sig + t, hp.seq[t]);
+  if(t < 2 && hp.active[t]) wait_seq(hp.my_sig + t, hp.seq[t], hp.my_sig + 5);
   __syncthreads();
   // F
   const int warp = (blockIdx.x * blockDim.x + t) >> 5;
@@ -2249,6 +2255,7 @@ int tsdg_band_halo_sync(tsd_grid_t* g, int lo_px0, int lo_px1, int hi_px0, int h
   if(ctas < 1) ctas = 1;
   k_halo_sync<<<ctas, 256, 0, g->stream>>>(hp);
   TSD_LAUNCHED();
+  g->halo_used = true;
   return TSD_OK;
 }
 
@@ -2346,6 +2353,20 @@ int tsdg_sync(tsd_grid_t* g)
   if(!g) return TSD_E_INVALID;
   TSD_CUDA(cudaSetDevice(g->device));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
+  if(g->band && g->halo_used)
+  {
+    // a halo synchronisation whose neighbour never showed up leaves a flag instead of trapping (k_halo_sync)
+    uint32_t err = 0;
+    TSD_CUDA(cudaMemcpy(&err, g->d_signal + 5, sizeof(err), cudaMemcpyDeviceToHost));
+    if(err)
+    {
+      const uint32_t zero = 0;
+      cudaMemcpy(g->d_signal + 5, &zero, sizeof(zero), cudaMemcpyHostToDevice);
+      set_error("halo synchronisation timed out: a neighbouring band did not take part (both sides of a boundary must call "
+                "tsdg_band_halo_sync equally often)");
+      return TSD_E_CUDA;
+    }
+  }
   return TSD_OK;
 }
 

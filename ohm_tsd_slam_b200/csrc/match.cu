@@ -144,6 +144,25 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
     s_my[i] = rp.model_valid[2 * i + 1];
     s_mphi[i] = rp.phi_valid[i];
   }
+  // Exact nearest neighbour without looking at every model point: the valid model points come in beam order, i.e.
+  // along the scan contour, so 32 consecutive points are a compact group.  Every group gets a bounding box; a query
+  // scans a group only if the box could hold a point at least as near as the best one found so far.  Lanes of a warp
+  // hold consecutive control points (also along a contour), so they mostly want the same few groups and the warp
+  // stays coherent.  Distances are formed exactly as in the brute-force scan, ties go to the lowest index: the
+  // result is the brute-force result (the FLANN stand-in's rule), at ~1/7 of the distance evaluations.
+  const int nGroups = (rp.n_valid + 31) >> 5;
+  double* s_box = s_mphi + rp.n_valid;  // 4 per group: x0 x1 y0 y1
+  __syncthreads();
+  for(int g = threadIdx.x; g < nGroups; g += blockDim.x)
+  {
+    double x0 = s_mx[32 * g], x1 = x0, y0 = s_my[32 * g], y1 = y0;
+    for(int k = 32 * g + 1; k < min(32 * g + 32, rp.n_valid); k++)
+    {
+      x0 = fmin(x0, s_mx[k]); x1 = fmax(x1, s_mx[k]);
+      y0 = fmin(y0, s_my[k]); y1 = fmax(y1, s_my[k]);
+    }
+    s_box[4 * g] = x0; s_box[4 * g + 1] = x1; s_box[4 * g + 2] = y0; s_box[4 * g + 3] = y1;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warpsTotal = gridDim.x * MATCH_WARPS;
@@ -155,7 +174,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
       if(lane == 0) { rp.cnt_match[h] = -1; rp.max_cnt_match[h] = 0; rp.err_sum[h] = 0.0; }
       continue;
     }
-    int maxCnt = 0, cnt = 0;
+    int maxCnt = 0, cnt = 0, prevBest = -1;
     double errSum = 0.0;
     for(int s = lane; s < hc.n_control; s += 32)
     {
@@ -167,15 +186,32 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
       // exact 1-NN among the valid model points ((0 + dx*dx) + dy*dy, lowest index on ties)
       int bi = -1;
       double bd = __longlong_as_double(0x7ff0000000000000LL);
-      for(int k = 0; k < rp.n_valid; k++)
+      auto scan_group = [&](int g)
       {
-        const double d0 = x - s_mx[k];
-        const double d1 = y - s_my[k];
-        double d = 0.0;
-        d += d0 * d0;
-        d += d1 * d1;
-        if(d < bd) { bd = d; bi = k; }
+        const int k1 = min(32 * g + 32, rp.n_valid);
+        for(int k = 32 * g; k < k1; k++)
+        {
+          const double d0 = x - s_mx[k];
+          const double d1 = y - s_my[k];
+          double d = 0.0;
+          d += d0 * d0;
+          d += d1 * d1;
+          if(d < bd || (d == bd && k < bi)) { bd = d; bi = k; }
+        }
+      };
+      // seed with the group the previous control point of this lane ended in (usually the right one already)
+      const int seed = (prevBest >= 0) ? (prevBest >> 5) : -1;
+      if(seed >= 0) scan_group(seed);
+      for(int g = 0; g < nGroups; g++)
+      {
+        if(g == seed) continue;
+        const double ex = fmax(fmax(s_box[4 * g] - x, x - s_box[4 * g + 1]), 0.0);
+        const double ey = fmax(fmax(s_box[4 * g + 2] - y, y - s_box[4 * g + 3]), 0.0);
+        // lower bound of the squared distance to anything in the box, shaved by more than its rounding error
+        const double lb = (ex * ex + ey * ey) * (1.0 - 1e-12);
+        if(lb <= bd) scan_group(g);
       }
+      prevBest = bi;
       if(bi < 0) continue;
       const double normalConsensus = (1.0 - cos(s_mphi[bi] - s_phic[s] - phi)) / 2.0;
       const double err = bd * rp.scale_distance + normalConsensus * rp.scale_orientation;
@@ -553,7 +589,7 @@ int match_score_rnm(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
   rp.max_cnt_match = a.put<int>(nullptr, n_hyp, &h_max);
   rp.err_sum = a.put<double>(nullptr, n_hyp, &h_err);
   TSD_CUDA(cudaMemcpyAsync(m->d_buf, m->h_buf, inEnd, cudaMemcpyHostToDevice, m->stream));
-  const size_t smem = sizeof(double) * (4 * (size_t)n_control + 3 * (size_t)n_valid + 2);
+  const size_t smem = sizeof(double) * (4 * (size_t)n_control + 3 * (size_t)n_valid + 4 * (((size_t)n_valid + 31) / 32) + 2);
   if(smem > 200 * 1024) { set_error("control set / model too large for shared memory"); return TSD_E_INVALID; }
   if(smem > 48 * 1024) TSD_CUDA(cudaFuncSetAttribute(k_score_rnm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sm = 148;

@@ -4,6 +4,7 @@
 // 1 + init weight = seen empty, 2 + 1024 x (tsd, weight) = allocated.  Borders are not stored: a loaded partition
 // has the borders TsdGridPartition::init gives it, and the next push refreshes them (propagateBorders).
 // Host code around bulk D2H / H2D copies of whole partition rows; unsharded grids only.
+#include <locale.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,6 +19,15 @@ using namespace tsd;
 
 namespace
 {
+
+// The format is the "C" locale's (decimal point); a host application may have set another LC_NUMERIC: pin the
+// calling thread to "C" for the duration of a store / load.
+struct CLocale
+{
+  locale_t c, old;
+  CLocale() : c(newlocale(LC_ALL_MASK, "C", (locale_t)0)), old((locale_t)0) { if(c) old = uselocale(c); }
+  ~CLocale() { if(c) { uselocale(old); freelocale(c); } }
+};
 
 // tools.cpp:190-215
 double get_double_line(FILE* f)
@@ -45,6 +55,7 @@ int tsdg_store(tsd_grid_t* g, const char* path)
   if(g->band) { set_error("tsdg_store works on an unsharded grid"); return TSD_E_INVALID; }
   TSD_CUDA(cudaSetDevice(g->device));
   TSD_CUDA(cudaStreamSynchronize(g->stream));
+  CLocale pinned;
   FILE* f = fopen(path, "w");
   if(!f) { set_error("tsdg_store: cannot open %s", path); return TSD_E_INVALID; }
   std::vector<uint8_t> flags(g->n_parts);
@@ -97,6 +108,7 @@ int tsdg_load(const char* path, int device, tsd_grid_t** out)
 {
   if(!path || !out) return TSD_E_INVALID;
   *out = nullptr;
+  CLocale pinned;
   FILE* f = fopen(path, "r");
   if(!f) { set_error("tsdg_load: cannot open %s", path); return TSD_E_INVALID; }
   const double cellSize = get_double_line(f);
