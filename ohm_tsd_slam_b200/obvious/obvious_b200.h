@@ -792,32 +792,130 @@ protected:
     double phiMax, thetaMin, thetaMax;
   };
 
-  // principal axes of <= 10 points by the closed-form eigen-decomposition of the 2x2 scatter matrix; same
-  // quantities as Matrix::pcaAnalysis feeds calcNormals with (gsl/Matrix.cpp:227-327): unit axes and extents
-  static void pca2(const double* A, int rows, double vLong[2], double vShort[2], double* extLong, double* extShort)
+  // obvious::Matrix::pcaAnalysis (obcore/math/linalg/gsl/Matrix.cpp:227-327) for an n x 2 matrix, statement by
+  // statement, with the published algorithms of the GSL routines it calls: gsl_stats_mean (running mean in long
+  // double), cblas_dgemm in the reference loop orders, gsl_linalg_SV_decomp_jacobi (one-sided Jacobi, linalg/svd.c).
+  // axes: 2 x 4 row-major, {x0 x1 y0 y1} of the long and of the short principal axis.  Bit-identical with the reference
+  // built against those routines (tests: the adapter's match() against tests/golden/matchers_tiny.npz).
+  static double nrm2(const double* x, int n, int stride)  // gslcblas source_nrm2_r.h
   {
-    double cx = 0, cy = 0;
-    for(int i = 0; i < rows; i++) { cx += A[2 * i]; cy += A[2 * i + 1]; }
-    cx /= rows; cy /= rows;
-    double a = 0, b = 0, c = 0;
-    for(int i = 0; i < rows; i++)
+    double scale = 0.0, ssq = 1.0;
+    if(n == 1) return fabs(x[0]);
+    for(int i = 0; i < n; i++)
     {
-      const double x = A[2 * i] - cx, y = A[2 * i + 1] - cy;
-      a += x * x; b += x * y; c += y * y;
+      const double v = x[i * stride];
+      if(v != 0.0)
+      {
+        const double ax = fabs(v);
+        if(scale < ax) { ssq = 1.0 + ssq * (scale / ax) * (scale / ax); scale = ax; }
+        else { ssq += (ax / scale) * (ax / scale); }
+      }
     }
-    const double th = 0.5 * atan2(2.0 * b, a - c);
-    vLong[0] = cos(th); vLong[1] = sin(th);
-    vShort[0] = -sin(th); vShort[1] = cos(th);
-    double lo0 = 1e300, hi0 = -1e300, lo1 = 1e300, hi1 = -1e300;
-    for(int i = 0; i < rows; i++)
+    return scale * sqrt(ssq);
+  }
+
+  static void pcaAxes(const double* Ain, int rows, double axes[8])
+  {
+    const double eps = 2.2204460492503131e-16;  // GSL_DBL_EPSILON
+    std::vector<double> M(Ain, Ain + 2 * (size_t)rows);
+    double cent[2];
+    for(int c = 0; c < 2; c++)
     {
-      const double x = A[2 * i] - cx, y = A[2 * i + 1] - cy;
-      const double p0 = vLong[0] * x + vLong[1] * y, p1 = vShort[0] * x + vShort[1] * y;
-      lo0 = std::min(lo0, p0); hi0 = std::max(hi0, p0);
-      lo1 = std::min(lo1, p1); hi1 = std::max(hi1, p1);
+      long double mean = 0;
+      for(int i = 0; i < rows; i++) mean += (Ain[2 * i + c] - mean) / (i + 1);
+      cent[c] = (double)mean;
     }
-    *extLong = hi0 - lo0;
-    *extShort = hi1 - lo1;
+    for(int c = 0; c < 2; c++)
+      for(int i = 0; i < rows; i++) M[2 * i + c] += -cent[c];
+    // MtM = M' * M  (dgemm Trans, NoTrans: k outer, zero coefficients skipped)
+    double A[4] = {0.0, 0.0, 0.0, 0.0};
+    for(int k = 0; k < rows; k++)
+      for(int i = 0; i < 2; i++)
+      {
+        const double temp = 1.0 * M[2 * k + i];
+        if(temp != 0.0)
+          for(int j = 0; j < 2; j++) A[2 * i + j] += temp * M[2 * k + j];
+      }
+    // one-sided Jacobi SVD of the 2 x 2 matrix A (columns j = 0, k = 1); V accumulates the rotations
+    double V[4] = {1.0, 0.0, 0.0, 1.0}, S[2];
+    const double tolerance = 10 * 2 * eps;
+    for(int j = 0; j < 2; j++) S[j] = eps * nrm2(A + j, 2, 2);
+    int count = 1, sweep = 0;
+    const int sweepmax = 12;
+    while(count > 0 && sweep <= sweepmax)
+    {
+      count = 1;
+      {
+        double pp = 0.0;
+        for(int i = 0; i < 2; i++) pp += A[2 * i] * A[2 * i + 1];
+        pp *= 2.0;
+        const double a = nrm2(A, 2, 2), b = nrm2(A + 1, 2, 2);
+        const double q = a * a - b * b;
+        const double v = hypot(pp, q);
+        const double abserr_a = S[0], abserr_b = S[1];
+        const bool sorted = (a >= b), orthog = (fabs(pp) <= tolerance * (a * b)), noisya = (a < abserr_a), noisyb = (b < abserr_b);
+        if(sorted && (orthog || noisya || noisyb)) count--;
+        else
+        {
+          double cosine, sine;
+          if(v == 0 || !sorted) { cosine = 0.0; sine = 1.0; }
+          else
+          {
+            cosine = sqrt((v + q) / (2.0 * v));
+            sine = pp / (2.0 * v * cosine);
+          }
+          for(int i = 0; i < 2; i++)
+          {
+            const double Aik = A[2 * i + 1], Aij = A[2 * i];
+            A[2 * i] = Aij * cosine + Aik * sine;
+            A[2 * i + 1] = -Aij * sine + Aik * cosine;
+          }
+          S[0] = fabs(cosine) * abserr_a + fabs(sine) * abserr_b;
+          S[1] = fabs(sine) * abserr_a + fabs(cosine) * abserr_b;
+          for(int i = 0; i < 2; i++)
+          {
+            const double Qij = V[2 * i], Qik = V[2 * i + 1];
+            V[2 * i] = Qij * cosine + Qik * sine;
+            V[2 * i + 1] = -Qij * sine + Qik * cosine;
+          }
+        }
+      }
+      sweep++;
+    }
+    // (the singular values and the normalisation of A's columns are not used by pcaAnalysis)
+    // P = V' * M'  (dgemm Trans, Trans): P[i][j] = sum_k V[k][i] * M[j][k]
+    std::vector<double> P(2 * (size_t)rows);
+    for(int i = 0; i < 2; i++)
+      for(int j = 0; j < rows; j++)
+      {
+        double temp = 0.0;
+        for(int k = 0; k < 2; k++) temp += V[2 * k + i] * M[2 * j + k];
+        P[(size_t)i * rows + j] = 0.0 + 1.0 * temp;
+      }
+    auto vmax = [&](int i) { double m = P[(size_t)i * rows]; for(int j = 0; j < rows; j++) if(P[(size_t)i * rows + j] > m) m = P[(size_t)i * rows + j]; return m; };
+    auto vmin = [&](int i) { double m = P[(size_t)i * rows]; for(int j = 0; j < rows; j++) if(P[(size_t)i * rows + j] < m) m = P[(size_t)i * rows + j]; return m; };
+    for(int i = 0; i < 2; i++)
+    {
+      const double max = vmax(i), min = vmin(i);
+      const double ext = max - min;
+      double align = 0.0;
+      if(ext > 1e-6) align = (max + min) / 2.0;
+      for(int j = 0; j < 2; j++)
+      {
+        const double e = V[2 * j + i] * align;
+        cent[j] += e;
+      }
+    }
+    for(int i = 0; i < 2; i++)
+    {
+      const double ext = vmax(i) - vmin(i);
+      for(int j = 0; j < 2; j++)
+      {
+        const double e = V[2 * j + i] * ext / 2.0;
+        axes[i * 4 + 2 * j] = cent[j] - e;
+        axes[i * 4 + 2 * j + 1] = cent[j] + e;
+      }
+    }
   }
 
   // RandomMatching.cpp:77-146
@@ -843,20 +941,30 @@ protected:
             A[2 * cnt + 1] = M[2 * (i + j) + 1];
             cnt++;
           }
-        double vl[2], vs[2], el, es;
-        pca2(A.data(), (int)cnt, vl, vs, &el, &es);
-        const double lenLongSqr = el * el, lenShortSqr = es * es;
+        double Axes[8];
+        pcaAxes(A.data(), (int)cnt, Axes);
+        const double xLong = Axes[1] - Axes[0];
+        const double yLong = Axes[3] - Axes[2];
+        const double xShort = Axes[5] - Axes[4];
+        const double yShort = Axes[7] - Axes[6];
+        const double lenLongSqr = xLong * xLong + yLong * yLong;
+        const double lenShortSqr = xShort * xShort + yShort * yShort;
         if(lenShortSqr > 1e-6 && (lenLongSqr / lenShortSqr) < 4.0)
         {
           maskOut[i] = 0;
           continue;
         }
-        // the reference normalises (xShort, yShort) = vShort * extShort; a degenerate short axis gives NaN there too
-        const double xShort = vs[0] * es, yShort = vs[1] * es;
         const double len = sqrt(lenShortSqr);
-        const double sgn = ((M[2 * i] * xShort + M[2 * i + 1] * yShort) < 0.0) ? 1.0 : -1.0;
-        N[2 * i] = sgn * xShort / len;
-        N[2 * i + 1] = sgn * yShort / len;
+        if((M[2 * i] * xShort + M[2 * i + 1] * yShort) < 0.0)
+        {
+          N[2 * i] = xShort / len;
+          N[2 * i + 1] = yShort / len;
+        }
+        else
+        {
+          N[2 * i] = -xShort / len;
+          N[2 * i + 1] = -yShort / len;
+        }
       }
       else
         maskOut[i] = 0;

@@ -103,3 +103,69 @@ def test_one_handle_from_three_threads_equals_the_serial_run():
     out = subprocess.run([build_threads_exe(), "500"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "identical to the single-threaded run" in out.stdout
+
+
+MATCH_EXE = os.path.join(ROOT, "tests", "cpp", "matchers_adapter_b200")
+
+
+def build_matchers_exe():
+    _build.build()
+    src = os.path.join(ROOT, "tests", "cpp", "matchers_adapter.cpp")
+    hdr = os.path.join(ROOT, "ohm_tsd_slam_b200", "obvious", "obvious_b200.h")
+    if os.path.exists(MATCH_EXE) and os.path.getmtime(MATCH_EXE) > max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(_build.LIB)):
+        return MATCH_EXE
+    libdir = os.path.join(ROOT, "ohm_tsd_slam_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Werror", "-I" + os.path.join(libdir, "obvious"), src, "-o",
+                    MATCH_EXE, "-L" + libdir, "-ltsdslam_b200", "-Wl,-rpath," + libdir], check=True)
+    return MATCH_EXE
+
+
+def test_matcher_replay_compiles():
+    assert os.path.exists(build_matchers_exe())
+
+
+@pytest.mark.gpu
+def test_adapter_matchers_reproduce_reference_golden(tmp_path):
+    """obvious::TSD_PDFMatching / RandomNormalMatching / PDFMatching::match of the adapter (host pre-processing restated
+    from RandomMatching.cpp:52-183 incl. Matrix::pcaAnalysis' Jacobi SVD, hypothesis scoring on the device) under the
+    replayed rand() stream against the reference's own results (tests/golden/matchers_tiny.npz): the same 3x3
+    transformation for every scan, matcher and parameter set.  Tolerance 1e-12 (the winner is the same hypothesis; its
+    matrix is formed on the host from the same two angles)."""
+    import struct
+    from ohm_tsd_slam_b200 import synth
+    G = np.load(os.path.join(ROOT, "tests", "golden", "matchers_tiny.npz"))
+    cfg = synth.config("tiny")
+    sp = cfg.sensor
+    scans = list(cfg.scans(4))
+    path = str(tmp_path / "matchers.bin")
+    with open(path, "wb") as f:
+        f.write(struct.pack("<3i", sp.beams, 3, cfg.layout_grid))
+        f.write(struct.pack("<8d", cfg.cell_size, cfg.truncation_cells, sp.angular_res, sp.phi_min, sp.max_range, sp.min_range,
+                            sp.low_reflectivity_range, math.radians(30.0)))
+        (x, y, th), r0 = scans[0]
+        f.write(np.asarray(r0, dtype=np.float32).tobytes())
+        f.write(synth.pose_matrix(x, y, th).astype(np.float64).tobytes())
+        for k in range(3):
+            f.write(np.asarray(scans[k + 1][1], dtype=np.float32).tobytes())
+            f.write(G[f"pose_{k}"].astype(np.float64).tobytes())
+            f.write(np.ascontiguousarray(G[f"M_{k}"], dtype=np.float64).tobytes())
+            f.write(np.ascontiguousarray(G[f"S_{k}"], dtype=np.float64).tobytes())
+            f.write(G[f"maskM_{k}"].astype(np.uint8).tobytes())
+            f.write(G[f"maskS_{k}"].astype(np.uint8).tobytes())
+            after = G[f"pose_{k + 1}"] if k < 2 else np.zeros((3, 3))
+            f.write(after.astype(np.float64).tobytes())
+    out = subprocess.run([build_matchers_exe(), path], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert len(lines) == 18
+    worst = 0.0
+    exact = 0
+    for ln in lines:
+        p = ln.split()
+        T = np.array([float(v) for v in p[4:]]).reshape(3, 3)
+        ref_T = G[f"{p[0]}_{p[1]}_{p[2]}_{p[3]}"]
+        assert not np.array_equal(ref_T, np.eye(3)) or p[0] != "tsd"
+        worst = max(worst, float(np.max(np.abs(T - ref_T))))
+        exact += int(np.array_equal(T, ref_T))
+    assert worst < 1e-12, (worst, exact, out.stdout)
+    assert exact >= 12, (exact, out.stdout)
