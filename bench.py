@@ -166,7 +166,10 @@ def run_cuda(args):
             acc.append((e0, e1))
             if samples is not None:  # (synchronises, between the event pairs) kernel times + update count of this launch
                 samples.append((grid.last_push_kernel_ms(), grid.last_push_stats()["cell_updates"]))
-        if band:
+        # Pushes need no communication (each band integrates the scans that reach it); the halo rows are synchronised
+        # before something READS across a band boundary -- the sharded ray cast below does, and its time includes it.
+        # --halo-every-step puts one synchronisation into every step, as round 1 did.
+        if band and args.halo_every_step:
             e0, e1 = ev_pair()
             e0.record(stream)
             band.sync_halos()
@@ -198,7 +201,7 @@ def run_cuda(args):
             if count is not None:
                 count.append(grid.last_push_stats()["cell_updates"])
                 scans_pushed[0] += len(b)
-        if band:
+        if band and args.halo_every_step:
             band.sync_halos()
             grid.sync()
 
@@ -231,6 +234,17 @@ def run_cuda(args):
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag.set()
     sampler.join(timeout=2)
+
+    # ---------------- one halo synchronisation after all those pushes (what a read across the band boundary waits for)
+    halo_ms = None
+    if band:
+        barrier()
+        e0, e1 = ev_pair()
+        e0.record(stream)
+        band.sync_halos()
+        e1.record(stream)
+        grid.sync()
+        halo_ms = e0.elapsed_time(e1)
 
     # ---------------- raycast + ICP through the C ABI (host buffers), for the scans/s part of the metric
     icp = capi.Icp(30, 0.4, 0.02, grid.bounds, device=local)
@@ -353,8 +367,9 @@ def run_cuda(args):
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "cuda",
             "config": dict(wl.describe(), parallelism=(f"one band of partition rows per GPU ({world} bands), scans replicated, pushes without "
-                                                       f"communication, boundary rows stored into the neighbours' halo rows once per step by one "
-                                                       f"kernel over CUDA-IPC peer mappings (NVLink P2P stores; no NCCL on the data path)"
+                                                       f"communication; before a read across a band boundary (the sharded ray cast) boundary rows are stored "
+                                                       f"into the neighbours' halo rows by one kernel over CUDA-IPC peer mappings (NVLink P2P stores), and "
+                                                       f"the bands' ray crossings are min-merged by the marching kernel's own P2P stores + a merge kernel"
                                                        if world > 1 else "single GPU"),
                            cell_updates_per_step=upd_per_step_all, push_launch_pairs_per_step_rank0=pushes_per_step,
                            batched=not args.no_batch),
@@ -371,6 +386,8 @@ def run_cuda(args):
                             "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
                             "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(scans_per_step, 1)) if icp_ms else None,
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
+            "halo_sync_ms_rank0": halo_ms,
+            "halo_every_step": bool(args.halo_every_step),
             "map_publication": pub,
             "hypothesis_scoring": hyp,
             "raycast_sweep": rc_sweep,
@@ -552,6 +569,7 @@ def main():
     ap.add_argument("--workload", default=None, help="C3 (default at 1 GPU) or C2; N > 1 always uses C2 robots")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch", action="store_true", help="push the two lasers of a robot one by one (two launch pairs)")
+    ap.add_argument("--halo-every-step", action="store_true", help="N > 1: synchronise the halo rows inside every timed step")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 16384^2 push sweep (4.6 GB of HBM, a few seconds)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup

@@ -228,6 +228,23 @@ int tsdg_raycast(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_wo
  * is a hit iff the winning key has code 0 (ohm_tsd_slam_b200/sharded.py). */
 int tsdg_raycast_band_keys(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_world,
                            uint64_t** dev_keys, double** dev_payload);
+/* The same merge done by the library over peer memory, one call per band (a COLLECTIVE: every band of the grid calls
+ * it with the same scan): the marching kernel of each band stores its per-beam first events straight into every band's
+ * exchange block (NVLink P2P stores / CUDA-IPC mappings) and signals; a second kernel waits for all bands' signals and
+ * keeps, per beam, the earliest event.  Every band returns the full result -- what RayCastPolar2D::
+ * calcCoordsFromCurrentViewMask returns on the unsharded grid (RayCastPolar2D.cpp:113-192).  Set-up, once: every band
+ * exports its exchange block (tsdg_band_rcx_export, a blob of TSD_BAND_EXPORT_BYTES) and connects with the blobs of ALL
+ * bands, ordered by rank (tsdg_band_rcx_connect; world <= 16, scans <= 2048 beams); bands living in one process
+ * connect with tsdg_band_rcx_connect_local.  Halos and allocation flags must be current, as for tsdg_raycast_band_keys. */
+int tsdg_band_rcx_export(tsd_grid_t* grid, void* blob);
+int tsdg_band_rcx_connect(tsd_grid_t* grid, int rank, int world, const void* blobs);
+int tsdg_band_rcx_connect_local(tsd_grid_t* grid, int rank, int world, tsd_grid_t** bands);
+int tsdg_raycast_mask_sharded(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_world, double* coords,
+                              double* normals, uint8_t* mask, uint32_t* count);
+/* Its two halves, for bands that live in one process (a blocking call per band would wait for bands not yet launched):
+ * tsdg_raycast_sharded_launch on every band, then tsdg_raycast_sharded_collect on every band. */
+int tsdg_raycast_sharded_launch(tsd_grid_t* grid, const tsd_scan_t* scan, const double* rays_world);
+int tsdg_raycast_sharded_collect(tsd_grid_t* grid, int32_t n, double* coords, double* normals, uint8_t* mask, uint32_t* count);
 /* step counters of the most recent raycast on this handle */
 int tsdg_last_raycast_steps(tsd_grid_t* grid, uint64_t* fine_steps, uint64_t* coarse_steps);
 

@@ -31,6 +31,8 @@ EXPORTS = [
     "tsdg_stream", "tsdg_stream_order", "tsdg_set_timing", "tsdg_set_update_filter", "tsdg_last_push_kernel_ms", "tsdg_last_push_stats", "tsdg_interpolate_bilinear", "tsdg_interpolate_normal",
     "tsdg_num_partitions", "tsdg_partition_states", "tsdg_download_partition", "tsdg_upload_partition", "tsdg_fill",
     "tsdg_raycast_mask", "tsdg_raycast", "tsdg_raycast_band_keys", "tsdg_last_raycast_steps",
+    "tsdg_band_rcx_export", "tsdg_band_rcx_connect", "tsdg_band_rcx_connect_local", "tsdg_raycast_mask_sharded",
+    "tsdg_raycast_sharded_launch", "tsdg_raycast_sharded_collect",
     "tsdg_axis_aligned_map", "tsdg_color_image", "tsdg_store", "tsdg_load", "tsds_prepare_scan",
     "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
@@ -72,6 +74,12 @@ def lib():
     L.tsdg_band_halo_sync.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
     L.tsdg_band_row.argtypes = [C.c_void_p, C.c_int, _vpp, _vpp, C.POINTER(C.c_uint64)]
     L.tsdg_raycast_band_keys.argtypes = [C.c_void_p, _sp, _dp, _vpp, _vpp]
+    L.tsdg_band_rcx_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.tsdg_band_rcx_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.tsdg_band_rcx_connect_local.argtypes = [C.c_void_p, C.c_int, C.c_int, _vpp]
+    L.tsdg_raycast_mask_sharded.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _bp, _up]
+    L.tsdg_raycast_sharded_launch.argtypes = [C.c_void_p, _sp, _dp]
+    L.tsdg_raycast_sharded_collect.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _bp, _up]
     L.tsdg_set_max_truncation.argtypes = [C.c_void_p, C.c_double]
     L.tsdg_get_geometry.argtypes = [C.c_void_p, _ip, _ip, _ip] + [_dp] * 6
     L.tsdg_free_footprint.argtypes = [C.c_void_p] + [C.c_double] * 4
@@ -416,6 +424,43 @@ class Grid:
         t, w, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
         check(lib().tsdg_band_row(self.h, which, C.byref(t), C.byref(w), C.byref(n)))
         return int(t.value or 0), int(w.value or 0), int(n.value)
+
+    def band_rcx_export(self) -> bytes:
+        buf = C.create_string_buffer(BAND_EXPORT_BYTES)
+        check(lib().tsdg_band_rcx_export(self.h, buf))
+        return bytes(buf.raw)
+
+    def band_rcx_connect(self, rank: int, blobs):
+        """blobs: the tsdg_band_rcx_export blobs of ALL bands, ordered by rank."""
+        raw = b"".join(blobs)
+        check(lib().tsdg_band_rcx_connect(self.h, rank, len(blobs), C.create_string_buffer(raw, len(raw))))
+
+    def band_rcx_connect_local(self, rank: int, grids):
+        arr = (C.c_void_p * len(grids))(*[g.h for g in grids])
+        check(lib().tsdg_band_rcx_connect_local(self.h, rank, len(grids), arr))
+
+    def raycast_mask_sharded(self, scan: Scan, rays_world, coords=None, normals=None):
+        """Collective over the bands of a sharded grid (one call per band / process): the full ray-cast result."""
+        n = scan.n
+        rays = _f64(rays_world)
+        coords = np.zeros((n, 2)) if coords is None else coords
+        normals = np.zeros((n, 2)) if normals is None else normals
+        mask = np.zeros(n, dtype=np.uint8)
+        cnt = C.c_uint32()
+        check(lib().tsdg_raycast_mask_sharded(self.h, scan.byref(), _d(rays), _d(coords), _d(normals), mask.ctypes.data_as(_bp),
+                                               C.byref(cnt)))
+        return coords, normals, mask, int(cnt.value)
+
+    def raycast_sharded_launch(self, scan: Scan, rays_world):
+        check(lib().tsdg_raycast_sharded_launch(self.h, scan.byref(), _d(_f64(rays_world))))
+
+    def raycast_sharded_collect(self, n: int, coords=None, normals=None):
+        coords = np.zeros((n, 2)) if coords is None else coords
+        normals = np.zeros((n, 2)) if normals is None else normals
+        mask = np.zeros(n, dtype=np.uint8)
+        cnt = C.c_uint32()
+        check(lib().tsdg_raycast_sharded_collect(self.h, n, _d(coords), _d(normals), mask.ctypes.data_as(_bp), C.byref(cnt)))
+        return coords, normals, mask, int(cnt.value)
 
     def raycast_band_keys(self, scan: Scan, rays_world):
         """Device pointers (keys u64[n], payload f64[4n]) of this band's first events."""

@@ -21,6 +21,8 @@
 #define TSD_BORDER_OFF 1024       // [0,32): column x=32, rows y=0..31 ; [32,64): row y=32, columns 0..31 ; 64: corner
 #define TSD_MAXWEIGHT 32.0        // reconstruct_defs.h:4
 #define TSD_NOT_OWNED 4           // sample status: partition belongs to another band (sharded grid only)
+#define TSD_RCX_MAX 16            // bands of a sharded grid that can exchange ray-cast events over peer memory
+#define TSD_RCX_CAP 2048          // beams per scan in that exchange
 
 namespace tsd
 {
@@ -208,6 +210,35 @@ __device__ __forceinline__ void mat3_vec_nn(const double* T, double v0, double v
   *o1 = r1;
 }
 
+// ---- release / acquire signals at system scope (peer memory over NVLink, or another process on the same GPU) ----
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// sequence numbers wrap: compare as a signed distance.  A neighbour that never calls (the C ABI asks both sides of a
+// boundary to call equally often) must not hang the GPU, and must not take the CUDA context -- and the map -- down
+// either: after ~10 s the wait gives up and raises an error flag that the host reports (TSD_E_CUDA) at the next
+// synchronisation; the kernel finishes with whatever arrived.
+__device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq, uint32_t* err)
+{
+  for(unsigned spins = 0; (int32_t)(ld_acquire_sys(p) - seq) < 0; spins++)
+  {
+    __nanosleep(256);
+    if(spins > (1u << 25))
+    {
+      atomicExch(err, 1u);
+      return;
+    }
+  }
+}
+
+
 #endif  // __CUDACC__
 
 int fill_scan_dev(const tsd_scan_t* scan, ScanDev* out);  // scalars only (pointers are set by the caller)
@@ -307,6 +338,13 @@ struct tsd_grid
     int alloc_begin;         // the neighbour's first allocated partition row
   } peer[2];
   uint32_t halo_seq[2];      // synchronisations done per boundary (both sides count alike)
+  // ray-cast exchange over peer memory (raycast.cu): every band stores its per-beam first events into its slot of EVERY
+  // band's block; [2 parities][TSD_RCX_MAX slots][TSD_RCX_CAP beams] keys, the same of 4-double payloads, then signals
+  unsigned char* d_rcx;
+  unsigned char* peer_rcx[16];
+  bool peer_rcx_ipc[16];
+  int rcx_rank, rcx_world;
+  uint32_t rcx_seq;
   bool halo_used;            // k_halo_sync ran: tsdg_sync looks at its timeout flag (d_signal[5])
   bool has_staged;
   unsigned update_filter;  // measurement aid: k_update skips K2 (bit 0) / K3 (bit 1) work (tsdg_set_update_filter)

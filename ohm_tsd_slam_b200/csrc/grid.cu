@@ -1271,33 +1271,6 @@ struct HaloParams
   uint32_t seq[2];
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
-{
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
-{
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// sequence numbers wrap: compare as a signed distance.  A neighbour that never calls (the C ABI asks both sides of a
-// boundary to call equally often) must not hang the GPU, and must not take the CUDA context -- and the map -- down
-// either: after ~10 s the wait gives up and raises an error flag that the host reports (TSD_E_CUDA) at the next
-// synchronisation; the kernel finishes with whatever arrived.
-__device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq, uint32_t* err)
-{
-  for(unsigned spins = 0; (int32_t)(ld_acquire_sys(p) - seq) < 0; spins++)
-  {
-    __nanosleep(256);
-    if(spins > (1u << 25))
-    {
-      atomicExch(err, 1u);
-      return;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(256) k_halo_sync(HaloParams hp)
 {
   const int t = threadIdx.x;
@@ -1830,6 +1803,9 @@ int tsdg_destroy(tsd_grid_t* g)
     {
       cudaIpcCloseMemHandle(g->peer[b].tsd); cudaIpcCloseMemHandle(g->peer[b].weight); cudaIpcCloseMemHandle(g->peer[b].signal);
     }
+  for(int r = 0; r < 16; r++)
+    if(g->peer_rcx[r] && g->peer_rcx_ipc[r]) cudaIpcCloseMemHandle(g->peer_rcx[r]);
+  cudaFree(g->d_rcx);
   cudaFree(g->d_pending); cudaFree(g->d_counters);
   cudaFree(g->d_stats64); cudaFree(g->d_coltab); cudaFree(g->d_rowtab); cudaFree(g->d_col4); cudaFree(g->d_row4); cudaFree(g->d_scans); cudaFree(g->d_prof); cudaFree(g->d_gate); cudaFree(g->d_kinds); cudaFree(g->d_dirs); cudaFree(g->d_in);
   cudaFree(g->d_rc); cudaFree(g->d_scratch);

@@ -27,16 +27,22 @@ struct RayParams
   double xmin, ymin, xmax, ymax;  // RayCastPolar2D.cpp:128-146
   double idxMin, idxMax;          // :148-149
   int band;                       // 1: sharded grid, emit band-local first events (tsdg_raycast_band_keys)
+  // Sharded grid, exchange over peer memory (tsdg_raycast_mask_sharded): rcx_world > 0 makes every beam's first event
+  // go into slot rcx_rank of EVERY band's exchange block (NVLink P2P stores from the marching kernel itself: the
+  // all-gather is part of the kernel that computes the data), followed by a release signal to every band.
+  int rcx_world, rcx_rank;
+  uint32_t rcx_seq;
+  unsigned long long* rcx_keys[TSD_RCX_MAX];  // band r's key array of the current parity: [slot][TSD_RCX_CAP]
+  double* rcx_out[TSD_RCX_MAX];               // band r's payload array: [slot][TSD_RCX_CAP][4]
+  uint32_t* rcx_sig[TSD_RCX_MAX];             // band r's signal words: [slot]
+  uint32_t* rcx_ticket;                       // this band's CTA ticket
 };
 
 #define RC_WARPS 4
 #define NO_EVENT 0x7fffffffffffffffULL  // INT64_MAX: the largest key under a signed or unsigned min-reduction
 
-__global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
+__device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam, const int lane)
 {
-  const int lane = threadIdx.x & 31;
-  const int beam = blockIdx.x * RC_WARPS + (threadIdx.x >> 5);
-  if(beam >= rp.scan.n) return;
   const GridView& g = rp.g;
   const double ray0 = rp.rays[beam];
   const double ray1 = rp.rays[rp.scan.n + beam];
@@ -234,12 +240,104 @@ __global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
     rp.keys[beam] = key;
     atomicAdd(&rp.steps[0], nFine);
     atomicAdd(&rp.steps[1], nCoarse);
+    if(rp.rcx_world > 0)
+    {
+      const double o0 = rp.out[4 * beam + 0], o1 = rp.out[4 * beam + 1], o2 = rp.out[4 * beam + 2], o3 = rp.out[4 * beam + 3];
+      const size_t slot = (size_t)rp.rcx_rank * TSD_RCX_CAP + (size_t)beam;
+      for(int r = 0; r < rp.rcx_world; r++)
+      {
+        rp.rcx_keys[r][slot] = key;
+        *reinterpret_cast<double2*>(rp.rcx_out[r] + 4 * slot) = make_double2(o0, o1);
+        *reinterpret_cast<double2*>(rp.rcx_out[r] + 4 * slot + 2) = make_double2(o2, o3);
+      }
+    }
   }
+}
+
+__global__ void __launch_bounds__(RC_WARPS * 32) k_raycast(RayParams rp)
+{
+  const int lane = threadIdx.x & 31;
+  const int beam = blockIdx.x * RC_WARPS + (threadIdx.x >> 5);
+  if(beam < rp.scan.n) raycast_beam(rp, beam, lane);
+  if(rp.rcx_world > 0)
+  {
+    // the last CTA to finish tells every band (itself included) that this band's slot is complete
+    __threadfence_system();
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+      if(atomicAdd(rp.rcx_ticket, 1u) == gridDim.x - 1)
+      {
+        *rp.rcx_ticket = 0;
+        __threadfence_system();
+        for(int r = 0; r < rp.rcx_world; r++) st_release_sys(rp.rcx_sig[r] + rp.rcx_rank, rp.rcx_seq);
+      }
+    }
+  }
+}
+
+// Second half of the sharded ray cast: wait until every band's slot of this band's exchange block is complete, then
+// every beam takes the earliest event among the bands (keys are 4 * step + code: the reference's serial march stops at
+// the first event) and the payload of the band that saw it.  One launch; the result lands where the unsharded ray
+// caster leaves its own (keys + {cx cy nx ny}), so the host side is shared.
+struct MergeParams
+{
+  int n, world;
+  uint32_t seq;
+  const uint32_t* sig;   // this band's signal words [slot]
+  uint32_t* err;
+  const unsigned long long* keys_in;  // [slot][TSD_RCX_CAP]
+  const double* out_in;               // [slot][TSD_RCX_CAP][4]
+  unsigned long long* keys;
+  double* out;
+};
+
+__global__ void __launch_bounds__(256) k_raycast_merge(MergeParams mp)
+{
+  if(threadIdx.x < mp.world) wait_seq(mp.sig + threadIdx.x, mp.seq, mp.err);
+  __syncthreads();
+  const int beam = blockIdx.x * blockDim.x + threadIdx.x;
+  if(beam >= mp.n) return;
+  unsigned long long best = NO_EVENT;
+  int br = 0;
+  for(int r = 0; r < mp.world; r++)
+  {
+    const unsigned long long k = mp.keys_in[(size_t)r * TSD_RCX_CAP + beam];
+    if(k < best) { best = k; br = r; }
+  }
+  const double* src = mp.out_in + 4 * ((size_t)br * TSD_RCX_CAP + beam);
+  const bool any = best != NO_EVENT;
+  mp.keys[beam] = best;
+  mp.out[4 * beam + 0] = any ? src[0] : 0.0;
+  mp.out[4 * beam + 1] = any ? src[1] : 0.0;
+  mp.out[4 * beam + 2] = any ? src[2] : 0.0;
+  mp.out[4 * beam + 3] = any ? src[3] : 0.0;
 }
 
 #define RC_IS_HIT(k) ((k) != NO_EVENT && ((k) & 3ULL) == 0ULL)
 
-static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, bool download = true)
+// layout of a band's exchange block
+#define RCX_KEYS_BYTES ((size_t)2 * TSD_RCX_MAX * TSD_RCX_CAP * sizeof(unsigned long long))
+#define RCX_OUT_BYTES ((size_t)2 * TSD_RCX_MAX * TSD_RCX_CAP * 4 * sizeof(double))
+#define RCX_SIG_OFF (RCX_KEYS_BYTES + RCX_OUT_BYTES)   // uint32: [TSD_RCX_MAX] signals, [TSD_RCX_MAX] ticket, [+1] timeout flag
+#define RCX_BYTES (RCX_SIG_OFF + (TSD_RCX_MAX + 8) * sizeof(uint32_t))
+
+static int raycast_exchange_finish(tsd_grid_t* g)
+{
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  uint32_t err = 0;
+  TSD_CUDA(cudaMemcpy(&err, g->d_rcx + RCX_SIG_OFF + (TSD_RCX_MAX + 1) * sizeof(uint32_t), sizeof(err), cudaMemcpyDeviceToHost));
+  if(err)
+  {
+    cudaMemset(g->d_rcx + RCX_SIG_OFF + (TSD_RCX_MAX + 1) * sizeof(uint32_t), 0, sizeof(uint32_t));
+    set_error("sharded ray cast timed out: not every band took part (the sharded ray cast is a collective)");
+    return TSD_E_CUDA;
+  }
+  return TSD_OK;
+}
+
+static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, bool download = true, bool exchange = false,
+                          bool sync = true)
 {
   TSD_LOCK(g);
   if(!g || !scan || !rays_world) return TSD_E_INVALID;
@@ -268,9 +366,45 @@ static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* r
   }
   rp.idxMin = scan->min_range / g->cell_size;
   rp.idxMax = scan->max_range / g->cell_size;
+  if(exchange)
+  {
+    if(g->rcx_world < 1 || !g->d_rcx) { set_error("ray-cast exchange not connected (tsdg_band_rcx_connect)"); return TSD_E_INVALID; }
+    if(n > TSD_RCX_CAP) { set_error("scan too large for the ray-cast exchange block (%d beams)", TSD_RCX_CAP); return TSD_E_INVALID; }
+    const uint32_t seq = ++g->rcx_seq;
+    const size_t par = seq & 1u;
+    rp.rcx_world = g->rcx_world;
+    rp.rcx_rank = g->rcx_rank;
+    rp.rcx_seq = seq;
+    for(int r = 0; r < g->rcx_world; r++)
+    {
+      unsigned char* blk = (r == g->rcx_rank) ? g->d_rcx : g->peer_rcx[r];
+      rp.rcx_keys[r] = reinterpret_cast<unsigned long long*>(blk) + par * TSD_RCX_MAX * TSD_RCX_CAP;
+      rp.rcx_out[r] = reinterpret_cast<double*>(blk + RCX_KEYS_BYTES) + par * TSD_RCX_MAX * TSD_RCX_CAP * 4;
+      rp.rcx_sig[r] = reinterpret_cast<uint32_t*>(blk + RCX_SIG_OFF);
+    }
+    rp.rcx_ticket = reinterpret_cast<uint32_t*>(g->d_rcx + RCX_SIG_OFF) + TSD_RCX_MAX;
+  }
   k_raycast<<<(n + RC_WARPS - 1) / RC_WARPS, RC_WARPS * 32, 0, g->stream>>>(rp);
   TSD_LAUNCHED();
+  if(exchange)
+  {
+    MergeParams mp;
+    mp.n = n;
+    mp.world = g->rcx_world;
+    mp.seq = g->rcx_seq;
+    mp.sig = reinterpret_cast<const uint32_t*>(g->d_rcx + RCX_SIG_OFF);
+    mp.err = reinterpret_cast<uint32_t*>(g->d_rcx + RCX_SIG_OFF) + TSD_RCX_MAX + 1;
+    const size_t par = g->rcx_seq & 1u;
+    mp.keys_in = reinterpret_cast<const unsigned long long*>(g->d_rcx) + par * TSD_RCX_MAX * TSD_RCX_CAP;
+    mp.out_in = reinterpret_cast<const double*>(g->d_rcx + RCX_KEYS_BYTES) + par * TSD_RCX_MAX * TSD_RCX_CAP * 4;
+    mp.keys = g->d_rc_keys;
+    mp.out = g->d_rc_out;
+    k_raycast_merge<<<(n + 255) / 256, 256, 0, g->stream>>>(mp);
+    TSD_LAUNCHED();
+  }
   if(download) TSD_CUDA(cudaMemcpyAsync(g->h_rc, g->d_rc, g->rc_bytes, cudaMemcpyDeviceToHost, g->stream));
+  if(!sync) return TSD_OK;
+  if(exchange) return raycast_exchange_finish(g);
   TSD_CUDA(cudaStreamSynchronize(g->stream));
   return TSD_OK;
 }
@@ -334,6 +468,140 @@ int tsdg_last_raycast_steps(tsd_grid_t* g, uint64_t* fine_steps, uint64_t* coars
   if(fine_steps) *fine_steps = g->h_rc_steps[0] - g->rc_steps_prev[0];
   if(coarse_steps) *coarse_steps = g->h_rc_steps[1] - g->rc_steps_prev[1];
   return TSD_OK;
+}
+
+// --- sharded ray cast over peer memory --------------------------------------------------------------------------
+struct RcxExport
+{
+  cudaIpcMemHandle_t block;
+  int32_t row_begin, row_end, parts_x;
+};
+static_assert(sizeof(RcxExport) <= TSD_BAND_EXPORT_BYTES, "tsd_band_export_t too small");
+
+static int rcx_ensure(tsd_grid_t* g)
+{
+  if(g->d_rcx) return TSD_OK;
+  TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaMalloc(&g->d_rcx, RCX_BYTES));
+  TSD_CUDA(cudaMemset(g->d_rcx, 0, RCX_BYTES));
+  return TSD_OK;
+}
+
+int tsdg_band_rcx_export(tsd_grid_t* g, void* blob)
+{
+  TSD_LOCK(g);
+  if(!g || !blob || !g->band) { set_error("not a sharded grid"); return TSD_E_INVALID; }
+  int rc = rcx_ensure(g);
+  if(rc) return rc;
+  RcxExport e;
+  memset(&e, 0, sizeof(e));
+  TSD_CUDA(cudaIpcGetMemHandle(&e.block, g->d_rcx));
+  e.row_begin = g->row_begin;
+  e.row_end = g->row_end;
+  e.parts_x = g->parts_x;
+  memset(blob, 0, TSD_BAND_EXPORT_BYTES);
+  memcpy(blob, &e, sizeof(e));
+  return TSD_OK;
+}
+
+int tsdg_band_rcx_connect(tsd_grid_t* g, int rank, int world, const void* blobs)
+{
+  TSD_LOCK(g);
+  if(!g || !g->band || !blobs || world < 1 || world > TSD_RCX_MAX || rank < 0 || rank >= world) return TSD_E_INVALID;
+  int rc = rcx_ensure(g);
+  if(rc) return rc;
+  TSD_CUDA(cudaSetDevice(g->device));
+  for(int r = 0; r < world; r++)
+  {
+    if(r == rank) continue;
+    RcxExport e;
+    memcpy(&e, (const unsigned char*)blobs + (size_t)r * TSD_BAND_EXPORT_BYTES, sizeof(e));
+    if(e.parts_x != g->parts_x) { set_error("band %d has another grid geometry", r); return TSD_E_INVALID; }
+    void* p = nullptr;
+    TSD_CUDA(cudaIpcOpenMemHandle(&p, e.block, cudaIpcMemLazyEnablePeerAccess));
+    g->peer_rcx[r] = static_cast<unsigned char*>(p);
+    g->peer_rcx_ipc[r] = true;
+  }
+  g->rcx_rank = rank;
+  g->rcx_world = world;
+  return TSD_OK;
+}
+
+int tsdg_band_rcx_connect_local(tsd_grid_t* g, int rank, int world, tsd_grid_t** bands)
+{
+  TSD_LOCK(g);
+  if(!g || !g->band || !bands || world < 1 || world > TSD_RCX_MAX || rank < 0 || rank >= world) return TSD_E_INVALID;
+  int rc = rcx_ensure(g);
+  if(rc) return rc;
+  for(int r = 0; r < world; r++)
+  {
+    if(r == rank) continue;
+    if(!bands[r] || !bands[r]->band) return TSD_E_INVALID;
+    rc = rcx_ensure(bands[r]);
+    if(rc) return rc;
+    if(bands[r]->device != g->device)
+    {
+      TSD_CUDA(cudaSetDevice(g->device));
+      int can = 0;
+      TSD_CUDA(cudaDeviceCanAccessPeer(&can, g->device, bands[r]->device));
+      if(!can) { set_error("no peer access between devices %d and %d", g->device, bands[r]->device); return TSD_E_INVALID; }
+      cudaError_t pe = cudaDeviceEnablePeerAccess(bands[r]->device, 0);
+      if(pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) TSD_CUDA(pe);
+      cudaGetLastError();
+    }
+    g->peer_rcx[r] = bands[r]->d_rcx;
+    g->peer_rcx_ipc[r] = false;
+  }
+  g->rcx_rank = rank;
+  g->rcx_world = world;
+  return TSD_OK;
+}
+
+static int raycast_copy_out(tsd_grid_t* g, int n, double* coords, double* normals, uint8_t* mask, uint32_t* count)
+{
+  uint32_t cnt = 0;
+  for(int b = 0; b < n; b++)
+  {
+    if(RC_IS_HIT(g->h_rc_keys[b]))
+    {
+      coords[2 * b] = g->h_rc_out[4 * b];
+      coords[2 * b + 1] = g->h_rc_out[4 * b + 1];
+      normals[2 * b] = g->h_rc_out[4 * b + 2];
+      normals[2 * b + 1] = g->h_rc_out[4 * b + 3];
+      mask[b] = 1;
+      cnt++;
+    }
+    else
+      mask[b] = 0;
+  }
+  if(count) *count = cnt;
+  return TSD_OK;
+}
+
+int tsdg_raycast_mask_sharded(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, double* coords, double* normals,
+                              uint8_t* mask, uint32_t* count)
+{
+  TSD_LOCK(g);
+  if(!coords || !normals || !mask) return TSD_E_INVALID;
+  int rc = raycast_launch(g, scan, rays_world, true, true);
+  if(rc) return rc;
+  return raycast_copy_out(g, scan->n, coords, normals, mask, count);
+}
+
+/* the two halves of tsdg_raycast_mask_sharded, for bands that live in ONE process: launch on every band, then collect */
+int tsdg_raycast_sharded_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world)
+{
+  TSD_LOCK(g);
+  return raycast_launch(g, scan, rays_world, true, true, false);
+}
+
+int tsdg_raycast_sharded_collect(tsd_grid_t* g, int32_t n, double* coords, double* normals, uint8_t* mask, uint32_t* count)
+{
+  TSD_LOCK(g);
+  if(!g || !coords || !normals || !mask || n < 1 || n > g->scan_cap) return TSD_E_INVALID;
+  int rc = raycast_exchange_finish(g);
+  if(rc) return rc;
+  return raycast_copy_out(g, n, coords, normals, mask, count);
 }
 
 int tsdg_raycast_band_keys(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, uint64_t** dev_keys,

@@ -126,6 +126,9 @@ class LocalBands:
                     g.band_connect_local(0, self.grids[i - 1])
                 if i + 1 < len(self.grids):
                     g.band_connect_local(1, self.grids[i + 1])
+            if len(self.grids) <= 16:
+                for i, g in enumerate(self.grids):
+                    g.band_rcx_connect_local(i, self.grids)
 
     def set_max_truncation(self, v):
         for g in self.grids:
@@ -240,6 +243,22 @@ class LocalBands:
         self.sync_halos()
         self.sync_flags()
         n = scan.n
+        if self.peer and len(self.grids) <= 16 and n <= 2048:
+            # the library's own merge over peer memory (tsdg_raycast_sharded_launch / _collect): every band's marching
+            # kernel stores its events into every band's exchange block, a second kernel per band keeps the earliest
+            for g in self.grids:
+                g.raycast_sharded_launch(scan, rays_world)
+            res = [g.raycast_sharded_collect(n) for g in self.grids]
+            c0, n0, m0, k0 = res[0]
+            for c1, n1, m1, k1 in res[1:]:  # every band holds the same, full result
+                assert k1 == k0 and np.array_equal(m1, m0) and np.array_equal(c1, c0) and np.array_equal(n1, n0)
+            if coords is not None:
+                coords[m0 > 0] = c0[m0 > 0]
+                c0 = coords
+            if normals is not None:
+                normals[m0 > 0] = n0[m0 > 0]
+                n0 = normals
+            return c0, n0, m0, k0
         ks, ps = [], []
         for g in self.grids:
             kp, pp = g.raycast_band_keys(scan, rays_world)
@@ -294,6 +313,8 @@ class DistBand:
         self._flags = None
         self._views = None
         self.transport = transport
+        self.rcx = False
+        self.dirty_rows = None  # partition rows whose allocation flags may have changed since the last merge
         # gloo (the CPU backend; also what the one-GPU multi-process parity test uses) reduces host tensors only
         self._host_collectives = dist.get_backend() != "nccl"
         if self._host_collectives and transport != "peer":
@@ -305,6 +326,12 @@ class DistBand:
                 self.grid.band_connect(0, blobs[self.rank - 1])
             if self.rank + 1 < self.world:
                 self.grid.band_connect(1, blobs[self.rank + 1])
+            # the ray-cast exchange connects every band with every band
+            self.rcx = self.world <= 16
+            if self.rcx:
+                rblobs = [None] * self.world
+                dist.all_gather_object(rblobs, self.grid.band_rcx_export())
+                self.grid.band_rcx_connect(self.rank, rblobs)
             dist.barrier()
 
     def _all_reduce(self, t: torch.Tensor, op):
@@ -329,6 +356,7 @@ class DistBand:
         """Book-keeping for one scan that EVERY rank calls with the same box: which boundaries it dirties.
         Returns whether this rank has to push it."""
         b, e = self.rows[self.rank]
+        self.dirty_rows = (box[1], box[3]) if self.dirty_rows is None else (min(self.dirty_rows[0], box[1]), max(self.dirty_rows[1], box[3]))
         lower, upper = touched_boundaries(box, b, e, self.rank, self.world)
         if lower:
             self.dirty_lo.add(box[0], box[2])
@@ -393,11 +421,18 @@ class DistBand:
         if self._flags is None:
             ptr, n = self.grid.band_flags()
             self._flags = device_tensor(ptr, n, "|u1", self.device)
+        # only the partition rows a scan could have reached since the last merge (every rank saw the same scans, hence
+        # the same range); everything, when the range is unknown (fills, footprints)
+        view = self._flags
+        if self.dirty_rows is not None:
+            r0, r1 = max(self.dirty_rows[0] - 1, 0), min(self.dirty_rows[1] + 1, self.parts_x - 1)
+            view = self._flags[r0 * self.parts_x:(r1 + 1) * self.parts_x]
         cur = torch.cuda.current_stream(self.device)
         self.grid.stream_order(cur.cuda_stream, 0)
-        self._all_reduce(self._flags, self.dist.ReduceOp.MAX)
+        self._all_reduce(view, self.dist.ReduceOp.MAX)
         self.grid.stream_order(cur.cuda_stream, 1)
         self.flags_dirty = False
+        self.dirty_rows = None
 
     def _box(self, scan: Scan):
         """tsdg_scan_box, cached on the scan object (keyed by what the box depends on): a step of N robots asks for
@@ -442,6 +477,9 @@ class DistBand:
         n = scan.n
         self.sync_halos()
         self.sync_flags()
+        if self.rcx and n <= 2048:
+            # min-merge of the bands' crossings inside the library, over peer memory (no collective call here)
+            return self.grid.raycast_mask_sharded(scan, rays_world)
         kp, pp = self.grid.raycast_band_keys(scan, rays_world)
         keys = device_tensor(kp, n, "<i8", self.device)
         payload = device_tensor(pp, 4 * n, "<f8", self.device).view(n, 4)
