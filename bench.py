@@ -102,7 +102,14 @@ def run_cuda(args):
         # (tsdg_scan_box) into its own rows -- no communication -- and synchronises the boundary rows with its
         # neighbours once per step (P2P over NCCL), as a SLAM cycle that ray-casts after pushing would.
         from ohm_tsd_slam_b200.sharded import DistBand
-        from ohm_tsd_slam_b200.workload import MultiRobotWorkload
+        from ohm_tsd_slam_b200.workload import MultiRobotWorkload, secondary_push_benchmark
+        # The weak-scaling unit is one robot of this kind on one GPU.  The default N = 1 run of this script headlines the
+        # 16384^2 map instead (BASELINE configs[2]), so the N > 1 line carries its own reference: rank 0 first runs one
+        # robot alone on its 4096^2 grid (the others wait).
+        one_gpu = None
+        if rank == 0:
+            one_gpu = secondary_push_benchmark(args.workload, device=local, steps=min(args.steps, 200), peak_gbs=measured_peak()[0])
+        dist.barrier()
         wl = MultiRobotWorkload(world, args.workload, invert=capi.invert3x3)
         cfg = wl.cfg
         band = DistBand(wl.cell_size, wl.layout_grid, local)
@@ -386,6 +393,8 @@ def run_cuda(args):
                             "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
                             "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(scans_per_step, 1)) if icp_ms else None,
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
+            "one_gpu_same_workload": (None if world == 1 else {k: one_gpu[k] for k in ("workload", "value_gcell_updates_per_s", "ms_per_step",
+                                                                                       "e2e_gcell_updates_per_s", "k_update_frac_of_hbm_peak")}),
             "halo_sync_ms_rank0": halo_ms,
             "halo_every_step": bool(args.halo_every_step),
             "map_publication": pub,

@@ -227,15 +227,17 @@ def hypothesis_benchmark(device: int = 0, n_hyp: int = 100000, reps: int = 3, di
     out = {"n_hypotheses": n_hyp, "control_points": int(wl.control.shape[1]), "model_points_valid": int(len(wl.model_valid)),
            "n_gpus": world}
 
-    if dist:
-        import torch
-        dev_word = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", device))
+    dev_words = {}
 
     def amax(t):
         # one 8-byte word through a device tensor that lives for the whole benchmark (NCCL reduces device memory)
-        dev_word.copy_(t)
-        dist.all_reduce(dev_word, op=dist.ReduceOp.MAX)
-        t.copy_(dev_word)
+        import torch
+        w = dev_words.get(t.dtype)
+        if w is None:
+            w = dev_words[t.dtype] = torch.zeros(1, dtype=t.dtype, device=torch.device("cuda", device))
+        w.copy_(t)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        t.copy_(w)
 
     def merged(name, res):
         score = res[0] if name != "rnm" else res[2]
