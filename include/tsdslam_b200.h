@@ -307,6 +307,13 @@ int icp_set_max_iterations(tsd_icp_t* icp, uint32_t max_iterations);
 int icp_run(tsd_icp_t* icp, const double* model, const double* normals, int32_t n_model, const double* scene,
             int32_t n_scene, const double pose[9], const double* t_init, double t_out[9], double* mse,
             uint32_t* pairs, uint32_t* iterations, int32_t* state);
+/* PairAssignment::determinePairs on its own (registration/icp/assign/PairAssignment.cpp:38-84 with the filters the node
+ * wires, ThreadLocalize.cpp:210-221: OutOfBoundsFilter2D.cpp:27-37 before; FlannPairAssignment.cpp:64-92 exact 1-NN;
+ * DistanceFilter.cpp:32-64 at its initial threshold and ReciprocalFilter.cpp:32-78 after).  Pairs in model-index
+ * order: pair_model[i] = indexFirst, pair_scene[i] = indexSecond, dist_sqr[i] (may be NULL) their squared distance.
+ * Arrays must hold min(n_model, n_scene) entries.  pose: the sensor pose the bounds filter transforms the scene with. */
+int icp_pairs(tsd_icp_t* icp, const double* model, int32_t n_model, const double* scene, int32_t n_scene, const double pose[9],
+              uint32_t* pair_model, uint32_t* pair_scene, double* dist_sqr, uint32_t* n_pairs);
 /* Parity aid, off by default: record the pair list of every iteration (icp_get_trace). */
 int icp_set_trace(tsd_icp_t* icp, int enable);
 /* Parity aid: pair list, mse and accumulated 4x4 of every iteration of the last icp_run (tracing enabled).

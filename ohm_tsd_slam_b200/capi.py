@@ -34,7 +34,7 @@ EXPORTS = [
     "tsdg_band_rcx_export", "tsdg_band_rcx_connect", "tsdg_band_rcx_connect_local", "tsdg_raycast_mask_sharded",
     "tsdg_raycast_sharded_launch", "tsdg_raycast_sharded_collect",
     "tsdg_axis_aligned_map", "tsdg_color_image", "tsdg_store", "tsdg_load", "tsds_prepare_scan",
-    "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_set_trace", "icp_get_trace",
+    "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_pairs", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
 
@@ -113,6 +113,7 @@ def lib():
     L.icp_create.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_uint32, _dp, C.c_int, _vpp]
     L.icp_destroy.argtypes = [C.c_void_p]
     L.icp_run.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _up, _up, _ip]
+    L.icp_pairs.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, C.c_int32, _dp, _up, _up, _dp, _up]
     L.icp_set_termination.argtypes = [C.c_void_p, C.c_double, C.c_uint32]
     L.icp_set_max_iterations.argtypes = [C.c_void_p, C.c_uint32]
     L.icp_set_trace.argtypes = [C.c_void_p, C.c_int]
@@ -510,6 +511,18 @@ class Icp:
         check(lib().icp_run(self.h, _d(model), _d(normals), len(model), _d(scene), len(scene), _d(pose),
                             None if Ti is None else _d(Ti), _d(T), C.byref(mse), C.byref(pairs), C.byref(its), C.byref(st)))
         return T, mse.value, pairs.value, its.value, st.value
+
+    def pairs(self, model, scene, pose):
+        """PairAssignment::determinePairs on its own (icp_pairs): (model indices, scene indices, squared distances)."""
+        model, scene, pose = _f64(model), _f64(scene), _f64(pose)
+        cap = max(min(len(model), len(scene)), 1)
+        pm = np.zeros(cap, dtype=np.uint32)
+        ps = np.zeros(cap, dtype=np.uint32)
+        d = np.zeros(cap)
+        n = C.c_uint32()
+        check(lib().icp_pairs(self.h, _d(model), len(model), _d(scene), len(scene), _d(pose), pm.ctypes.data_as(_up),
+                              ps.ctypes.data_as(_up), _d(d), C.byref(n)))
+        return pm[:n.value].copy(), ps[:n.value].copy(), d[:n.value].copy()
 
     def trace(self, cap):
         mi = self.max_iterations

@@ -783,6 +783,48 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   return TSD_OK;
 }
 
+// PairAssignment::determinePairs on its own (assign/PairAssignment.cpp:38-84 with the node's filters: OutOfBoundsFilter2D
+// before, FlannPairAssignment::determinePairsSequential (FlannPairAssignment.cpp:64-92), DistanceFilter and
+// ReciprocalFilter after): the pair list of ONE pass over the scene as given -- the first step of Icp::iterate with an
+// identity initial guess and freshly reset filters.  Pairs come in model-index order (ReciprocalFilter.cpp:32-78).
+int icp_pairs(tsd_icp_t* h, const double* model, int32_t n_model, const double* scene, int32_t n_scene, const double pose[9],
+              uint32_t* pair_model, uint32_t* pair_scene, double* dist_sqr, uint32_t* n_pairs)
+{
+  TSD_LOCK(h);
+  if(!h || !pair_model || !pair_scene || !n_pairs || !pose) return TSD_E_INVALID;
+  *n_pairs = 0;
+  if(h->trace_cap_it < 1) { set_error("icp_pairs needs a handle created for at least one iteration"); return TSD_E_INVALID; }
+  const int keepIt = h->p.max_iterations, keepTrace = h->trace;
+  h->p.max_iterations = 1;
+  h->trace = 1;
+  double T[9], mse;
+  uint32_t pairs = 0, its = 0;
+  int32_t state = 0;
+  int rc = icp_run(h, model, nullptr, n_model, scene, n_scene, pose, nullptr, T, &mse, &pairs, &its, &state);
+  h->p.max_iterations = keepIt;
+  h->trace = keepTrace;
+  if(rc) return rc;
+  if(state == TSD_ICP_NOTMATCHABLE) return TSD_OK;  // empty model or scene: no pairs
+  int cnt = -1;
+  TSD_CUDA(cudaMemcpy(&cnt, h->d_tr_count, sizeof(int), cudaMemcpyDeviceToHost));
+  if(cnt <= 0) return TSD_OK;
+  TSD_CUDA(cudaMemcpy(pair_model, h->d_tr_model, sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost));
+  TSD_CUDA(cudaMemcpy(pair_scene, h->d_tr_scene, sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost));
+  if(dist_sqr)
+    for(int i = 0; i < cnt; i++)
+    {
+      // flann::L2: result += diff * diff, dimension by dimension
+      const double d0 = scene[2 * pair_scene[i]] - model[2 * pair_model[i]];
+      const double d1 = scene[2 * pair_scene[i] + 1] - model[2 * pair_model[i] + 1];
+      double d = 0.0;
+      d += d0 * d0;
+      d += d1 * d1;
+      dist_sqr[i] = d;
+    }
+  *n_pairs = (uint32_t)cnt;
+  return TSD_OK;
+}
+
 int icp_set_termination(tsd_icp_t* h, double max_rms, uint32_t convergence_counter)
 {
   TSD_LOCK(h);

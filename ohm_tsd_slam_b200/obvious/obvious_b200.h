@@ -639,16 +639,82 @@ public:
 class PairAssignment  // assign/PairAssignment.h
 {
 public:
-  PairAssignment(int dimension = 2) : _dimension(dimension) {}
-  virtual ~PairAssignment() {}
+  PairAssignment(int dimension = 2) : _dimension(dimension), _model(NULL), _sizeModel(0), _hp(NULL) {}
+  virtual ~PairAssignment() { icp_destroy(_hp); }
   void addPreFilter(IPreAssignmentFilter* filter) { _vPrefilter.push_back(filter); }
   void addPostFilter(IPostAssignmentFilter* filter) { _vPostfilter.push_back(filter); }
   int getDimension() { return _dimension; }
+  // PairAssignment.h:49-63.  The model pointer is borrowed, as in the reference (FlannPairAssignment.cpp:48-50).
+  virtual void setModel(double** model, int size) { _model = model; _sizeModel = size; }
+  // PairAssignment.cpp:38-84 used on its own (Icp::iterate does not come through here: it runs the whole loop in one
+  // kernel): pre-filter, exact nearest neighbours, post-filters in one pass on the device (icp_pairs).  Supports the
+  // filters the node wires (ThreadLocalize.cpp:212-221); any of them may be absent.
+  virtual void determinePairs(double** scene, bool* mask, int size)
+  {
+    _pairs.clear();
+    _distancesSqr.clear();
+    _nonPairs.clear();
+    if(!_model || _sizeModel < 1 || size < 1) return;
+    OutOfBoundsFilter2D* fb = NULL;
+    DistanceFilter* fd = NULL;
+    bool reciprocal = false;
+    for(size_t i = 0; i < _vPrefilter.size(); i++)
+      if(!fb) fb = dynamic_cast<OutOfBoundsFilter2D*>(_vPrefilter[i]);
+    for(size_t i = 0; i < _vPostfilter.size(); i++)
+    {
+      if(!fd) fd = dynamic_cast<DistanceFilter*>(_vPostfilter[i]);
+      if(dynamic_cast<ReciprocalFilter*>(_vPostfilter[i])) reciprocal = true;
+    }
+    // masked scene points do not take part (PairAssignment.cpp:49-58): compact, remember the original indices
+    std::vector<double> M(2 * (size_t)_sizeModel), S;
+    std::vector<unsigned int> idx;
+    for(int i = 0; i < _sizeModel; i++) { M[2 * i] = _model[i][0]; M[2 * i + 1] = _model[i][1]; }
+    for(int i = 0; i < size; i++)
+      if(!mask || mask[i]) { S.push_back(scene[i][0]); S.push_back(scene[i][1]); idx.push_back((unsigned int)i); }
+    if(idx.empty()) return;
+    const double inf = 1e150;
+    double bounds[4] = {-inf, inf, -inf, inf}, pose[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if(fb) { memcpy(bounds, fb->_b, sizeof(bounds)); fb->_T.getData(pose); }
+    const double dmax = fd ? fd->_max : 1e150, dmin = fd ? fd->_min : 1e150;
+    if(!_hp || memcmp(_hpB, bounds, sizeof(bounds)) != 0 || _hpMax != dmax || _hpMin != dmin)
+    {
+      icp_destroy(_hp);
+      _hp = NULL;
+      OBVIOUS_B200_CHECK(icp_create(1, dmax, dmin, fd ? fd->_it : 2, bounds, 0, &_hp));
+      memcpy(_hpB, bounds, sizeof(bounds)); _hpMax = dmax; _hpMin = dmin;
+    }
+    const size_t cap = std::min<size_t>((size_t)_sizeModel, idx.size());
+    std::vector<uint32_t> pm(cap), ps(cap);
+    std::vector<double> d(cap);
+    uint32_t n = 0;
+    OBVIOUS_B200_CHECK(icp_pairs(_hp, M.data(), _sizeModel, S.data(), (int32_t)idx.size(), pose, pm.data(), ps.data(), d.data(), &n));
+    (void)reciprocal;  // (the device pass always applies the reciprocal filter: the node's wiring)
+    for(uint32_t i = 0; i < n; i++)
+    {
+      StrCartesianIndexPair p;
+      p.indexFirst = pm[i];
+      p.indexSecond = idx[ps[i]];
+      _pairs.push_back(p);
+      _distancesSqr.push_back(d[i]);
+    }
+  }
+  void determinePairs(double** scene, int size) { determinePairs(scene, NULL, size); }
+  std::vector<StrCartesianIndexPair>* getPairs() { return &_pairs; }
+  std::vector<double>* getDistancesSqr() { return &_distancesSqr; }
+  std::vector<unsigned int>* getNonPairs() { return &_nonPairs; }
+  void reset() { _pairs.clear(); _distancesSqr.clear(); _nonPairs.clear(); }
   std::vector<IPreAssignmentFilter*> _vPrefilter;
   std::vector<IPostAssignmentFilter*> _vPostfilter;
 
 protected:
   int _dimension;
+  double** _model;
+  int _sizeModel;
+  std::vector<StrCartesianIndexPair> _pairs;
+  std::vector<double> _distancesSqr;
+  std::vector<unsigned int> _nonPairs;
+  tsd_icp_t* _hp;
+  double _hpB[4] = {0, 0, 0, 0}, _hpMax = 0, _hpMin = 0;
 };
 
 class FlannPairAssignment : public PairAssignment  // assign/FlannPairAssignment.h
