@@ -365,6 +365,33 @@ int match_score_pdf(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
                     const double* model_dists, const double params[12], double* prob, int32_t* fov_count,
                     int32_t* best, double t_best[9]);
 
+/* ------------------------------------------------------------------------------------------------
+ * One TsdGrid sharded over several devices INSIDE the library (one handle, one process; n_bands bands of whole
+ * partition rows, band i on devices[i], or on device i mod #devices when devices is NULL; several bands may share a
+ * device).  This is the handle behind obvious::TsdGrid(cellSize, layoutPartition, layoutGrid, nBands) in the adapter
+ * (the node constructs ONE grid, SlamNode.cpp:77).  Pushes run on every band a scan reaches, concurrently, without
+ * communication; the first read after pushes (ray cast, sampling, partition download) brings halo rows and allocation
+ * flags up to date over peer memory; the ray cast is the collective of tsdg_raycast_mask_sharded.  Every result equals the
+ * unsharded grid's bit for bit.  n_bands <= 16.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct tsd_sharded tsd_sharded_t;
+int tsdg_create_sharded(double cell_size, int layout_partition, int layout_grid, int n_bands, const int* devices,
+                        tsd_sharded_t** out);
+int tsdg_sharded_destroy(tsd_sharded_t* grid);
+int tsdg_sharded_num_bands(const tsd_sharded_t* grid);
+tsd_grid_t* tsdg_sharded_band(tsd_sharded_t* grid, int band);   /* a band's own handle (getters, per-band statistics) */
+int tsdg_sharded_set_max_truncation(tsd_sharded_t* grid, double val);                      /* TsdGrid::setMaxTruncation */
+int tsdg_sharded_free_footprint(tsd_sharded_t* grid, double cx, double cy, double w, double h);   /* TsdGrid::freeFootprint */
+int tsdg_sharded_push(tsd_sharded_t* grid, const tsd_scan_t* scan);                        /* TsdGrid::push, blocking */
+int tsdg_sharded_push_batch(tsd_sharded_t* grid, const tsd_scan_t* scans, int32_t n);
+int tsdg_sharded_sync(tsd_sharded_t* grid);                  /* halos + flags now (otherwise done by the first read) */
+int tsdg_sharded_last_push_stats(tsd_sharded_t* grid, tsd_push_stats_t* out);              /* summed over the bands */
+int tsdg_sharded_raycast_mask(tsd_sharded_t* grid, const tsd_scan_t* scan, const double* rays_world, double* coords,
+                              double* normals, uint8_t* mask, uint32_t* count);             /* calcCoordsFromCurrentViewMask */
+int tsdg_sharded_interpolate_bilinear(tsd_sharded_t* grid, int32_t n, const double* xy, double* tsd, int32_t* status);
+int tsdg_sharded_partition_states(tsd_sharded_t* grid, int32_t* state, double* init_weight);
+int tsdg_sharded_download_partition(tsd_sharded_t* grid, int32_t p, double* tsd, double* weight);
+
 #ifdef __cplusplus
 }
 #endif

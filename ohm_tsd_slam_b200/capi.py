@@ -34,6 +34,9 @@ EXPORTS = [
     "tsdg_band_rcx_export", "tsdg_band_rcx_connect", "tsdg_band_rcx_connect_local", "tsdg_raycast_mask_sharded",
     "tsdg_raycast_sharded_launch", "tsdg_raycast_sharded_collect",
     "tsdg_axis_aligned_map", "tsdg_color_image", "tsdg_store", "tsdg_load", "tsds_prepare_scan",
+    "tsdg_create_sharded", "tsdg_sharded_destroy", "tsdg_sharded_num_bands", "tsdg_sharded_band", "tsdg_sharded_set_max_truncation",
+    "tsdg_sharded_free_footprint", "tsdg_sharded_push", "tsdg_sharded_push_batch", "tsdg_sharded_sync", "tsdg_sharded_last_push_stats",
+    "tsdg_sharded_raycast_mask", "tsdg_sharded_interpolate_bilinear", "tsdg_sharded_partition_states", "tsdg_sharded_download_partition",
     "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_pairs", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
@@ -110,6 +113,21 @@ def lib():
     L.tsdg_raycast_mask.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _bp, _up]
     L.tsdg_raycast.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _up]
     L.tsdg_last_raycast_steps.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.tsdg_create_sharded.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _vpp]
+    L.tsdg_sharded_destroy.argtypes = [C.c_void_p]
+    L.tsdg_sharded_num_bands.argtypes = [C.c_void_p]
+    L.tsdg_sharded_band.argtypes = [C.c_void_p, C.c_int]
+    L.tsdg_sharded_band.restype = C.c_void_p
+    L.tsdg_sharded_set_max_truncation.argtypes = [C.c_void_p, C.c_double]
+    L.tsdg_sharded_free_footprint.argtypes = [C.c_void_p] + [C.c_double] * 4
+    L.tsdg_sharded_push.argtypes = [C.c_void_p, _sp]
+    L.tsdg_sharded_push_batch.argtypes = [C.c_void_p, _sp, C.c_int32]
+    L.tsdg_sharded_sync.argtypes = [C.c_void_p]
+    L.tsdg_sharded_last_push_stats.argtypes = [C.c_void_p, C.POINTER(PushStats)]
+    L.tsdg_sharded_raycast_mask.argtypes = [C.c_void_p, _sp, _dp, _dp, _dp, _bp, _up]
+    L.tsdg_sharded_interpolate_bilinear.argtypes = [C.c_void_p, C.c_int32, _dp, _dp, _ip]
+    L.tsdg_sharded_partition_states.argtypes = [C.c_void_p, _ip, _dp]
+    L.tsdg_sharded_download_partition.argtypes = [C.c_void_p, C.c_int32, _dp, _dp]
     L.icp_create.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_uint32, _dp, C.c_int, _vpp]
     L.icp_destroy.argtypes = [C.c_void_p]
     L.icp_run.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _up, _up, _ip]
@@ -209,7 +227,8 @@ class Grid:
 
     def close(self):
         if getattr(self, "h", None):
-            lib().tsdg_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                lib().tsdg_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -474,6 +493,93 @@ class Grid:
         a, b = C.c_uint64(), C.c_uint64()
         check(lib().tsdg_last_raycast_steps(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+class ShardedGrid:
+    """tsd_sharded_t: one TsdGrid in n_bands bands of partition rows, one handle, one process (csrc/sharded.cu)."""
+
+    def __init__(self, cell_size: float, layout_partition: int, layout_grid: int, n_bands: int, devices=None):
+        self.h = C.c_void_p()
+        dev = None if devices is None else (C.c_int * n_bands)(*devices)
+        check(lib().tsdg_create_sharded(cell_size, layout_partition, layout_grid, n_bands, dev, C.byref(self.h)))
+        self.cell_size = cell_size
+        self.n_bands = lib().tsdg_sharded_num_bands(self.h)
+        self.parts_x = (1 << layout_grid) // 32
+        self.n_parts = self.parts_x * self.parts_x
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().tsdg_sharded_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def band(self, i: int) -> "Grid":
+        """A view of band i's own handle (not owned: do not close)."""
+        g = Grid.__new__(Grid)
+        g.h = C.c_void_p(lib().tsdg_sharded_band(self.h, i))
+        g._borrowed = True
+        return g
+
+    def set_max_truncation(self, v):
+        check(lib().tsdg_sharded_set_max_truncation(self.h, v))
+
+    def free_footprint(self, cx, cy, w, h) -> bool:
+        rc = lib().tsdg_sharded_free_footprint(self.h, cx, cy, w, h)
+        if rc == -5:
+            return False
+        check(rc)
+        return True
+
+    def push(self, scan: Scan):
+        check(lib().tsdg_sharded_push(self.h, scan.byref()))
+
+    def push_batch(self, scans):
+        arr = Grid._scan_array(scans)
+        check(lib().tsdg_sharded_push_batch(self.h, arr, len(arr)))
+
+    def sync(self):
+        check(lib().tsdg_sharded_sync(self.h))
+
+    def last_push_stats(self):
+        st = PushStats()
+        check(lib().tsdg_sharded_last_push_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def raycast_mask(self, scan: Scan, rays_world, coords=None, normals=None):
+        n = scan.n
+        rays = _f64(rays_world)
+        coords = np.zeros((n, 2)) if coords is None else coords
+        normals = np.zeros((n, 2)) if normals is None else normals
+        mask = np.zeros(n, dtype=np.uint8)
+        cnt = C.c_uint32()
+        check(lib().tsdg_sharded_raycast_mask(self.h, scan.byref(), _d(rays), _d(coords), _d(normals), mask.ctypes.data_as(_bp),
+                                              C.byref(cnt)))
+        return coords, normals, mask, int(cnt.value)
+
+    def interpolate_bilinear(self, xy):
+        xy = _f64(xy)
+        tsd = np.empty(len(xy))
+        st = np.empty(len(xy), dtype=np.int32)
+        check(lib().tsdg_sharded_interpolate_bilinear(self.h, len(xy), _d(xy), _d(tsd), st.ctypes.data_as(_ip)))
+        return tsd, st
+
+    def partition_states(self):
+        st = np.empty(self.n_parts, dtype=np.int32)
+        iw = np.empty(self.n_parts)
+        check(lib().tsdg_sharded_partition_states(self.h, st.ctypes.data_as(_ip), _d(iw)))
+        return st, iw
+
+    def download_partition(self, p: int):
+        t = np.empty(33 * 33)
+        w = np.empty(33 * 33)
+        if lib().tsdg_sharded_download_partition(self.h, p, _d(t), _d(w)) != 0:
+            return None
+        return t.reshape(33, 33), w.reshape(33, 33)
 
 
 class Icp:

@@ -11,6 +11,7 @@
 //
 // Each class cites the reference interface it replaces.
 #pragma once
+#define OBVIOUS_B200_H 1
 
 #include <math.h>
 #include <stdio.h>
@@ -397,13 +398,25 @@ class TsdGrid
 public:
   // TsdGrid.cpp:20-23 (SlamNode.cpp:77).  `device` is the only addition: the CUDA ordinal, default 0.
   TsdGrid(const obfloat cellSize, const EnumTsdGridLayout layoutPartition, const EnumTsdGridLayout layoutGrid, int device = 0)
-      : _h(NULL), _pushed(false)
+      : _h(NULL), _sh(NULL), _pushed(false)
   {
     OBVIOUS_B200_CHECK(tsdg_create(cellSize, (int)layoutPartition, (int)layoutGrid, device, &_h));
     refresh();
   }
+  // Not in the reference: the same grid sharded over nBands bands of partition rows inside the library, band i on
+  // devices[i] (NULL: device i mod #devices).  push / pushBatch / RayCastPolar2D / interpolateBilinear / freeFootprint
+  // return what the unsharded grid returns, bit for bit; the publisher's calls (RayCastAxisAligned2D, grid2ColorImage),
+  // interpolateNormal, storeGrid and TSD_PDFMatching want an unsharded grid and say so.
+  TsdGrid(const obfloat cellSize, const EnumTsdGridLayout layoutPartition, const EnumTsdGridLayout layoutGrid, int nBands,
+          const int* devices)
+      : _h(NULL), _sh(NULL), _pushed(false)
+  {
+    OBVIOUS_B200_CHECK(tsdg_create_sharded(cellSize, (int)layoutPartition, (int)layoutGrid, nBands, devices, &_sh));
+    _h = tsdg_sharded_band(_sh, 0);  // geometry getters
+    refresh();
+  }
   // TsdGrid.cpp:25-110: a grid from a file written by storeGrid (FILE_SOURCE only)
-  TsdGrid(const std::string& data, const EnumTsdGridLoadSource source = FILE_SOURCE, int device = 0) : _h(NULL), _pushed(false)
+  TsdGrid(const std::string& data, const EnumTsdGridLoadSource source = FILE_SOURCE, int device = 0) : _h(NULL), _sh(NULL), _pushed(false)
   {
     if(source != FILE_SOURCE)
     {
@@ -422,9 +435,14 @@ public:
   bool storeGrid(const std::string& path)
   {
     if(!path.size()) return false;
+    unsharded("storeGrid");
     return tsdg_store(_h, path.c_str()) == TSD_OK;
   }
-  virtual ~TsdGrid() { tsdg_destroy(_h); }
+  virtual ~TsdGrid()
+  {
+    if(_sh) tsdg_sharded_destroy(_sh);
+    else tsdg_destroy(_h);
+  }
   TsdGrid(const TsdGrid&) = delete;
   TsdGrid& operator=(const TsdGrid&) = delete;
 
@@ -443,7 +461,8 @@ public:
   }
   void setMaxTruncation(const double val)
   {
-    OBVIOUS_B200_CHECK(tsdg_set_max_truncation(_h, val));
+    if(_sh) OBVIOUS_B200_CHECK(tsdg_sharded_set_max_truncation(_sh, val));
+    else OBVIOUS_B200_CHECK(tsdg_set_max_truncation(_h, val));
     refresh();
   }
   double getMaxTruncation() const { return _maxTruncation; }
@@ -453,7 +472,8 @@ public:
     tsd_scan_t s;
     std::vector<uint8_t> m;
     sensor->snapshot(&s, &m);
-    OBVIOUS_B200_CHECK(tsdg_push(_h, &s));
+    if(_sh) OBVIOUS_B200_CHECK(tsdg_sharded_push(_sh, &s));
+    else OBVIOUS_B200_CHECK(tsdg_push(_h, &s));
     _pushed = true;
   }
   // Not in the reference: every queued sensor in one call, with the result of push() on each in turn.
@@ -465,7 +485,8 @@ public:
     std::vector<tsd_scan_t> s(sensors.size());
     std::vector<std::vector<uint8_t> > m(sensors.size());
     for(size_t i = 0; i < sensors.size(); i++) sensors[i]->snapshot(&s[i], &m[i]);
-    OBVIOUS_B200_CHECK(tsdg_push_batch(_h, s.data(), (int32_t)s.size()));
+    if(_sh) OBVIOUS_B200_CHECK(tsdg_sharded_push_batch(_sh, s.data(), (int32_t)s.size()));
+    else OBVIOUS_B200_CHECK(tsdg_push_batch(_h, s.data(), (int32_t)s.size()));
     _pushed = true;
   }
   bool containsData() { return _pushed; }
@@ -474,7 +495,8 @@ public:
   {
     int32_t st = 0;
     double v = NAN;
-    OBVIOUS_B200_CHECK(tsdg_interpolate_bilinear(_h, 1, coord, &v, &st));
+    if(_sh) OBVIOUS_B200_CHECK(tsdg_sharded_interpolate_bilinear(_sh, 1, coord, &v, &st));
+    else OBVIOUS_B200_CHECK(tsdg_interpolate_bilinear(_h, 1, coord, &v, &st));
     if(st == INTERPOLATE_SUCCESS || st == INTERPOLATE_ISNAN) *tsd = v;
     return (EnumTsdGridInterpolate)st;
   }
@@ -483,6 +505,7 @@ public:
   {
     int32_t ok = 0;
     double n[2];
+    unsharded("interpolateNormal");
     OBVIOUS_B200_CHECK(tsdg_interpolate_normal(_h, 1, coord, n, &ok));
     if(ok) { normal[0] = n[0]; normal[1] = n[1]; }
     return ok != 0;
@@ -497,7 +520,8 @@ public:
   // TsdGrid.cpp:609-638
   bool freeFootprint(const obfloat centerCoords[2], const obfloat width, const obfloat height)
   {
-    const int rc = tsdg_free_footprint(_h, centerCoords[0], centerCoords[1], width, height);
+    const int rc = _sh ? tsdg_sharded_free_footprint(_sh, centerCoords[0], centerCoords[1], width, height)
+                       : tsdg_free_footprint(_h, centerCoords[0], centerCoords[1], width, height);
     if(rc == TSD_E_RANGE) return false;
     OBVIOUS_B200_CHECK(rc);
     return true;
@@ -505,9 +529,16 @@ public:
   // TsdGrid.cpp:429-488 (ThreadGrid.cpp:125)
   void grid2ColorImage(unsigned char* image, unsigned int width, unsigned int height)
   {
+    unsharded("grid2ColorImage");
     OBVIOUS_B200_CHECK(tsdg_color_image(_h, image, width, height));
   }
-  tsd_grid_t* handle() const { return _h; }
+  // the unsharded handle (the calls that take one do not work on a sharded grid)
+  tsd_grid_t* handle() const
+  {
+    unsharded("this call");
+    return _h;
+  }
+  tsd_sharded_t* shardedHandle() const { return _sh; }
 
 private:
   void refresh()
@@ -515,7 +546,13 @@ private:
     OBVIOUS_B200_CHECK(tsdg_get_geometry(_h, &_cellsX, &_cellsY, &_partSize, &_cellSize, &_minX, &_maxX, &_minY, &_maxY,
                                          &_maxTruncation));
   }
+  void unsharded(const char* what) const
+  {
+    if(!_sh) return;
+    throw std::runtime_error(std::string("obvious_b200: ") + what + " needs an unsharded TsdGrid");
+  }
   tsd_grid_t* _h;
+  tsd_sharded_t* _sh;
   int32_t _cellsX, _cellsY, _partSize;
   double _cellSize, _minX, _maxX, _minY, _maxY, _maxTruncation;
   bool _pushed;
@@ -538,7 +575,10 @@ public:
     Matrix* R = sensor->getNormalizedRayMap(grid->getCellSize());
     std::vector<uint8_t> hit(s.n);
     uint32_t cnt = 0;
-    OBVIOUS_B200_CHECK(tsdg_raycast_mask(grid->handle(), &s, R->data(), coords, normals, hit.data(), &cnt));
+    if(grid->shardedHandle())
+      OBVIOUS_B200_CHECK(tsdg_sharded_raycast_mask(grid->shardedHandle(), &s, R->data(), coords, normals, hit.data(), &cnt));
+    else
+      OBVIOUS_B200_CHECK(tsdg_raycast_mask(grid->handle(), &s, R->data(), coords, normals, hit.data(), &cnt));
     for(int i = 0; i < s.n; i++) mask[i] = hit[i] != 0;
     return cnt;
   }

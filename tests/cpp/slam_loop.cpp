@@ -50,7 +50,17 @@ int main(int argc, char** argv)
   LOGMSG_CONF("slam.log", obvious::Logger::file_off | obvious::Logger::screen_off, DBG_DEBUG, DBG_DEBUG);  // src/slam.cpp:17
 
   // SlamNode.cpp:77-78
-  obvious::TsdGrid* grid = new obvious::TsdGrid(cellSize, obvious::LAYOUT_32x32, (obvious::EnumTsdGridLayout)layoutGrid);
+  obvious::TsdGrid* grid = NULL;
+  bool sharded = false;
+#ifdef OBVIOUS_B200_H
+  // adapter build only: SLAM_LOOP_BANDS=n runs the same loop on a grid sharded in n bands inside the library
+  if(getenv("SLAM_LOOP_BANDS"))
+  {
+    grid = new obvious::TsdGrid(cellSize, obvious::LAYOUT_32x32, (obvious::EnumTsdGridLayout)layoutGrid, atoi(getenv("SLAM_LOOP_BANDS")), NULL);
+    sharded = true;
+  }
+#endif
+  if(!grid) grid = new obvious::TsdGrid(cellSize, obvious::LAYOUT_32x32, (obvious::EnumTsdGridLayout)layoutGrid);
   grid->setMaxTruncation(truncCells * cellSize);
 
   // ThreadLocalize ctor, ThreadLocalize.cpp:205-225
@@ -133,6 +143,7 @@ int main(int argc, char** argv)
     k++;
   }
   fclose(f);
+  if(!sharded)  // the publisher's calls want an unsharded grid
   {
     // what ThreadGrid::eventLoop does with the map (ThreadGrid.cpp:17-28, :84, :125): crossings + occupancy grid,
     // colour image.  One summary line: -1 <crossings> <sum x> <sum y> <free cells> <image byte sum> 0

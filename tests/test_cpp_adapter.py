@@ -31,9 +31,12 @@ def build_exe():
     return EXE
 
 
-def run(name, mode):
+def run(name, mode, bands=None):
+    env = dict(os.environ)
+    if bands:
+        env["SLAM_LOOP_BANDS"] = str(bands)
     out = subprocess.run([build_exe(), os.path.join(ROOT, "tests", "golden", f"scans_{name}.bin")] + ARGS[name] + [str(mode)],
-                         capture_output=True, text=True, timeout=300)
+                         capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr
     return np.array([[float(v) for v in line.split()] for line in out.stdout.strip().splitlines()])
 
@@ -67,6 +70,16 @@ def test_slam_loop_tracks_reference_poses(name):
     assert pub_got[0] == -1 and abs(pub_got[1] - pub_ref[1]) <= 2
     assert np.max(np.abs(pub_got[2:4] - pub_ref[2:4]) / pub_ref[2:4]) < 1e-3
     assert abs(pub_got[4] - pub_ref[4]) <= 8 and abs(pub_got[5] - pub_ref[5]) / pub_ref[5] < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,bands", [("tiny", 2), ("C1", 4)])
+def test_slam_loop_on_a_sharded_grid_is_identical(name, bands):
+    """obvious::TsdGrid(cellSize, layoutPartition, layoutGrid, nBands, devices): the node's loop on a grid sharded inside
+    the library prints the same poses, digit for digit, as on the unsharded grid."""
+    a = run(name, 0)[:-1]
+    b = run(name, 0, bands=bands)
+    assert a.shape == b.shape and np.array_equal(a, b)
 
 
 @pytest.mark.gpu

@@ -112,3 +112,49 @@ def test_batched_pushes_on_bands():
     parts.sync_halos()
     ok, lines = compare_grids(whole, parts)
     assert ok, lines
+
+
+@pytest.mark.parametrize("name,bands", [("tiny", 2), ("C1", 1), ("C1", 3), ("C1", 7)])
+def test_library_sharded_handle_equals_single_grid(name, bands):
+    """tsdg_create_sharded (csrc/sharded.cu): the SLAM loop -- ray cast from the current pose, sample, push -- on ONE
+    handle whose bands, halos, flags and ray-cast exchange live inside the library; every result equals the unsharded
+    grid's bit for bit, reads synchronising lazily after the pushes."""
+    cfg = synth.config(name)
+    whole = capi.Grid(cfg.cell_size, 5, cfg.layout_grid)
+    parts = capi.ShardedGrid(cfg.cell_size, 5, cfg.layout_grid, bands)
+    assert parts.n_bands == bands
+    whole.set_max_truncation(cfg.max_truncation)
+    parts.set_max_truncation(cfg.max_truncation)
+    hs = HostSensor(cfg.sensor, capi.invert3x3)
+    scans = list(cfg.scans(8))
+    (x, y, th), r0 = scans[0]
+    assert whole.free_footprint(x, y, 0.6, 0.6) and parts.free_footprint(x, y, 0.6, 0.6)
+    assert not whole.free_footprint(-50.0, -50.0, 0.6, 0.6) and not parts.free_footprint(-50.0, -50.0, 0.6, 0.6)
+    rng = np.random.default_rng(5)
+    side = cfg.cell_size * (1 << cfg.layout_grid)
+    for k, (pose, r) in enumerate(scans):
+        hs.set_scan(r)
+        hs.T = synth.pose_matrix(*pose)
+        sc = hs.scan()
+        if k > 0:
+            rays = hs.normalized_rays(cfg.cell_size).copy()
+            c1, n1, m1, k1 = whole.raycast_mask(sc, rays)
+            c2, n2, m2, k2 = parts.raycast_mask(sc, rays)
+            assert same(m1, m2) and k1 == k2 and k1 > 0
+            assert same(c1[m1 > 0], c2[m2 > 0]) and same(n1[m1 > 0], n2[m2 > 0])
+            xy = np.concatenate([c1[m1 > 0] + rng.normal(0, 0.03, (k1, 2)), rng.uniform(-0.1 * side, 1.1 * side, (200, 2))])
+            t1, s1 = whole.interpolate_bilinear(xy)
+            t2, s2 = parts.interpolate_bilinear(xy)
+            assert same(s1, s2) and same(t1[s1 == 0], t2[s2 == 0]) and (s1 == 0).sum() > 0
+        if k % 3 == 2:
+            whole.push(sc)
+            whole.push(sc)
+            parts.push_batch([sc, sc])
+        else:
+            whole.push(sc)
+            parts.push(sc)
+            a, b = whole.last_push_stats(), parts.last_push_stats()
+            assert a["cell_updates"] == b["cell_updates"] and a["active_tiles"] == b["active_tiles"]
+    ok, lines = compare_grids(whole, parts)
+    assert ok, lines
+    parts.close()
