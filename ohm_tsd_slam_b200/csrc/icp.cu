@@ -18,9 +18,10 @@
 //
 // Work split and communication inside the cluster: see k_icp.
 //
-// Sums of the estimator are block reductions with a fixed tree, so results are deterministic but not
-// bit-identical to the reference's sequential sums (and atan2/sin/cos differ from glibc in the last ulp
-// anyway): pair lists are compared exactly, poses to 1e-9 (tests/test_icp_gpu.py).
+// Sums of the estimator are block reductions with a fixed tree (over the model points in hash-slot order), taken
+// about a provisional centre and corrected exactly, and the rotation's cos / sin come from the sums directly instead of
+// through atan2: results are deterministic -- the same bits on every run and in every CTA -- but not bit-identical to
+// the reference's sequential sums.  Pair lists are compared exactly, poses to 1e-9 (tests/test_gpu_parity.py).
 #include <string.h>
 
 #include <vector>
@@ -31,9 +32,14 @@
 
 using namespace tsd;
 
-#define ICP_THREADS 1024
+#ifndef ICP_THREADS
+#define ICP_THREADS 256   // per CTA.  An iteration is a dozen short phases that every warp walks through, and most of what a CTA
+                          // issues is that walk, not work: measured per CTA and iteration, 1024 threads issue 21 k warp
+                          // instructions, 256 threads 6 k, for the same pairs (at most 256 queries per CTA either way)
+#endif
 #define ICP_MAX_POINTS 2048
 #define ICP_SLOTS 4096  // hash buckets
+#define ICP_SUM_THREADS 256  // threads that walk the model points for the estimator's sums
 #ifndef ICP_CLUSTER
 #define ICP_CLUSTER 8   // CTAs (SMs) per registration: the portable cluster size
 #endif
@@ -145,106 +151,190 @@ __device__ __forceinline__ void dsmem_st_u32(uint32_t addr, unsigned v)
 {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+#ifdef ICP_PROFILE
+#define ICP_STAMP(k) { const long long now__ = clock64(); pf[k] += now__ - pf_t; pf_t = now__; }
+#else
+#define ICP_STAMP(k)
+#endif
+__device__ __forceinline__ void st_release_cluster(uint32_t addr, unsigned v)
+{
+  asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_cluster(const unsigned* own_smem)
+{
+  unsigned v;
+  asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(own_smem)) : "memory");
+  return v;
+}
+
 // One thread-block CLUSTER of ICP_CLUSTER CTAs (one SM each) runs the whole loop.  Every CTA keeps the model, its
-// search structure, the scene and the transformation in its own shared memory and evolves them identically
-// (same code, same data, same reduction trees), so no state is ever broadcast.  What is split is the expensive
-// part, the nearest-neighbour search: query i belongs to CTA i % ICP_CLUSTER, and four lanes share a query (the
-// cells of a ring are dealt round-robin to the lanes, then two shuffles pick the winner).  The reciprocal filter
-// (closest scene point per model point) is reduced in two levels: every CTA filters its own queries with
-// shared-memory atomics and stores each local winner into the inbox of model point m's host, CTA m % ICP_CLUSTER
-// (distributed shared memory, one 16-byte store); the host keeps the best of its ICP_CLUSTER candidates and stores
-// the final winner into every CTA's copy.  Two cluster barriers per iteration:
-//      NN search, local reciprocal filter, local winners -> hosts' inboxes   | cluster.sync |
-//      hosts pick (best distance, lowest scene index), winners -> every CTA   | cluster.sync |
-//      estimator sums over the winners, pose update, scene transform -- replicated, identical in every CTA
+// search structure, the scene and the transformation in its own shared memory and evolves them identically (same
+// code, same data, same reduction trees), so no state is ever broadcast.  What is split is the nearest-neighbour
+// search, the one part of an iteration that is instructions rather than latency (measured: one SM alone issues
+// 17 k cycles of it per iteration on the C3 input, eight SMs 4 k): query i belongs to CTA i % ICP_CLUSTER, one lane
+// per query.
+//   * search: the previous iteration's neighbour seeds the bound; a lane first finds out which cells it has to open at
+//     all (its own, then the neighbours that are occupied and not farther than the bound -- a cell is skipped only if
+//     it is STRICTLY farther, so the result and the lowest-index tie rule are those of the full search), then walks
+//     its own short list: a warp runs as many rounds as its busiest lane has cells, not nine.  The few queries without
+//     a model point within one cell edge are finished by their whole warp (window of the distance filter's radius).
+//   * exchange: every lane stores its result {distance, model index} into EVERY CTA's copy of the result table
+//     (16-byte st.shared::cluster), then one thread per peer releases a flag in that peer's shared memory and every
+//     CTA waits for its ICP_CLUSTER flags -- no cluster-wide barrier of 8192 threads, no second round.  Tables are
+//     double-buffered by iteration parity: a CTA can only get two iterations ahead of the slowest reader.
+//   * reciprocal filter, estimator, pose update and scene transform are replicated.  The estimator is ONE reduction:
+//     centroids and cross sums in one pass, the cross sums taken about a provisional centre c' (last iteration's
+//     centroids) and corrected exactly: sum (a - c)(b - d) = sum (a - c')(b - d') - n (c - c')(d - d'); only
+//     ICP_SUM_THREADS threads walk the model points so that few warps pay for the 64-bit shuffle trees; cos and sin
+//     of atan2(n0, n1) are n1 / |n| and n0 / |n|.
+// Per iteration: one flag exchange and five block barriers.  (History, cycles per iteration on C3, 869 model / 686
+// scene points: two-level reciprocal filter with two cluster barriers and a two-pass estimator 25 k; everything on
+// one CTA 25 k, of which 17 k search.)
+struct IcpSmem
+{
+  double *mx, *my, *sx, *sy, *lb, *red, *T, *part, *pbd;
+  unsigned short *pend, *pos;
+  ulonglong2* nnd;
+  unsigned long long* best;
+  unsigned *win, *scan, *coarse, *occ, *flag;
+  int* prev;
+  unsigned short *bstart, *bcnt, *bidx;
+};
+__device__ __forceinline__ IcpSmem icp_carve(unsigned char* smem, int nM, int nS)
+{
+  IcpSmem S;
+  S.mx = reinterpret_cast<double*>(smem);
+  S.my = S.mx + nM;
+  S.sx = S.my + nM;
+  S.sy = S.sx + nS;
+  S.nnd = reinterpret_cast<ulonglong2*>(S.sy + nS);               // 2 x nS: {distance bits, model index} of every query, by parity
+  S.lb = reinterpret_cast<double*>(S.nnd + 2 * (size_t)nS);      // nQ: own queries
+  S.pbd = S.lb + (nS + ICP_CLUSTER - 1) / ICP_CLUSTER;            // nQ: bound of a far query before its window scan
+  S.red = S.pbd + (nS + ICP_CLUSTER - 1) / ICP_CLUSTER;                                              // 320 partials + 16 results
+  S.part = S.red + 336;                                           // 7 x ICP_SUM_THREADS partial sums
+  S.T = S.part + 7 * ICP_SUM_THREADS;                                              // Tfinal 16, Tlast 16
+  S.best = reinterpret_cast<unsigned long long*>(S.T + 32);       // nM
+  S.win = reinterpret_cast<unsigned*>(S.best + nM);               // nM
+  S.prev = reinterpret_cast<int*>(S.win + nM);                    // nQ: own queries
+  S.flag = reinterpret_cast<unsigned*>(S.prev + (nS + ICP_CLUSTER - 1) / ICP_CLUSTER);  // ICP_CLUSTER
+  S.scan = S.flag + ICP_CLUSTER;                                  // 40 + 32
+  S.coarse = S.scan + 72;                                         // 128
+  S.occ = S.coarse + 128;                                         // 128
+  S.bstart = reinterpret_cast<unsigned short*>(S.occ + 128);      // ICP_SLOTS + 2
+  S.bcnt = S.bstart + (ICP_SLOTS + 2);                            // ICP_SLOTS
+  S.pend = S.bcnt + ICP_SLOTS;                                    // nQ (+ pad): far queries of this iteration
+  S.bidx = S.pend + (((nS + ICP_CLUSTER - 1) / ICP_CLUSTER + 2) & ~1);
+  S.pos = S.bidx + ((nM + 2) & ~1);                                    // nM (+ pad)
+  return S;
+}
+static size_t icp_smem_bytes(int nM, int nS)
+{
+  const size_t nQ = ((size_t)nS + ICP_CLUSTER - 1) / ICP_CLUSTER;
+  size_t b = sizeof(double) * (2 * (size_t)nM + 2 * (size_t)nS + 2 * nQ + 336 + 7 * ICP_SUM_THREADS + 32) + 32 * (size_t)nS;  // mx my sx sy lb red T, nnd
+  b += 8 * (size_t)nM + 4 * (size_t)nM + 4 * nQ + 4 * (ICP_CLUSTER + 72 + 256);                    // best win prev flag scan coarse occ
+  b += 2 * ((size_t)ICP_SLOTS + 2 + ICP_SLOTS + 2 * ((size_t)nM + 2) + nQ + 2);
+  return b + 64;
+}
+
 __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREADS, 1) k_icp(IcpParams P)
 {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   extern __shared__ __align__(16) unsigned char smem[];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nM = P.nM, nS = P.nS;
-  const int nQ = (nS + ICP_CLUSTER - 1) / ICP_CLUSTER;  // queries per CTA (upper bound)
-  const int nH = (nM + ICP_CLUSTER - 1) / ICP_CLUSTER;  // model points hosted per CTA (upper bound)
-  // shared memory carve-up (identical in every CTA, so that map_shared_rank offsets agree)
-  double* s_mx = reinterpret_cast<double*>(smem);
-  double* s_my = s_mx + nM;
-  double* s_sx = s_my + nM;
-  double* s_sy = s_sx + nS;
-  double* s_d2 = s_sy + nS;                                                        // nQ: own queries
-  double* s_lb = s_d2 + nQ;                                                        // nQ: lower bound of the NN distance
-  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_lb + nQ);  // nM: over this CTA's queries
-  double* s_red = reinterpret_cast<double*>(s_best + nM);                          // 208
-  double* s_T = s_red + 208;                                                       // Tfinal 16, Tlast 16
-  unsigned* s_win = reinterpret_cast<unsigned*>(s_T + 32);                         // nM: over this CTA's queries
-  unsigned* s_fin = s_win + nM;                                                    // nM: final winner of every model point
-  int* s_nn = reinterpret_cast<int*>(s_fin + nM);                                  // nQ
-  unsigned* s_scan = reinterpret_cast<unsigned*>(s_nn + nQ);                       // 40
-  unsigned short* s_bstart = reinterpret_cast<unsigned short*>(s_scan + 40);       // ICP_SLOTS + 2
-  unsigned short* s_bcnt = s_bstart + (ICP_SLOTS + 2);                             // ICP_SLOTS
-  unsigned short* s_bidx = s_bcnt + ICP_SLOTS;                                     // nM (+1 pad)
-  unsigned* s_coarse = reinterpret_cast<unsigned*>(s_bidx + ((nM + 2) & ~1));      // 128 words: coarse occupancy bitmap
-  unsigned* s_occ = s_coarse + 128;                                                // 128 words: non-empty hash slots
-  // candidates sent to this host: ICP_CLUSTER x nH entries {distance bits, scene index}, one 16-byte store each
-  ulonglong2* s_inbox = reinterpret_cast<ulonglong2*>((reinterpret_cast<uintptr_t>(s_occ + 128) + 15) & ~(uintptr_t)15);
-
+  const int nQ = (nS + ICP_CLUSTER - 1) / ICP_CLUSTER;  // queries of this CTA (upper bound)
+  const IcpSmem S = icp_carve(smem, nM, nS);
+  double* const s_mx = S.mx; double* const s_my = S.my; double* const s_sx = S.sx; double* const s_sy = S.sy;
   const unsigned long long INF64 = 0xffffffffffffffffULL;
-  for(int i = tid; i < nM; i += ICP_THREADS) { s_mx[i] = P.model[2 * i]; s_my[i] = P.model[2 * i + 1]; }
-  for(int i = tid; i < nS; i += ICP_THREADS) { s_sx[i] = P.scene[2 * i]; s_sy[i] = P.scene[2 * i + 1]; }
-  for(int i = tid; i < nQ; i += ICP_THREADS) s_lb[i] = 0.0;
-  for(int i = tid; i < ICP_CLUSTER * nH; i += ICP_THREADS) s_inbox[i] = make_ulonglong2(INF64, 0xffffffffULL);
-  for(int i = tid; i < ICP_SLOTS; i += ICP_THREADS) s_bcnt[i] = 0;
-  if(tid < 128) { s_coarse[tid] = 0u; s_occ[tid] = 0u; }
-  if(tid < 16) { s_T[tid] = (tid % 5 == 0) ? 1.0 : 0.0; s_T[16 + tid] = s_T[tid]; }
+  for(int i = tid; i < nM; i += ICP_THREADS) { S.best[i] = INF64; S.win[i] = 0xffffffffu; }
+  for(int i = tid; i < nS; i += ICP_THREADS)
+  {
+    s_sx[i] = P.scene[2 * i]; s_sy[i] = P.scene[2 * i + 1];
+  }
+  for(int i = tid; i < nQ; i += ICP_THREADS) { S.lb[i] = 0.0; S.prev[i] = -1; }
+  if(tid < ICP_CLUSTER) S.flag[tid] = 0u;
+  if(tid == 0) S.scan[64] = 0u;
+  for(int i = tid; i < ICP_SLOTS; i += ICP_THREADS) S.bcnt[i] = 0;
+  if(tid < 128) { S.coarse[tid] = 0u; S.occ[tid] = 0u; }
+  if(tid < 16) { S.T[tid] = (tid % 5 == 0) ? 1.0 : 0.0; S.T[16 + tid] = S.T[tid]; }
   __syncthreads();
 
-  // ---- spatial hash of the model: counting sort of the points by hash slot (built by every CTA for itself) ----
+  // ---- spatial hash of the model: counting sort of the points by hash slot ----
   const double h = P.hash_h, invh = 1.0 / P.hash_h;
-  const double invhc = 1.0 / P.coarse_h;  // coarse cells: edge >= the distance filter's largest threshold
-  const double bx0 = s_mx[0], by0 = s_my[0];
+  const double invhc = 1.0 / P.coarse_h;
+  // The model is kept SORTED by hash slot (ties: by index), and from here on a model point is known by its position in
+  // that order: the points of a cell are consecutive in memory, so the search reads coordinates without the detour over
+  // an index list.  S.bidx[p] is the index the caller knows the point by (the tie rule and the pair lists use it).
+  const double bx0 = P.model[0], by0 = P.model[1];
   for(int i = tid; i < nM; i += ICP_THREADS)
   {
-    const unsigned b = slot_of(cell_of(s_mx[i], bx0, invh), cell_of(s_my[i], by0, invh));
-    atomicAdd(reinterpret_cast<unsigned*>(s_bcnt) + (b >> 1), (b & 1) ? 0x10000u : 1u);  // u16 counters, nM <= 2048
-    const unsigned c = slot_of(cell_of(s_mx[i], bx0, invhc), cell_of(s_my[i], by0, invhc));
-    atomicOr(&s_coarse[c >> 5], 1u << (c & 31));
-    atomicOr(&s_occ[b >> 5], 1u << (b & 31));
+    const double mxi = P.model[2 * i], myi = P.model[2 * i + 1];
+    const unsigned b = slot_of(cell_of(mxi, bx0, invh), cell_of(myi, by0, invh));
+    atomicAdd(reinterpret_cast<unsigned*>(S.bcnt) + (b >> 1), (b & 1) ? 0x10000u : 1u);
+    const unsigned c = slot_of(cell_of(mxi, bx0, invhc), cell_of(myi, by0, invhc));
+    atomicOr(&S.coarse[c >> 5], 1u << (c & 31));
+    atomicOr(&S.occ[b >> 5], 1u << (b & 31));
   }
   __syncthreads();
   {
-    // exclusive prefix over ICP_SLOTS = 4 * ICP_THREADS counters
-    const unsigned c0 = s_bcnt[4 * tid], c1 = s_bcnt[4 * tid + 1], c2 = s_bcnt[4 * tid + 2], c3 = s_bcnt[4 * tid + 3];
-    const unsigned mine = c0 + c1 + c2 + c3;
+    // exclusive prefix over the ICP_SLOTS counters, ICP_SLOTS / ICP_THREADS consecutive ones per thread
+    constexpr int PER = ICP_SLOTS / ICP_THREADS;
+    unsigned mine = 0;
+#pragma unroll 1
+    for(int k = 0; k < PER; k++) mine += S.bcnt[PER * tid + k];
     unsigned incl = mine;
 #pragma unroll
     for(int o = 1; o < 32; o <<= 1)
     {
       const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-      if((tid & 31) >= o) incl += t;
+      if(lane >= o) incl += t;
     }
-    if((tid & 31) == 31) s_scan[tid >> 5] = incl;
+    if(lane == 31) S.scan[tid >> 5] = incl;
     __syncthreads();
     unsigned off = incl - mine;
-    for(int w = 0; w < (tid >> 5); w++) off += s_scan[w];
-    s_bstart[4 * tid] = (unsigned short)off;
-    s_bstart[4 * tid + 1] = (unsigned short)(off + c0);
-    s_bstart[4 * tid + 2] = (unsigned short)(off + c0 + c1);
-    s_bstart[4 * tid + 3] = (unsigned short)(off + c0 + c1 + c2);
-    if(tid == ICP_THREADS - 1) s_bstart[ICP_SLOTS] = (unsigned short)(off + mine);
-    __syncthreads();
-    s_bcnt[4 * tid] = 0; s_bcnt[4 * tid + 1] = 0; s_bcnt[4 * tid + 2] = 0; s_bcnt[4 * tid + 3] = 0;
+    for(int w = 0; w < (tid >> 5); w++) off += S.scan[w];
+#pragma unroll 1
+    for(int k = 0; k < PER; k++)
+    {
+      const unsigned c = S.bcnt[PER * tid + k];
+      S.bstart[PER * tid + k] = (unsigned short)off;
+      S.bcnt[PER * tid + k] = 0;
+      off += c;
+    }
+    if(tid == ICP_THREADS - 1) S.bstart[ICP_SLOTS] = (unsigned short)off;
     __syncthreads();
   }
   for(int i = tid; i < nM; i += ICP_THREADS)
   {
-    const unsigned b = slot_of(cell_of(s_mx[i], bx0, invh), cell_of(s_my[i], by0, invh));
-    const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(s_bcnt) + (b >> 1), (b & 1) ? 0x10000u : 1u);
+    const unsigned b = slot_of(cell_of(P.model[2 * i], bx0, invh), cell_of(P.model[2 * i + 1], by0, invh));
+    const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(S.bcnt) + (b >> 1), (b & 1) ? 0x10000u : 1u);
     const unsigned within = (b & 1) ? (old >> 16) : (old & 0xffffu);
-    s_bidx[s_bstart[b] + within] = (unsigned short)i;
+    S.bidx[S.bstart[b] + within] = (unsigned short)i;
   }
   __syncthreads();
-
+  // (the atomics above hand out places within a slot in any order: put them in index order, so that every CTA of the
+  //  cluster -- and every run -- numbers the points the same way)
+  for(int b = tid; b < ICP_SLOTS; b += ICP_THREADS)
+  {
+    const int k0 = S.bstart[b], k1 = S.bstart[b + 1];
+    for(int k = k0 + 1; k < k1; k++)
+    {
+      const unsigned short v = S.bidx[k];
+      int j = k - 1;
+      while(j >= k0 && S.bidx[j] > v) { S.bidx[j + 1] = S.bidx[j]; j--; }
+      S.bidx[j + 1] = v;
+    }
+  }
+  __syncthreads();
+  for(int k = tid; k < nM; k += ICP_THREADS)
+  {
+    const int i = S.bidx[k];
+    s_mx[k] = P.model[2 * i];
+    s_my[k] = P.model[2 * i + 1];
+    S.pos[i] = (unsigned short)k;
+  }
   // ---- Icp::iterate (Icp.cpp:480-487): initial transformation ----
   if(P.has_init)
   {
@@ -260,7 +350,6 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
     }
     if(tid == 0)
     {
-      // Tfinal = Tinit * Tfinal(identity), dgemm NoTrans x NoTrans with zero skipping
       double out[16];
       for(int i = 0; i < 16; i++) out[i] = 0.0;
       for(int k = 0; k < 4; k++)
@@ -268,340 +357,449 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
         {
           const double temp = 1.0 * P.t_init[4 * i + k];
           if(temp != 0.0)
-            for(int j = 0; j < 4; j++) out[4 * i + j] += temp * s_T[4 * k + j];
+            for(int j = 0; j < 4; j++) out[4 * i + j] += temp * S.T[4 * k + j];
         }
-      for(int i = 0; i < 16; i++) s_T[i] = out[i];
+      for(int i = 0; i < 16; i++) S.T[i] = out[i];
     }
-    __syncthreads();
   }
-  cluster.sync();  // every CTA is resident before anybody addresses its shared memory
+  cluster.sync();  // every CTA is resident and initialised before anybody addresses its shared memory
 
   int eRetval = TSD_ICP_PROCESSING;
   unsigned iter = 0;
   double rms_prev = 10e12;
   unsigned conv_cnt = 0;
-  double rms = 0.0;  // the caller passes *rms = 0.0 (ThreadLocalize.cpp:577)
+  double rms = 0.0;
   unsigned pairs = 0;
-  double distSqr = P.max_dist_sqr;  // DistanceFilter::reset (DistanceFilter.cpp:27-30)
+  double distSqr = P.max_dist_sqr;
+  // provisional centres of the estimator's cross sums (any point near the data; afterwards the last centroids)
+  double pm0 = bx0, pm1 = by0, ps0 = s_sx[0], ps1 = s_sy[0];
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
-  // four lanes per query
-  const int quad = tid >> 2, ql = tid & 3;
-  const unsigned qmask = 0xfu << ((tid & 31) & ~3);
-
+#ifdef ICP_PROFILE
+  long long pf[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pf_t = clock64();
+#endif
   while(eRetval == TSD_ICP_PROCESSING)
   {
-    for(int m = tid; m < nM; m += ICP_THREADS) { s_best[m] = INF64; s_win[m] = 0xffffffffu; }
-    __syncthreads();
-
-    // ---- A: pre-filter + exact 1-NN + distance filter, for the queries of this CTA ----
-    // Four lanes per query scan the 3x3 cells around it (one pass for all queries: nQ <= ICP_THREADS / 4).  That
-    // settles every query with a model point within one cell edge.  The others are finished one after the other
-    // by their whole warp: the 32 lanes scan the rest of the (2R+1)^2 window that covers the distance filter's
-    // current radius, so that a few far-off points do not hold up the cluster.
+    ICP_STAMP(7)
+    // ---- A: pre-filter + exact 1-NN + distance filter, one lane per query ----
+    ulonglong2* const nndCur = S.nnd + (size_t)(iter & 1u) * nS;
+    // what a finished search leaves behind: the lower bound and the seed for the next iteration, and the result in
+    // every CTA's table (its own included)
+    auto finish = [&](int ql, int q, int best, double bestD, double lbNew)
     {
-      const int q = quad;
-      const int i = q * ICP_CLUSTER + (int)rank;
-      const bool exists = q < nQ && i < nS;
-      const int lane = tid & 31;
-      const double x = exists ? s_sx[i] : 0.0, y = exists ? s_sy[i] : 0.0;
+      S.lb[ql] = lbNew;
+      const bool keep = (best >= 0) && (bestD <= distSqr);  // DistanceFilter.cpp:38
+      S.prev[ql] = best >= 0 ? best : S.prev[ql];
+      const unsigned long long db = (unsigned long long)__double_as_longlong(bestD);
+      const unsigned long long mi = keep ? (unsigned long long)best : 0xffffffffffffffffULL;
+      const uint32_t own = (uint32_t)__cvta_generic_to_shared(nndCur + q);
+#pragma unroll 1
+      for(unsigned r = 0; r < ICP_CLUSTER; r++)
+      {
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(own), "r"(r));
+        dsmem_st_v2u64(ra, db, mi);
+      }
+    };
+    // (What an iteration costs is the instructions its 32 warps issue, so warps without queries skip the search altogether.)
+    for(int l0 = 0; l0 < nQ; l0 += ICP_THREADS)
+    {
+      if(l0 + (tid & ~31) >= nQ) continue;          // (warp-uniform)
+      const int ql = l0 + tid;                      // index among this CTA's queries
+      const int q = ql * ICP_CLUSTER + (int)rank;   // scene point
+      const bool exists = ql < nQ && q < nS;
+      const double x = exists ? s_sx[q] : 0.0, y = exists ? s_sy[q] : 0.0;
       // OutOfBoundsFilter2D.cpp:27-37: S.transform(pose) = S * R^T + t
       double tx = 0.0; tx += x * P.pose[0]; tx += y * P.pose[1]; tx = 0.0 + 1.0 * tx; tx += P.pose[2];
       double ty = 0.0; ty += x * P.pose[3]; ty += y * P.pose[4]; ty = 0.0 + 1.0 * ty; ty += P.pose[5];
       bool search = exists && !(tx < P.x_min || tx > P.x_max || ty < P.y_min || ty > P.y_max);
       int best = -1;
-      double bestD = __longlong_as_double(0x7ff0000000000000LL);
-      // A point whose nearest model point is provably farther than the distance filter's threshold cannot
-      // yield a pair (DistanceFilter.cpp:38): its search is skipped.  s_lb[q] is a lower bound of that
-      // distance, carried over from the last search and reduced by how far the point moved since.
-      double lbNew = exists ? s_lb[q] : 0.0;
+      double bestD = INF;
+      // A point whose nearest model point is provably farther than the distance filter's threshold cannot yield a
+      // pair (DistanceFilter.cpp:38): its search is skipped.  lb is a lower bound of that distance, carried over
+      // from the last search and reduced by how far the point moved since.
+      double lbNew = exists ? S.lb[ql] : 0.0;
       if(search && lbNew * lbNew > distSqr) search = false;
       else if(search) lbNew = 0.0;
+      // (the loops below are deliberately NOT unrolled: unrolled, the kernel is 100 KB of code, and an iteration that walks
+      //  through it once is bound by instruction fetch -- measured: 3 k cycles for a phase that issues 300 instructions)
       if(search)
       {
-        // a model point within the distance filter's radius lies in the 3x3 coarse cells around the query
         const int cqx = cell_of(x, bx0, invhc), cqy = cell_of(y, by0, invhc);
         unsigned any = 0;
 #pragma unroll
-        for(int dy = -1; dy <= 1; dy++)
-#pragma unroll
-          for(int dx = -1; dx <= 1; dx++)
-          {
-            const unsigned c = slot_of(cqx + dx, cqy + dy);
-            any |= (s_coarse[c >> 5] >> (c & 31)) & 1u;
-          }
+        for(int c = 0; c < 9; c++)
+        {
+          const unsigned cs = slot_of(cqx + c % 3 - 1, cqy + c / 3 - 1);
+          any |= (S.coarse[cs >> 5] >> (cs & 31)) & 1u;
+        }
         search = any != 0;
         if(!search) lbNew = P.coarse_h * (1.0 - 1e-6);  // nothing within one coarse cell
       }
-      // (search, x, y are uniform over the four lanes of the query)
+      ICP_STAMP(8)
       const int qx = cell_of(x, bx0, invh), qy = cell_of(y, by0, invh);
       bool pending = false;
+      // One lane per query.  The lane opens its own cell first, then finds out which neighbours it has to open at all
+      // (occupied, and not farther than the bound), then walks that short list: a warp runs as many rounds as its
+      // busiest lane has cells, not nine.  Cell c of the 3x3 block is (c % 3 - 1, c / 3 - 1); bit 4 is the query's own.
+      unsigned open = 0;
+      double l2 = 0.0, r2 = 0.0, d2 = 0.0, u2 = 0.0;  // squared distances to the edges of the own cell
       if(search)
       {
-        for(int c = ql; c < 9; c += 4)
+        const int pm = S.prev[ql];
+        if(pm >= 0)
         {
-          const unsigned b = slot_of(qx - 1 + c % 3, qy - 1 + c / 3);
-          if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
-          const int k1 = s_bstart[b + 1];
-          for(int k = s_bstart[b]; k < k1; k++)
+          const double d0 = x - s_mx[pm], d1 = y - s_my[pm];
+          double d = 0.0;
+          d += d0 * d0;
+          d += d1 * d1;
+          bestD = d;
+          best = pm;
+        }
+        // shaved so that rounding never skips a cell wrongly
+        const double fx = (x - bx0) * invh - (double)qx, fy = (y - by0) * invh - (double)qy;
+        const double shave = 1e-9 * h;
+        const double gl = fmax(fx * h - shave, 0.0), gr = fmax((1.0 - fx) * h - shave, 0.0);
+        const double gd = fmax(fy * h - shave, 0.0), gu = fmax((1.0 - fy) * h - shave, 0.0);
+        l2 = gl * gl; r2 = gr * gr; d2 = gd * gd; u2 = gu * gu;
+        open = 1u << 4;
+      }
+      bool first = true;
+      ICP_STAMP(12)
+#pragma unroll 1
+      while(__any_sync(0xffffffffu, open != 0))
+      {
+#ifdef ICP_PROFILE
+        pf[13] += 1;
+#endif
+        if(open)
+        {
+          const int c = first ? 4 : (__ffs(open) - 1);
+          open &= ~(1u << c);
+          const int dx = c % 3 - 1, dy = c / 3 - 1;
+          const double g2 = (dx < 0 ? l2 : (dx > 0 ? r2 : 0.0)) + (dy < 0 ? d2 : (dy > 0 ? u2 : 0.0));
+          const unsigned b = slot_of(qx + dx, qy + dy);
+          if(!(g2 > bestD) && ((S.occ[b >> 5] >> (b & 31)) & 1u))  // (the bound may have shrunk since the list was made)
           {
-            const int m = s_bidx[k];
-            const double d0 = x - s_mx[m];
-            const double d1 = y - s_my[m];
-            double d = 0.0;
-            d += d0 * d0;
-            d += d1 * d1;
-            if(d < bestD || (d == bestD && m < best)) { bestD = d; best = m; }
+            const int k1 = S.bstart[b + 1];
+#pragma unroll 4
+            for(int k = S.bstart[b]; k < k1; k++)
+            {
+              const double d0 = x - s_mx[k];
+              const double d1 = y - s_my[k];
+              double d = 0.0;
+              d += d0 * d0;
+              d += d1 * d1;
+              if(d < bestD || (d == bestD && S.bidx[k] < S.bidx[best])) { bestD = d; best = k; }
+            }
+          }
+          if(first)
+          {
+            // the neighbours worth opening, given what the own cell and last iteration's neighbour yielded
+            first = false;
+            // (straight-line code: the eight tests overlap; with three to five warps per CTA in this phase, latency counts)
+#pragma unroll
+            for(int c2 = 0; c2 < 9; c2++)
+            {
+              if(c2 == 4) continue;
+              const int ex = c2 % 3 - 1, ey = c2 / 3 - 1;
+              const double e2 = (ex < 0 ? l2 : (ex > 0 ? r2 : 0.0)) + (ey < 0 ? d2 : (ey > 0 ? u2 : 0.0));
+              const unsigned bb = slot_of(qx + ex, qy + ey);
+              const unsigned occ = (S.occ[bb >> 5] >> (bb & 31)) & 1u;
+              if(!(e2 > bestD)) open |= occ << c2;  // (a cell farther than the bound holds nothing as close)
+            }
           }
         }
-#pragma unroll
-        for(int o = 1; o < 4; o <<= 1)
-        {
-          const double od = __shfl_xor_sync(qmask, bestD, o);
-          const int ob = __shfl_xor_sync(qmask, best, o);
-          if(ob >= 0 && (best < 0 || od < bestD || (od == bestD && ob < best))) { bestD = od; best = ob; }
-        }
+      }
+      ICP_STAMP(9)
+      ICP_STAMP(10)
+      if(search)
+      {
         // everything unvisited lies in cells at Chebyshev distance > 1, i.e. farther than h
         const double lb = h * (1.0 - 1e-9);
         const double lb2 = lb * lb;
         if(bestD < lb2 || distSqr < lb2) lbNew = fmin(sqrt(bestD), lb) * (1.0 - 1e-9);  // shaved against rounding
         else pending = true;
       }
-      // smallest R with (R h)^2 > distSqr: the window then holds every point the distance filter can keep
-      int R = 2;
-      while(R < P.max_rings && !(distSqr < ((double)R * h * (1.0 - 1e-9)) * ((double)R * h * (1.0 - 1e-9)))) R++;
-      const int W = 2 * R + 1;
-      unsigned todo = __ballot_sync(0xffffffffu, pending && ql == 0);
-      while(todo)
+      ICP_STAMP(11)
+      // the few queries without a model point within one cell edge go to a list that all warps of the CTA work off below
+      if(pending)
       {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const double px = __shfl_sync(0xffffffffu, x, src), py = __shfl_sync(0xffffffffu, y, src);
-        const int pqx = __shfl_sync(0xffffffffu, qx, src), pqy = __shfl_sync(0xffffffffu, qy, src);
-        double wd = __longlong_as_double(0x7ff0000000000000LL);
-        int wb = -1;
-        for(int c = lane; c < W * W; c += 32)
+        const unsigned at = atomicAdd(S.scan + 64, 1u);
+        S.pend[at] = (unsigned short)ql;
+        S.pbd[ql] = bestD;
+        S.prev[ql] = best;  // (seed or nothing yet)
+      }
+      else if(exists) finish(ql, q, best, bestD, lbNew);
+    }
+    __syncthreads();
+    {
+      const unsigned nPend = S.scan[64];
+      if(nPend)
+      {
+        // smallest R with (R h)^2 > distSqr: the window then holds every point the distance filter can keep
+        int R = 2;
+        while(R < P.max_rings && !(distSqr < ((double)R * h * (1.0 - 1e-9)) * ((double)R * h * (1.0 - 1e-9)))) R++;
+#pragma unroll 1
+        for(unsigned at = (unsigned)(tid >> 5); at < nPend; at += ICP_THREADS / 32)
         {
-          const int dx = c % W - R, dy = c / W - R;
-          if(dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) continue;  // done above
-          const unsigned b = slot_of(pqx + dx, pqy + dy);
-          if(!((s_occ[b >> 5] >> (b & 31)) & 1u)) continue;
-          const int k1 = s_bstart[b + 1];
-          for(int k = s_bstart[b]; k < k1; k++)
+          // one warp per query: the 32 lanes scan the rest of the window
+          const int ql = S.pend[at];
+          const int q = ql * ICP_CLUSTER + (int)rank;
+          const double px = s_sx[q], py = s_sy[q];
+          const int pqx = cell_of(px, bx0, invh), pqy = cell_of(py, by0, invh);
+          double bestD = S.pbd[ql];
+          int best = S.prev[ql];
+          // a cell in ring k is farther than (k - 1) h: the bound found so far (last iteration's neighbour) limits the rings
+          int Rq = R;
+          if(bestD < INF) Rq = min(R, (int)(sqrt(bestD) * invh * (1.0 + 1e-9)) + 1);
+          const int Wq = 2 * Rq + 1;
+          double wd = INF;
+          int wb = -1;
+#pragma unroll 1
+          for(int c = lane; c < Wq * Wq; c += 32)
           {
-            const int m = s_bidx[k];
-            const double d0 = px - s_mx[m];
-            const double d1 = py - s_my[m];
-            double d = 0.0;
-            d += d0 * d0;
-            d += d1 * d1;
-            if(d < wd || (d == wd && m < wb)) { wd = d; wb = m; }
+            const int dx = c % Wq - Rq, dy = c / Wq - Rq;
+            if(dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) continue;  // done above
+            const unsigned b = slot_of(pqx + dx, pqy + dy);
+            if(!((S.occ[b >> 5] >> (b & 31)) & 1u)) continue;
+            const int k1 = S.bstart[b + 1];
+            for(int k = S.bstart[b]; k < k1; k++)
+            {
+              const double d0 = px - s_mx[k];
+              const double d1 = py - s_my[k];
+              double d = 0.0;
+              d += d0 * d0;
+              d += d1 * d1;
+              if(d < wd || (d == wd && S.bidx[k] < S.bidx[wb])) { wd = d; wb = k; }
+            }
+          }
+#pragma unroll
+          for(int o = 16; o > 0; o >>= 1)
+          {
+            const double od = __shfl_xor_sync(0xffffffffu, wd, o);
+            const int ob = __shfl_xor_sync(0xffffffffu, wb, o);
+            if(ob >= 0 && (wb < 0 || od < wd || (od == wd && S.bidx[ob] < S.bidx[wb]))) { wd = od; wb = ob; }
+          }
+          if(lane == 0)
+          {
+            if(wb >= 0 && (best < 0 || wd < bestD || (wd == bestD && S.bidx[wb] < S.bidx[best]))) { bestD = wd; best = wb; }
+            finish(ql, q, best, bestD, fmin(sqrt(bestD), (double)R * h * (1.0 - 1e-9)) * (1.0 - 1e-9));
           }
         }
-#pragma unroll
-        for(int o = 16; o > 0; o >>= 1)
-        {
-          const double od = __shfl_xor_sync(0xffffffffu, wd, o);
-          const int ob = __shfl_xor_sync(0xffffffffu, wb, o);
-          if(ob >= 0 && (wb < 0 || od < wd || (od == wd && ob < wb))) { wd = od; wb = ob; }
-        }
-        if((lane & ~3) == src)
-        {
-          if(wb >= 0 && (best < 0 || wd < bestD || (wd == bestD && wb < best))) { bestD = wd; best = wb; }
-          lbNew = fmin(sqrt(bestD), (double)R * h * (1.0 - 1e-9)) * (1.0 - 1e-9);
-        }
-      }
-      if(exists && ql == 0)
-      {
-        s_lb[q] = lbNew;
-        const bool keep = (best >= 0) && (bestD <= distSqr);  // DistanceFilter.cpp:38
-        s_nn[q] = keep ? best : -1;
-        s_d2[q] = bestD;
-        if(keep) atomicMin(&s_best[best], (unsigned long long)__double_as_longlong(bestD));
       }
     }
     __syncthreads();
+    ICP_STAMP(0)
+    // flag exchange: this CTA's results are in everybody's table / everybody's results are in mine
+    if(tid < ICP_CLUSTER)
+    {
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      st_release_cluster(dsmem_addr(S.flag + rank, (unsigned)tid), iter + 1u);
+      while(ld_acquire_cluster(S.flag + tid) < iter + 1u) {}
+    }
+    __syncthreads();
+    ICP_STAMP(5)
     // ---- B: ReciprocalFilter.cpp:32-78: closest scene point per model point (lowest scene index on ties) ----
-    // level 1: among this CTA's queries
-    for(int q = tid; q < nQ; q += ICP_THREADS)
+    if(tid == 0) S.scan[64] = 0u;  // the list of far queries is empty again
+    // The smallest distance per model point is found in two rounds of native 32-bit shared-memory atomics (high word,
+    // then low word among those that share it): a 64-bit atomicMin on shared memory is a compare-and-swap loop, which
+    // was 16% of what the active warps did.  (Distances are non-negative, so their bit patterns order like the values.)
+    unsigned* const bhi = reinterpret_cast<unsigned*>(S.best);
+    unsigned* const blo = bhi + nM;
+    for(int q = tid; q < nS; q += ICP_THREADS)
     {
-      const int i = q * ICP_CLUSTER + (int)rank;
-      if(i >= nS) continue;
-      const int m = s_nn[q];
-      if(m >= 0 && (unsigned long long)__double_as_longlong(s_d2[q]) == s_best[m]) atomicMin(&s_win[m], (unsigned)i);
+      const ulonglong2 e = nndCur[q];
+      if(e.y != 0xffffffffffffffffULL) atomicMin(&bhi[e.y], (unsigned)(e.x >> 32));
     }
     __syncthreads();
-    // the local winner of model point m goes to m's host: slot [this CTA][m / ICP_CLUSTER] of its inbox
-    for(int q = tid; q < nQ; q += ICP_THREADS)
+    for(int q = tid; q < nS; q += ICP_THREADS)
     {
-      const int i = q * ICP_CLUSTER + (int)rank;
-      if(i >= nS) continue;
-      const int m = s_nn[q];
-      if(m >= 0 && s_win[m] == (unsigned)i)
-      {
-        const unsigned host = m % ICP_CLUSTER, slot = rank * nH + m / ICP_CLUSTER;
-        dsmem_st_v2u64(dsmem_addr(s_inbox + slot, host), (unsigned long long)__double_as_longlong(s_d2[q]), (unsigned long long)i);
-      }
+      const ulonglong2 e = nndCur[q];
+      if(e.y != 0xffffffffffffffffULL && (unsigned)(e.x >> 32) == bhi[e.y]) atomicMin(&blo[e.y], (unsigned)e.x);
     }
-    cluster.sync();
-    // level 2: the host of model point m = k * ICP_CLUSTER + rank picks the winner among the ICP_CLUSTER candidates
-    // (lane l of a group looks at CTA l's), clears its inbox and tells every CTA (lane l tells CTA l)
-    for(int k0 = 0; k0 < nH; k0 += ICP_THREADS / ICP_CLUSTER)
+    __syncthreads();
+    for(int q = tid; q < nS; q += ICP_THREADS)
     {
-      const int k = k0 + tid / ICP_CLUSTER;
-      const unsigned peer = tid % ICP_CLUSTER;
-      const int m = k * ICP_CLUSTER + (int)rank;
-      const bool hosted = k < nH && m < nM;
-      unsigned long long bd = INF64;
-      unsigned wi = 0xffffffffu;
-      if(hosted)
-      {
-        const ulonglong2 e = s_inbox[peer * nH + k];
-        bd = e.x;
-        wi = (unsigned)e.y;
-        s_inbox[peer * nH + k] = make_ulonglong2(INF64, 0xffffffffULL);
-      }
-#pragma unroll
-      for(int o = 1; o < ICP_CLUSTER; o <<= 1)
-      {
-        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, bd, o);
-        const unsigned ow = __shfl_xor_sync(0xffffffffu, wi, o);
-        if(ob < bd || (ob == bd && ow < wi)) { bd = ob; wi = ow; }
-      }
-      if(hosted) dsmem_st_u32(dsmem_addr(s_fin + m, peer), (bd == INF64) ? 0xffffffffu : wi);
+      const ulonglong2 e = nndCur[q];
+      if(e.y != 0xffffffffffffffffULL && (unsigned)(e.x >> 32) == bhi[e.y] && (unsigned)e.x == blo[e.y])
+        atomicMin(&S.win[e.y], (unsigned)q);
     }
-    cluster.sync();
+    __syncthreads();
+    ICP_STAMP(1)
     // DistanceFilter.cpp:62-63
     distSqr *= P.multiplier;
     if(distSqr < P.min_dist_sqr) distSqr = P.min_dist_sqr;
 
-    // ---- C: ClosedFormEstimator2D::setPairs (+ the pair list in model order when tracing) ----
-    // (replicated: every CTA holds all winners)
-    double acc[6] = {0, 0, 0, 0, 0, 0};  // cm0 cm1 cs0 cs1 r count
-    unsigned winOf[(ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS];
-#pragma unroll
-    for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
-    {
-      const int m = tid + j * ICP_THREADS;
-      winOf[j] = (m < nM) ? s_fin[m] : 0xffffffffu;
-    }
+    // ---- C: ClosedFormEstimator2D::setPairs + estimateTransformation (ClosedFormEstimator2D.cpp:36-109) ----
     if(P.trace && rank == 0)
     {
+      // the pair list in model order
       unsigned baseCount = 0;
-#pragma unroll
-      for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
+      for(int j = 0; j * ICP_THREADS < nM; j++)
       {
-        const int m = tid + j * ICP_THREADS;
-        if(j * ICP_THREADS >= nM) break;
-        const bool has = winOf[j] != 0xffffffffu;
+        const int m = tid + j * ICP_THREADS;  // the caller's index
+        const unsigned w = (m < nM) ? S.win[S.pos[m]] : 0xffffffffu;
+        const bool has = w != 0xffffffffu;
         const unsigned bal = __ballot_sync(0xffffffffu, has);
-        if((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
+        if(lane == 0) S.scan[tid >> 5] = __popc(bal);
         __syncthreads();
         unsigned off = baseCount;
         unsigned total = 0;
-        for(int w = 0; w < ICP_THREADS / 32; w++)
+        for(int w2 = 0; w2 < ICP_THREADS / 32; w2++)
         {
-          const unsigned c = s_scan[w];
-          if(w < (tid >> 5)) off += c;
+          const unsigned c = S.scan[w2];
+          if(w2 < (tid >> 5)) off += c;
           total += c;
         }
         if(has)
         {
-          const unsigned pos = off + __popc(bal & ((1u << (tid & 31)) - 1u));
+          const unsigned pos = off + __popc(bal & ((1u << lane) - 1u));
           if((int)iter < P.max_iterations && pos < (unsigned)P.cap)
           {
             P.tr_model[(size_t)iter * P.cap + pos] = (unsigned)m;
-            P.tr_scene[(size_t)iter * P.cap + pos] = winOf[j];
+            P.tr_scene[(size_t)iter * P.cap + pos] = w;
           }
         }
         baseCount += total;
         __syncthreads();
       }
     }
-#pragma unroll
-    for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
+    // The sums are latency, not work (a few hundred pairs): ICP_SUM_THREADS threads walk the model points.
+    if(tid < ICP_SUM_THREADS)
     {
-      const int m = tid + j * ICP_THREADS;
-      const unsigned sidx = winOf[j];
-      if(sidx != 0xffffffffu)
+      double acc[7] = {0, 0, 0, 0, 0, 0, 0};  // sum m0 m1 s0 s1 | r | cross sums about (pm, ps): yx - xy, xx + yy
+      unsigned cnt = 0;
+      for(int m = tid; m < nM; m += ICP_SUM_THREADS)
       {
-        acc[0] += s_mx[m]; acc[1] += s_my[m];
-        acc[2] += s_sx[sidx]; acc[3] += s_sy[sidx];
-        const double dx = s_sx[sidx] - s_mx[m];
-        const double dy = s_sy[sidx] - s_my[m];
-        acc[4] += dx * dx + dy * dy;
-        acc[5] += 1.0;
+        const unsigned sidx = S.win[m];
+        S.win[m] = 0xffffffffu;  // for the next iteration (nobody else looks at them before the barriers below)
+        S.best[m] = INF64;       // (model points m and nM + m of the two 32-bit arrays the reciprocal filter sees: all ones)
+        if(sidx != 0xffffffffu)
+        {
+          const double m0 = s_mx[m], m1 = s_my[m], s0 = s_sx[sidx], s1 = s_sy[sidx];
+          acc[0] += m0; acc[1] += m1;
+          acc[2] += s0; acc[3] += s1;
+          const double dx = s0 - m0;
+          const double dy = s1 - m1;
+          acc[4] += dx * dx + dy * dy;
+          cnt++;
+          const double a0 = m0 - pm0, a1 = m1 - pm1, b0 = s0 - ps0, b1 = s1 - ps1;
+          acc[5] += a1 * b0 - a0 * b1;
+          acc[6] += a0 * b0 + a1 * b1;
+        }
+      }
+      // the partial sums go through shared memory: a 64-bit shuffle tree over 7 values is 560 instructions per warp
+#pragma unroll
+      for(int k = 0; k < 7; k++) S.part[k * ICP_SUM_THREADS + tid] = acc[k];
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if(lane == 0) S.scan[32 + (tid >> 5)] = cnt;
+    }
+    __syncthreads();
+    if(tid < 7 * 32)
+    {
+      // warp k adds up value k: every lane ICP_SUM_THREADS / 32 partials in a fixed order, then one shuffle tree
+      const int k = tid >> 5;
+      double v = 0.0;
+#pragma unroll
+      for(int j = 0; j < ICP_SUM_THREADS / 32; j++) v += S.part[k * ICP_SUM_THREADS + j * 32 + lane];
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if(lane == 0) S.red[k] = v;
+    }
+    __syncthreads();
+    ICP_STAMP(2)
+    if(tid < 32)
+    {
+      double v[7];
+#pragma unroll
+      for(int k = 0; k < 7; k++) v[k] = S.red[k];
+      unsigned np = lane < ICP_SUM_THREADS / 32 ? S.scan[32 + lane] : 0u;
+      np = __reduce_add_sync(0xffffffffu, np);
+      double* R_ = S.red + 320;  // results: pairs, rms, the new provisional centres
+      double* Tl = S.T + 16;
+      if(lane == 0) R_[0] = (double)np;
+      if(np > 2)
+      {
+        // (every lane computes the same few numbers; lanes 0-15 then each own one element of the matrices)
+        const double sizeInv = 1.0 / (double)np;
+        const double r = v[4] * sizeInv;
+        const double cm0 = v[0] * sizeInv, cm1 = v[1] * sizeInv, cs0 = v[2] * sizeInv, cs1 = v[3] * sizeInv;
+        // sum over the pairs of (m - cm)(s - cs)^T from the sums about the provisional centres
+        const double em0 = cm0 - pm0, em1 = cm1 - pm1, es0 = cs0 - ps0, es1 = cs1 - ps1;
+        const double n = (double)np;
+        const double nominator = v[5] - n * (em1 * es0 - em0 * es1);
+        const double denominator = v[6] - n * (em0 * es0 + em1 * es1);
+        // cos / sin of deltaTheta = atan2(nominator, denominator) (ClosedFormEstimator2D.cpp:93-96)
+        const double hyp = sqrt(nominator * nominator + denominator * denominator);
+        double c = 1.0, sn = 0.0;
+        if(hyp > 0.0) { c = denominator / hyp; sn = nominator / hyp; }
+        const double deltaX = (cm0 - (c * cs0 - sn * cs1));
+        const double deltaY = (cm1 - (c * cs1 + sn * cs0));
+        if(lane == 0)
+        {
+          R_[1] = r;
+          R_[2] = cm0; R_[3] = cm1; R_[4] = cs0; R_[5] = cs1;
+        }
+        if(lane < 16)
+        {
+          double tl = (lane % 5 == 0) ? 1.0 : 0.0;
+          if(lane == 0 || lane == 5) tl = c;
+          if(lane == 1) tl = -sn;
+          if(lane == 4) tl = sn;
+          if(lane == 3) tl = deltaX;
+          if(lane == 7) tl = deltaY;
+          Tl[lane] = tl;
+        }
+        __syncwarp();
+        // Tfinal = Tlast * Tfinal (Icp.cpp:454): element (i, j) accumulates over k in order, zero factors skipped (dgemm)
+        double o = 0.0;
+        if(lane < 16)
+        {
+          const int i = lane >> 2, j = lane & 3;
+#pragma unroll
+          for(int k = 0; k < 4; k++)
+          {
+            const double temp = 1.0 * Tl[4 * i + k];
+            if(temp != 0.0) o += temp * S.T[4 * k + j];
+          }
+        }
+        __syncwarp();
+        if(lane < 16) S.T[lane] = o;
       }
     }
-    block_sum_n<6>(acc, s_red, tid);
-    pairs = (unsigned)acc[5];
-
+    __syncthreads();
+    ICP_STAMP(3)
+    pairs = (unsigned)S.red[320];
     int retval = TSD_ICP_PROCESSING;
     if(pairs > 2)
     {
-      const double sizeInv = 1.0 / (double)pairs;
-      const double r = acc[4] * sizeInv;
-      const double cm0 = acc[0] * sizeInv, cm1 = acc[1] * sizeInv, cs0 = acc[2] * sizeInv, cs1 = acc[3] * sizeInv;
-      rms = r;
-      // estimateTransformation (ClosedFormEstimator2D.cpp:74-109)
-      double nd[2] = {0, 0};
-#pragma unroll
-      for(int j = 0; j < (ICP_MAX_POINTS + ICP_THREADS - 1) / ICP_THREADS; j++)
-      {
-        const int m = tid + j * ICP_THREADS;
-        const unsigned sidx = winOf[j];
-        if(sidx != 0xffffffffu)
-        {
-          const double xFCm = s_mx[m] - cm0, yFCm = s_my[m] - cm1;
-          const double xSCs = s_sx[sidx] - cs0, ySCs = s_sy[sidx] - cs1;
-          nd[0] += yFCm * xSCs - xFCm * ySCs;
-          nd[1] += xFCm * xSCs + yFCm * ySCs;
-        }
-      }
-      block_sum_n<2>(nd, s_red, tid);
-      if(tid == 0)
-      {
-        const double deltaTheta = atan2(nd[0], nd[1]);
-        const double c = cos(deltaTheta), s = sin(deltaTheta);
-        const double deltaX = (cm0 - (c * cs0 - s * cs1));
-        const double deltaY = (cm1 - (c * cs1 + s * cs0));
-        double* Tl = s_T + 16;
-        for(int i = 0; i < 16; i++) Tl[i] = (i % 5 == 0) ? 1.0 : 0.0;
-        Tl[0] = c; Tl[1] = -s; Tl[3] = deltaX;
-        Tl[4] = s; Tl[5] = c;  Tl[7] = deltaY;
-        Tl[11] = 0;
-        // Tfinal = Tlast * Tfinal (Icp.cpp:454)
-        double out[16];
-        for(int i = 0; i < 16; i++) out[i] = 0.0;
-        for(int k = 0; k < 4; k++)
-          for(int i = 0; i < 4; i++)
-          {
-            const double temp = 1.0 * Tl[4 * i + k];
-            if(temp != 0.0)
-              for(int j = 0; j < 4; j++) out[4 * i + j] += temp * s_T[4 * k + j];
-          }
-        for(int i = 0; i < 16; i++) s_T[i] = out[i];
-      }
-      __syncthreads();
+      rms = S.red[321];
+      pm0 = S.red[322]; pm1 = S.red[323]; ps0 = S.red[324]; ps1 = S.red[325];
       // applyTransformation (Icp.cpp:371-408)
+      const double* Tl = S.T + 16;
+      const double r00 = Tl[0], r01 = Tl[1], r10 = Tl[4], r11 = Tl[5], t0 = Tl[3], t1 = Tl[7];
+      for(int i = tid; i < nS; i += ICP_THREADS)
       {
-        const double* Tl = s_T + 16;
-        const double r00 = Tl[0], r01 = Tl[1], r10 = Tl[4], r11 = Tl[5], t0 = Tl[3], t1 = Tl[7];
-        for(int i = tid; i < nS; i += ICP_THREADS)
+        const double x = s_sx[i], y = s_sy[i];
+        double a = 0.0; a += x * r00; a += y * r01; a = 0.0 + 1.0 * a;
+        double b = 0.0; b += x * r10; b += y * r11; b = 0.0 + 1.0 * b;
+        const double nx = a + t0, ny = b + t1;
+        s_sx[i] = nx;
+        s_sy[i] = ny;
+        // the point moved by |(nx,ny) - (x,y)|: its nearest-neighbour distance shrank by at most that
+        if((unsigned)(i % ICP_CLUSTER) == rank)
         {
-          const double x = s_sx[i], y = s_sy[i];
-          double a = 0.0; a += x * r00; a += y * r01; a = 0.0 + 1.0 * a;
-          double b = 0.0; b += x * r10; b += y * r11; b = 0.0 + 1.0 * b;
-          const double nx = a + t0, ny = b + t1;
-          s_sx[i] = nx;
-          s_sy[i] = ny;
-          if((unsigned)(i % ICP_CLUSTER) == rank)
-          {
-            // the point moved by |(nx,ny) - (x,y)|: its nearest-neighbour distance shrank by at most that
-            const double mvx = nx - x, mvy = ny - y;
-            const double lb = s_lb[i / ICP_CLUSTER] - sqrt(mvx * mvx + mvy * mvy) * (1.0 + 1e-9) - 1e-12;
-            s_lb[i / ICP_CLUSTER] = lb > 0.0 ? lb : 0.0;
-          }
+          // (|dx| + |dy| bounds the distance moved from above; no square root)
+          const double lb = S.lb[i / ICP_CLUSTER] - (fabs(nx - x) + fabs(ny - y)) * (1.0 + 1e-9) - 1e-12;
+          S.lb[i / ICP_CLUSTER] = lb > 0.0 ? lb : 0.0;
         }
+      }
+      {
+        // the provisional scene centre moves with the scene
+        double a = 0.0; a += ps0 * r00; a += ps1 * r01;
+        double b = 0.0; b += ps0 * r10; b += ps1 * r11;
+        ps0 = a + t0; ps1 = b + t1;
       }
     }
     else
@@ -612,9 +810,9 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
     {
       P.tr_count[iter] = (int)pairs;
       P.tr_mse[iter] = rms;
-      for(int i = 0; i < 16; i++) P.tr_T[16 * iter + i] = s_T[i];
+      for(int i = 0; i < 16; i++) P.tr_T[16 * iter + i] = S.T[i];
     }
-    __syncthreads();
+    ICP_STAMP(4)
     eRetval = retval;
     // Icp.cpp:496-507
     iter++;
@@ -624,32 +822,28 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
     else if(iter >= (unsigned)P.max_iterations) eRetval = TSD_ICP_MAXITERATIONS;
     rms_prev = rms;
   }
-
+  // iterations that did not run have no pair list
+  if(rank == 0)
+    for(int i = (int)iter + tid; i < P.max_iterations; i += ICP_THREADS) P.tr_count[i] = -1;
   if(rank == 0 && tid == 0)
   {
     // getFinalTransformation (Icp.cpp:528-546)
-    P.result[0] = s_T[0]; P.result[1] = s_T[1]; P.result[2] = s_T[3];
-    P.result[3] = s_T[4]; P.result[4] = s_T[5]; P.result[5] = s_T[7];
+    P.result[0] = S.T[0]; P.result[1] = S.T[1]; P.result[2] = S.T[3];
+    P.result[3] = S.T[4]; P.result[4] = S.T[5]; P.result[5] = S.T[7];
     P.result[6] = 0; P.result[7] = 0; P.result[8] = 1;
     P.result[9] = rms;
     P.result[10] = (double)pairs;
     P.result[11] = (double)iter;
     P.result[12] = (double)eRetval;
+#ifdef ICP_PROFILE
+    printf("k_icp %u iterations, cycles per iteration: NN %lld | exchange %lld | recip %lld | gather+sums %lld | pose %lld | apply %lld | loop top %lld\n",
+           iter, pf[0] / iter, pf[5] / iter, pf[1] / iter, pf[2] / iter, pf[3] / iter, pf[4] / iter, pf[7] / iter);
+    printf("   cell walk: seed %lld cycles, %lld rounds per iteration\n", pf[12] / iter, pf[13] / iter);
+    printf("   NN: prefilter+coarse %lld | prev+own cell+mask %lld | neighbour cells %lld | far queries %lld | tail+barrier %lld\n", pf[8] / iter,
+           pf[9] / iter, pf[10] / iter, pf[11] / iter, pf[0] / iter);
+#endif
   }
   cluster.sync();  // no CTA's shared memory goes away while a neighbour may still address it
-}
-
-static size_t icp_smem_bytes(int nM, int nS)
-{
-  const size_t nQ = ((size_t)nS + ICP_CLUSTER - 1) / ICP_CLUSTER, nH = ((size_t)nM + ICP_CLUSTER - 1) / ICP_CLUSTER;
-  size_t b = 0;
-  b += sizeof(double) * (2 * (size_t)nM + 2 * (size_t)nS + 2 * nQ);  // mx my sx sy d2 lb
-  b += sizeof(unsigned long long) * nM;                            // best
-  b += sizeof(double) * (208 + 32);                               // red + T
-  b += sizeof(unsigned) * (2 * (size_t)nM) + sizeof(int) * nQ + sizeof(unsigned) * 40;
-  b += 16 * ICP_CLUSTER * nH + 16;                                 // inbox
-  b += sizeof(unsigned short) * (ICP_SLOTS + 2 + ICP_SLOTS + (size_t)nM + 2) + sizeof(unsigned) * 256;
-  return b + 64;
 }
 
 extern "C" {
@@ -695,8 +889,8 @@ int icp_create(uint32_t max_iterations, double dist_max, double dist_min, uint32
   }
   h->cap = ICP_MAX_POINTS;
   TSD_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  TSD_CUDA(cudaMalloc(&h->d_model, sizeof(double) * 2 * h->cap));
-  TSD_CUDA(cudaMalloc(&h->d_scene, sizeof(double) * 2 * h->cap));
+  TSD_CUDA(cudaMalloc(&h->d_model, sizeof(double) * 4 * h->cap));  // model, then scene
+  h->d_scene = nullptr;
   TSD_CUDA(cudaMalloc(&h->d_result, sizeof(double) * 16));
   const size_t mi = max_iterations > 0 ? max_iterations : 1;
   h->trace_cap_it = (int)mi;
@@ -748,10 +942,10 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   }
   TSD_CUDA(cudaSetDevice(h->device));
   TSD_CUDA(cudaStreamSynchronize(h->stream));
+  // model and scene travel in one copy
   memcpy(h->h_stage, model, sizeof(double) * 2 * n_model);
-  memcpy(h->h_stage + 2 * h->cap, scene, sizeof(double) * 2 * n_scene);
-  TSD_CUDA(cudaMemcpyAsync(h->d_model, h->h_stage, sizeof(double) * 2 * n_model, cudaMemcpyHostToDevice, h->stream));
-  TSD_CUDA(cudaMemcpyAsync(h->d_scene, h->h_stage + 2 * h->cap, sizeof(double) * 2 * n_scene, cudaMemcpyHostToDevice, h->stream));
+  memcpy(h->h_stage + 2 * n_model, scene, sizeof(double) * 2 * n_scene);
+  TSD_CUDA(cudaMemcpyAsync(h->d_model, h->h_stage, sizeof(double) * 2 * ((size_t)n_model + n_scene), cudaMemcpyHostToDevice, h->stream));
   IcpParams p = h->p;
   p.nM = n_model;
   p.nS = n_scene;
@@ -759,7 +953,7 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   p.has_init = t_init ? 1 : 0;
   for(int i = 0; i < 16; i++) p.t_init[i] = t_init ? t_init[i] : ((i % 5 == 0) ? 1.0 : 0.0);
   p.model = h->d_model;
-  p.scene = h->d_scene;
+  p.scene = h->d_model + 2 * (size_t)n_model;
   p.result = h->d_result;
   p.cap = h->cap;
   p.trace = h->trace;
@@ -768,7 +962,6 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   p.tr_count = h->d_tr_count;
   p.tr_mse = h->d_tr_mse;
   p.tr_T = h->d_tr_T;
-  if(p.max_iterations > 0) TSD_CUDA(cudaMemsetAsync(h->d_tr_count, 0xff, sizeof(int) * p.max_iterations, h->stream));
   k_icp<<<ICP_CLUSTER, ICP_THREADS, icp_smem_bytes(n_model, n_scene), h->stream>>>(p);  // one cluster (__cluster_dims__)
   TSD_LAUNCHED();
   TSD_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(double) * 13, cudaMemcpyDeviceToHost, h->stream));

@@ -9,7 +9,8 @@ import numpy as np
 from ohm_tsd_slam_b200 import capi
 from ohm_tsd_slam_b200.workload import DoubleLaserWorkload
 
-wl = DoubleLaserWorkload("C2", invert=capi.invert3x3)
+name = sys.argv[1] if len(sys.argv) > 1 else "C2"
+wl = DoubleLaserWorkload(name, invert=capi.invert3x3, n_map=4 if name == "C3" else 6)
 cfg = wl.cfg
 g = capi.Grid(cfg.cell_size, cfg.layout_partition, cfg.layout_grid)
 g.set_max_truncation(cfg.max_truncation)
@@ -17,7 +18,7 @@ wl.build_map(g)
 g.set_timing(True)
 L = capi.lib()
 L.tsdg_debug_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-for filt in (0, 2, 1):
+for filt in (0,):
     g.set_update_filter(filt)
     for st in wl.step_scans[:2]:
         g.stage_batch(list(st))
