@@ -39,6 +39,25 @@ struct RayParams
 };
 
 #define RC_WARPS 4
+#ifndef RC_PREFETCH_PASSES
+#define RC_PREFETCH_PASSES 6
+#endif
+#ifndef RC_DEPTH
+#define RC_DEPTH 3   // passes of a ray whose samples are in flight at once (C3, ms per call: 1 -> 0.41, 2 -> 0.30, 3 and 4 -> 0.29)
+#endif
+
+// L2 prefetch of the two cell rows a bilinear sample at (cx, cy) reads (clamped like sample_issue: always a valid address)
+__device__ __forceinline__ void sample_prefetch(const GridView& g, double cx, double cy)
+{
+  int xIdx = __double2int_rd(cx * g.inv_cell_size);
+  int yIdx = __double2int_rd(cy * g.inv_cell_size);
+  xIdx = min(max(xIdx, 0), g.cells_x - 1);
+  yIdx = min(max(yIdx, g.alloc_begin * 32), g.alloc_end * 32 - 1);
+  const int py = yIdx >> 5, px = xIdx >> 5;
+  const double* t = g.tsd + (size_t)((py - g.alloc_begin) * g.parts_x + px) * TSD_TILE_STRIDE + (yIdx & 31) * 32 + (xIdx & 31);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(t));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(t + 32));
+}
 #define NO_EVENT 0x7fffffffffffffffULL  // INT64_MAX: the largest key under a signed or unsigned min-reduction
 
 __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam, const int lane)
@@ -114,28 +133,64 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
 
     // :243-270 fine loop, 32 steps per pass.
     // The position chain of a pass is computed by all lanes (uniform DADDs), every lane keeps the position of its
-    // own step; the chain of pass c+1 is issued between the loads and the use of pass c's samples, so the L2
-    // latency of the samples hides behind it.
+    // own step.  The samples of TWO passes are in flight: while pass c is evaluated, the loads of pass c + 1 are on
+    // their way and the chain of pass c + 2 is being added up, so that a pass costs its arithmetic, not a trip to L2 or
+    // HBM (a ray of the 250 m sensor is 300 passes one after the other: the longest ray is the kernel's duration).
+    // Loads past the end of a ray are harmless (addresses are clamped to valid memory, results masked by `valid`).
     // The loop counter `i += 1.0` of the reference only decides when the loop ends: it is replayed exactly
     // (serially) only for passes that come within 2 steps of idxMax; elsewhere idxMin + k decides safely.
     // (every lane runs the whole chain and keeps the position of its own step in registers: parking the positions
     //  in shared memory made each addition wait for the previous store to read its operands)
-    double nmx = 0.0, nmy = 0.0;
     double iExact = idxMin;          // i of iteration kExact (exact serial value)
     unsigned long long kExact = 0;
     unsigned long long base = 0;
+    // The serial sum `position += ray` of a pass in closed form.  While a coordinate p stays inside one binade
+    // [2^e, 2^(e+1)) its values are multiples of u = ulp(p), and fl(p + r) = p + d with d = RN_u(r) the same multiple of u
+    // at every step -- unless r lies exactly half-way between two multiples (then round-to-even decides by p's parity).
+    // d is read off one real addition (d = fl(p + r) - p, exact), and p + k d is exact for k <= 32 (k d has fewer than
+    // 53 bits; the sum is a multiple of u inside the binade).  So if start and end of the pass share sign and exponent
+    // (the sequence is monotonic) and there is no tie, lane k's position is p + (k + 1) d: 2 operations instead of a
+    // chain of 32 dependent additions that every lane replays.  Otherwise (a coordinate crosses a power of two: about ten
+    // passes per ray) the pass falls back to the serial chain.
+    auto advance = [&](double* ox, double* oy)
+    {
+      const double d0 = (pos0 + ray0) - pos0, d1 = (pos1 + ray1) - pos1;
+      const double e0 = pos0 + 32.0 * d0, e1 = pos1 + 32.0 * d1;
+      const unsigned h0 = (unsigned)__double2hiint(pos0) >> 20, h1 = (unsigned)__double2hiint(pos1) >> 20;
+      const unsigned x0 = h0 & 0x7ffu, x1 = h1 & 0x7ffu;
+      // half an ulp of the binade (exponent - 53); 0 if that would be subnormal: then the strict test below fails
+      const double hu0 = __hiloint2double(x0 > 53u ? (int)((x0 - 53u) << 20) : 0, 0);
+      const double hu1 = __hiloint2double(x1 > 53u ? (int)((x1 - 53u) << 20) : 0, 0);
+      const bool closed = (h0 == ((unsigned)__double2hiint(e0) >> 20)) && (h1 == ((unsigned)__double2hiint(e1) >> 20)) &&
+                          (fabs(ray0 - d0) < hu0) && (fabs(ray1 - d1) < hu1);
+      if(closed)
+      {
+        const double k = (double)(lane + 1);
+        *ox = pos0 + k * d0;
+        *oy = pos1 + k * d1;
+        pos0 = e0;
+        pos1 = e1;
+      }
+      else
+      {
+        double ax = 0.0, ay = 0.0;
 #pragma unroll 8
-    for(int k = 0; k < 32; k++)
+        for(int k = 0; k < 32; k++)
+        {
+          pos0 += ray0;
+          pos1 += ray1;
+          if(k == lane) { ax = pos0; ay = pos1; }
+        }
+        *ox = ax;
+        *oy = ay;
+      }
+    };
+    // One pass: evaluate the samples in `cur` (taken at this lane's position (cmx, cmy)), then refill `cur` with the
+    // samples of the pass after next.  Returns true when the ray is finished.  The loop below alternates between two
+    // sets of registers, so that no loaded value has to be moved (a move waits for its load) before it is needed.
+    auto pass = [&](SampleLoads& cur, double& cmx, double& cmy) -> bool
     {
-      pos0 += ray0;
-      pos1 += ray1;
-      if(k == lane) { nmx = pos0; nmy = pos1; }
-    }
-    while(true)
-    {
-      const double mx = nmx, my = nmy;
       // validity of this lane's iteration: i_k <= idxMax
-      const double est = idxMin + (double)(base + (unsigned)lane);
       bool valid;
       const bool nearEnd = !(idxMin + (double)(base + 31u) + 2.0 < idxMax);
       if(!nearEnd) valid = true;
@@ -152,28 +207,18 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
           ii += 1.0;
         }
         valid = mi <= idxMax;
-        (void)est;
       }
+      // positions of the pass after next while the loads of this pass and the next are in flight
+      double mx2, my2;
+      advance(&mx2, &my2);
       double v = __longlong_as_double(0x7ff8000000000000LL);
       double t = 0.0;
-      const SampleLoads sl = sample_issue(g, mx, my);  // all lanes: addresses are clamped, results masked below
-      // next pass's positions while the loads above are in flight
-      {
-
-#pragma unroll 8
-        for(int k = 0; k < 32; k++)
-        {
-          pos0 += ray0;
-          pos1 += ray1;
-          if(k == lane) { nmx = pos0; nmy = pos1; }
-        }
-      }
-      const int rv = sample_finish(sl, &t);
+      const int rv = sample_finish(cur, &t);
       if(valid && rv == TSD_INTERPOLATE_SUCCESS) v = t;
       double prev = __shfl_up_sync(0xffffffffu, v, 1);
       if(lane == 0) prev = carry;
       // a step belongs to the band that owns its sample's partition (everything, for an unsharded grid)
-      const bool mine = valid && (sl.py >= g.row_begin) && (sl.py < g.row_end);
+      const bool mine = valid && (cur.py >= g.row_begin) && (cur.py < g.row_end);
       const bool hit = mine && (prev > 0) && (v < 0);
       const bool abortEv = mine && (prev < 0) && (v > 0);
       const unsigned mHit = __ballot_sync(0xffffffffu, hit);
@@ -192,8 +237,8 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
           if(lane == f)
           {
             const double interp = prev / (prev - v);
-            cx = mx + ray0 * (interp - 1.0);
-            cy = my + ray1 * (interp - 1.0);
+            cx = cmx + ray0 * (interp - 1.0);
+            cy = cmy + ray1 * (interp - 1.0);
             ok = sample_normal(g, cx, cy, &nx, &ny) ? 1 : 0;
           }
           ok = __shfl_sync(0xffffffffu, ok, f);
@@ -204,16 +249,40 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
           found = ok != 0;
           if(found) key &= ~3ULL;
         }
-        break;
+        return true;
       }
       if(mInval)
       {
         nFine += (unsigned)(__ffs(mInval) - 1);
-        break;
+        return true;
       }
       nFine += 32;
       base += 32;
       carry = __shfl_sync(0xffffffffu, v, 31);
+      cmx = mx2;
+      cmy = my2;
+      cur = sample_issue(g, mx2, my2);
+      // ... and the cells the ray reaches RC_PREFETCH_PASSES passes later are called into L2 (approximate positions are
+      // good enough for that): a ray walks through memory it has never touched -- a new partition every 32 steps, a new
+      // 2 MB page every partition row.
+      sample_prefetch(g, mx2 + (32.0 * RC_PREFETCH_PASSES) * ray0, my2 + (32.0 * RC_PREFETCH_PASSES) * ray1);
+      return false;
+    };
+    // RC_DEPTH passes in flight, each with its own registers
+    double pmx[RC_DEPTH], pmy[RC_DEPTH];
+    SampleLoads psl[RC_DEPTH];
+#pragma unroll
+    for(int d = 0; d < RC_DEPTH; d++)
+    {
+      advance(&pmx[d], &pmy[d]);
+      psl[d] = sample_issue(g, pmx[d], pmy[d]);
+    }
+    bool done = false;
+    while(!done)
+    {
+#pragma unroll
+      for(int d = 0; d < RC_DEPTH; d++)
+        if(!done) done = pass(psl[d], pmx[d], pmy[d]);
     }
   }
 
