@@ -258,7 +258,8 @@ def run_cuda(args):
     sc0, rays0 = wl.step_scans[0][0], wl.step_rays[0][0]
     hs = wl.sensors[0]
     scene = None
-    rc_ms = icp_ms = None
+    rc_ms = icp_ms = loc_ms = None
+    loc_out = None
     reps = max(3, min(args.steps, 20))
     def raycast():
         return band.raycast_mask(sc0, rays0) if band else grid.raycast_mask(sc0, rays0)
@@ -280,6 +281,14 @@ def run_cuda(args):
         for _ in range(reps):
             icp_out = icp.run(c[m > 0], nrm[m > 0], scene, sc0.pose)
         icp_ms = (time.perf_counter() - t0) / reps * 1e3
+        if not band:
+            # the same step through the fused entry point: the model never leaves the device
+            for _ in range(2):
+                loc_out = icp.localize(grid, sc0, rays0, scene)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                loc_out = icp.localize(grid, sc0, rays0, scene)
+            loc_ms = (time.perf_counter() - t0) / reps * 1e3
 
     # ---------------- map publication: RayCastAxisAligned2D::calcCoords + grid2ColorImage on the device,
     # host buffers in and out (occupancy grid cells_x * cells_y bytes both ways, crossings, 1024^2 RGB image)
@@ -390,7 +399,12 @@ def run_cuda(args):
                          "split": split},
             "push_kernel_ms": {k: float(np.mean([x[k] for x in kms])) for k in kms[0]},
             "raycast_icp": {"raycast_ms": rc_ms, "icp_ms": icp_ms, "raycast_hits": int(cnt),
+                            "localize_ms": loc_ms,
+                            "localize": ({"pairs": int(loc_out[2]), "iterations": int(loc_out[3]), "n_model": int(loc_out[5]),
+                                          "what": "tsdg_localize: ray cast + maskMatrix + Icp::iterate, model kept on the device, host buffers in and out"}
+                                         if loc_out else None),
                             "scans_per_s": (1e3 / (rc_ms + icp_ms)) if icp_ms else None,
+                            "scan_ms_push_localize": (loc_ms + e2e_ms_max / args.steps / max(scans_per_step, 1)) if loc_ms else None,
                             "scan_ms_push_raycast_icp": (rc_ms + icp_ms + e2e_ms_max / args.steps / max(scans_per_step, 1)) if icp_ms else None,
                             "icp": None if icp_out is None else {"pairs": icp_out[2], "iterations": icp_out[3]}},
             "one_gpu_same_workload": (None if world == 1 else {k: one_gpu[k] for k in ("workload", "value_gcell_updates_per_s", "ms_per_step",

@@ -307,6 +307,14 @@ int icp_set_max_iterations(tsd_icp_t* icp, uint32_t max_iterations);
 int icp_run(tsd_icp_t* icp, const double* model, const double* normals, int32_t n_model, const double* scene,
             int32_t n_scene, const double pose[9], const double* t_init, double t_out[9], double* mse,
             uint32_t* pairs, uint32_t* iterations, int32_t* state);
+/* One localisation step with the model kept on the device: RayCastPolar2D::calcCoordsFromCurrentViewMask from the scan's
+ * pose, ThreadLocalize::maskMatrix and Icp::iterate (reference src/ThreadLocalize.cpp:333-361 and :571-581) -- the result
+ * of tsdg_raycast_mask + icp_run(model = the hits in beam order, pose = scan->pose) without the two host round trips.
+ * scene: n_scene x 2, the scan's valid points in the sensor frame (ThreadLocalize.cpp:341-352); *n_model: the number of
+ * hits (the caller's validModelPoints).  grid and icp must live on the same device; at most 2048 beams. */
+int tsdg_localize(tsd_grid_t* grid, tsd_icp_t* icp, const tsd_scan_t* scan, const double* rays_world, const double* scene,
+                  int32_t n_scene, const double* t_init, double t_out[9], double* mse, uint32_t* pairs,
+                  uint32_t* iterations, int32_t* state, uint32_t* n_model);
 /* PairAssignment::determinePairs on its own (registration/icp/assign/PairAssignment.cpp:38-84 with the filters the node
  * wires, ThreadLocalize.cpp:210-221: OutOfBoundsFilter2D.cpp:27-37 before; FlannPairAssignment.cpp:64-92 exact 1-NN;
  * DistanceFilter.cpp:32-64 at its initial threshold and ReciprocalFilter.cpp:32-78 after).  Pairs in model-index

@@ -37,7 +37,7 @@ EXPORTS = [
     "tsdg_create_sharded", "tsdg_sharded_destroy", "tsdg_sharded_num_bands", "tsdg_sharded_band", "tsdg_sharded_set_max_truncation",
     "tsdg_sharded_free_footprint", "tsdg_sharded_push", "tsdg_sharded_push_batch", "tsdg_sharded_sync", "tsdg_sharded_last_push_stats",
     "tsdg_sharded_raycast_mask", "tsdg_sharded_interpolate_bilinear", "tsdg_sharded_partition_states", "tsdg_sharded_download_partition",
-    "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_pairs", "icp_set_trace", "icp_get_trace",
+    "tsdg_localize", "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_pairs", "icp_set_trace", "icp_get_trace",
     "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
 
@@ -131,6 +131,7 @@ def lib():
     L.icp_create.argtypes = [C.c_uint32, C.c_double, C.c_double, C.c_uint32, _dp, C.c_int, _vpp]
     L.icp_destroy.argtypes = [C.c_void_p]
     L.icp_run.argtypes = [C.c_void_p, _dp, _dp, C.c_int32, _dp, C.c_int32, _dp, _dp, _dp, _dp, _up, _up, _ip]
+    L.tsdg_localize.argtypes = [C.c_void_p, C.c_void_p, _sp, _dp, _dp, C.c_int32, _dp, _dp, _dp, _up, _up, _ip, _up]
     L.icp_pairs.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, C.c_int32, _dp, _up, _up, _dp, _up]
     L.icp_set_termination.argtypes = [C.c_void_p, C.c_double, C.c_uint32]
     L.icp_set_max_iterations.argtypes = [C.c_void_p, C.c_uint32]
@@ -617,6 +618,17 @@ class Icp:
         check(lib().icp_run(self.h, _d(model), _d(normals), len(model), _d(scene), len(scene), _d(pose),
                             None if Ti is None else _d(Ti), _d(T), C.byref(mse), C.byref(pairs), C.byref(its), C.byref(st)))
         return T, mse.value, pairs.value, its.value, st.value
+
+    def localize(self, grid, scan, rays_world, scene, Tinit44=None):
+        """tsdg_localize: ray cast from scan.pose + maskMatrix + Icp::iterate with the model kept on the device.
+        Returns (T, mse, pairs, iterations, state, n_model)."""
+        rays, scene = _f64(rays_world), _f64(scene)
+        Ti = None if Tinit44 is None else _f64(Tinit44)
+        T = np.empty((3, 3))
+        mse, pairs, its, st, nm = C.c_double(), C.c_uint32(), C.c_uint32(), C.c_int32(), C.c_uint32()
+        check(lib().tsdg_localize(grid.h, self.h, scan.byref(), _d(rays), _d(scene), len(scene), None if Ti is None else _d(Ti),
+                                  _d(T), C.byref(mse), C.byref(pairs), C.byref(its), C.byref(st), C.byref(nm)))
+        return T, mse.value, pairs.value, its.value, st.value, nm.value
 
     def pairs(self, model, scene, pose):
         """PairAssignment::determinePairs on its own (icp_pairs): (model indices, scene indices, squared distances)."""

@@ -353,6 +353,8 @@ struct tsd_grid
   cudaEvent_t ev_order;
 };
 
+int tsd_raycast_enqueue(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world);  // raycast.cu
+
 #define TSD_LOCK(g)                                      \
   std::unique_lock<std::recursive_mutex> tsd_lock__;     \
   if(g) tsd_lock__ = std::unique_lock<std::recursive_mutex>(*(g)->mtx)

@@ -47,6 +47,7 @@ using namespace tsd;
 struct IcpParams
 {
   int nM, nS;
+  const int* nM_dev;    // if set: the number of model points is read on the device (tsdg_localize: the ray caster's hits)
   int max_iterations;
   unsigned conv_cnt;
   double max_rms;
@@ -90,6 +91,7 @@ struct tsd_icp
   double* h_stage;   // pinned: model + scene
   double* h_result;  // pinned
   int last_nM, last_nS;
+  int* d_nM;         // tsdg_localize: the model's size, counted on the device
   int trace;
   int trace_cap_it;
 };
@@ -243,7 +245,19 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
   const unsigned rank = cluster.block_rank();
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int nM = P.nM, nS = P.nS;
+  const int nM = P.nM_dev ? *P.nM_dev : P.nM, nS = P.nS;
+  if(nM <= 0)
+  {
+    // Icp.cpp:467-471: no model, no registration (the host checks this itself when it knows the count)
+    if(rank == 0 && tid == 0)
+    {
+      for(int i = 0; i < 9; i++) P.result[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      P.result[9] = 0.0; P.result[10] = 0.0; P.result[11] = 0.0;
+      P.result[12] = (double)TSD_ICP_NOTMATCHABLE;
+      P.result[13] = 0.0;
+    }
+    return;  // (every CTA of the cluster, before any of them waits for another)
+  }
   const int nQ = (nS + ICP_CLUSTER - 1) / ICP_CLUSTER;  // queries of this CTA (upper bound)
   const IcpSmem S = icp_carve(smem, nM, nS);
   double* const s_mx = S.mx; double* const s_my = S.my; double* const s_sx = S.sx; double* const s_sy = S.sy;
@@ -835,6 +849,7 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
     P.result[10] = (double)pairs;
     P.result[11] = (double)iter;
     P.result[12] = (double)eRetval;
+    P.result[13] = (double)nM;
 #ifdef ICP_PROFILE
     printf("k_icp %u iterations, cycles per iteration: NN %lld | exchange %lld | recip %lld | gather+sums %lld | pose %lld | apply %lld | loop top %lld\n",
            iter, pf[0] / iter, pf[5] / iter, pf[1] / iter, pf[2] / iter, pf[3] / iter, pf[4] / iter, pf[7] / iter);
@@ -892,6 +907,7 @@ int icp_create(uint32_t max_iterations, double dist_max, double dist_min, uint32
   TSD_CUDA(cudaMalloc(&h->d_model, sizeof(double) * 4 * h->cap));  // model, then scene
   h->d_scene = nullptr;
   TSD_CUDA(cudaMalloc(&h->d_result, sizeof(double) * 16));
+  TSD_CUDA(cudaMalloc(&h->d_nM, sizeof(int)));
   const size_t mi = max_iterations > 0 ? max_iterations : 1;
   h->trace_cap_it = (int)mi;
   TSD_CUDA(cudaMalloc(&h->d_tr_model, sizeof(unsigned) * mi * h->cap));
@@ -912,7 +928,7 @@ int icp_destroy(tsd_icp_t* h)
   if(!h) return TSD_OK;
   cudaSetDevice(h->device);
   if(h->stream) cudaStreamSynchronize(h->stream);
-  cudaFree(h->d_model); cudaFree(h->d_scene); cudaFree(h->d_result); cudaFree(h->d_tr_model); cudaFree(h->d_tr_scene);
+  cudaFree(h->d_model); cudaFree(h->d_scene); cudaFree(h->d_result); cudaFree(h->d_nM); cudaFree(h->d_tr_model); cudaFree(h->d_tr_scene);
   cudaFree(h->d_tr_count); cudaFree(h->d_tr_mse); cudaFree(h->d_tr_T);
   cudaFreeHost(h->h_stage); cudaFreeHost(h->h_result);
   if(h->stream) cudaStreamDestroy(h->stream);
@@ -948,6 +964,7 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   TSD_CUDA(cudaMemcpyAsync(h->d_model, h->h_stage, sizeof(double) * 2 * ((size_t)n_model + n_scene), cudaMemcpyHostToDevice, h->stream));
   IcpParams p = h->p;
   p.nM = n_model;
+  p.nM_dev = nullptr;
   p.nS = n_scene;
   for(int i = 0; i < 9; i++) p.pose[i] = pose[i];
   p.has_init = t_init ? 1 : 0;
@@ -972,6 +989,115 @@ int icp_run(tsd_icp_t* h, const double* model, const double* normals, int32_t n_
   *iterations = (uint32_t)h->h_result[11];
   *state = (int32_t)h->h_result[12];
   h->last_nM = n_model;
+  h->last_nS = n_scene;
+  return TSD_OK;
+}
+
+// ThreadLocalize::maskMatrix (ThreadLocalize.cpp:738-755) on the device: the ray caster's hits, in beam order, become the
+// ICP model.  One block; n <= ICP_MAX_POINTS beams.
+__global__ void __launch_bounds__(1024) k_icp_model_from_raycast(const double* __restrict__ out4, const unsigned long long* __restrict__ keys,
+                                                                 int n, double* __restrict__ model, int* __restrict__ n_model)
+{
+  __shared__ unsigned s_cnt[32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned base = 0;
+  for(int b0 = 0; b0 < n; b0 += 1024)
+  {
+    const int b = b0 + tid;
+    const unsigned long long k = b < n ? keys[b] : 0x7fffffffffffffffULL;
+    const bool hit = k != 0x7fffffffffffffffULL && (k & 3ULL) == 0ULL;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if(lane == 0) s_cnt[tid >> 5] = __popc(bal);
+    __syncthreads();
+    unsigned off = base, total = 0;
+    for(int w = 0; w < 32; w++)
+    {
+      const unsigned c = s_cnt[w];
+      if(w < (tid >> 5)) off += c;
+      total += c;
+    }
+    if(hit)
+    {
+      const unsigned pos = off + __popc(bal & ((1u << lane) - 1u));
+      model[2 * pos] = out4[4 * b];
+      model[2 * pos + 1] = out4[4 * b + 1];
+    }
+    base += total;
+    __syncthreads();
+  }
+  if(tid == 0) *n_model = (int)base;
+}
+
+// One localisation step without the model ever visiting the host: RayCastPolar2D::calcCoordsFromCurrentViewMask, maskMatrix
+// and Icp::iterate (ThreadLocalize.cpp:333-361, :571-581) as three launches on the grid's stream -- ray cast, compaction
+// of the hits into the model, k_icp reading the model's size on the device -- with one upload (scan, ray directions,
+// scene) before and one download (pose, mse, pairs, iterations, state, model size) after.
+int tsdg_localize(tsd_grid_t* g, tsd_icp_t* h, const tsd_scan_t* scan, const double* rays_world, const double* scene,
+                  int32_t n_scene, const double* t_init, double t_out[9], double* mse, uint32_t* pairs, uint32_t* iterations,
+                  int32_t* state, uint32_t* n_model)
+{
+  TSD_LOCK(g);
+  std::unique_lock<std::recursive_mutex> lk2;
+  if(h) lk2 = std::unique_lock<std::recursive_mutex>(*h->mtx);
+  if(!g || !h || !scan || !rays_world || !t_out || !mse || !pairs || !iterations || !state || !n_model) return TSD_E_INVALID;
+  for(int i = 0; i < 9; i++) t_out[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  *mse = 0.0; *pairs = 0; *iterations = 0; *n_model = 0;
+  if(g->device != h->device) { set_error("tsdg_localize: grid and icp handle live on different devices"); return TSD_E_INVALID; }
+  if(scan->n > ICP_MAX_POINTS || n_scene > ICP_MAX_POINTS)
+  {
+    set_error("tsdg_localize supports at most %d beams and scene points", ICP_MAX_POINTS);
+    return TSD_E_INVALID;
+  }
+  if(n_scene > 0 && !scene) return TSD_E_INVALID;
+  TSD_CUDA(cudaSetDevice(g->device));
+  TSD_CUDA(cudaStreamSynchronize(h->stream));  // (an icp_run of another thread's making still owns the staging buffer)
+  int rc = tsd_raycast_enqueue(g, scan, rays_world);
+  if(rc) return rc;
+  if(n_scene <= 0)
+  {
+    // Icp.cpp:467-471; the model's size is still reported
+    k_icp_model_from_raycast<<<1, 1024, 0, g->stream>>>(g->d_rc_out, g->d_rc_keys, scan->n, h->d_model, h->d_nM);
+    TSD_LAUNCHED();
+    int nm = 0;
+    TSD_CUDA(cudaMemcpyAsync(&nm, h->d_nM, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    TSD_CUDA(cudaStreamSynchronize(g->stream));
+    *n_model = (uint32_t)nm;
+    *state = TSD_ICP_NOTMATCHABLE;
+    return TSD_OK;
+  }
+  double* d_scene = h->d_model + 2 * (size_t)h->cap;
+  memcpy(h->h_stage, scene, sizeof(double) * 2 * n_scene);
+  TSD_CUDA(cudaMemcpyAsync(d_scene, h->h_stage, sizeof(double) * 2 * n_scene, cudaMemcpyHostToDevice, g->stream));
+  k_icp_model_from_raycast<<<1, 1024, 0, g->stream>>>(g->d_rc_out, g->d_rc_keys, scan->n, h->d_model, h->d_nM);
+  TSD_LAUNCHED();
+  IcpParams p = h->p;
+  p.nM = scan->n;  // upper bound (shared memory is sized for it)
+  p.nM_dev = h->d_nM;
+  p.nS = n_scene;
+  for(int i = 0; i < 9; i++) p.pose[i] = scan->pose[i];
+  p.has_init = t_init ? 1 : 0;
+  for(int i = 0; i < 16; i++) p.t_init[i] = t_init ? t_init[i] : ((i % 5 == 0) ? 1.0 : 0.0);
+  p.model = h->d_model;
+  p.scene = d_scene;
+  p.result = h->d_result;
+  p.cap = h->cap;
+  p.trace = h->trace;
+  p.tr_model = h->d_tr_model;
+  p.tr_scene = h->d_tr_scene;
+  p.tr_count = h->d_tr_count;
+  p.tr_mse = h->d_tr_mse;
+  p.tr_T = h->d_tr_T;
+  k_icp<<<ICP_CLUSTER, ICP_THREADS, icp_smem_bytes(scan->n, n_scene), g->stream>>>(p);
+  TSD_LAUNCHED();
+  TSD_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, sizeof(double) * 14, cudaMemcpyDeviceToHost, g->stream));
+  TSD_CUDA(cudaStreamSynchronize(g->stream));
+  for(int i = 0; i < 9; i++) t_out[i] = h->h_result[i];
+  *mse = h->h_result[9];
+  *pairs = (uint32_t)h->h_result[10];
+  *iterations = (uint32_t)h->h_result[11];
+  *state = (int32_t)h->h_result[12];
+  *n_model = (uint32_t)h->h_result[13];
+  h->last_nM = (int)*n_model;
   h->last_nS = n_scene;
   return TSD_OK;
 }

@@ -478,6 +478,12 @@ static int raycast_launch(tsd_grid_t* g, const tsd_scan_t* scan, const double* r
   return TSD_OK;
 }
 
+// the ray cast enqueued on the grid's stream, results left on the device (tsdg_localize, icp.cu)
+int tsd_raycast_enqueue(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world)
+{
+  return raycast_launch(g, scan, rays_world, false, false, false);
+}
+
 extern "C" {
 
 int tsdg_raycast_mask(tsd_grid_t* g, const tsd_scan_t* scan, const double* rays_world, double* coords,
