@@ -150,8 +150,15 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
   // hold consecutive control points (also along a contour), so they mostly want the same few groups and the warp
   // stays coherent.  Distances are formed exactly as in the brute-force scan, ties go to the lowest index: the
   // result is the brute-force result (the FLANN stand-in's rule), at ~1/7 of the distance evaluations.
+  //
+  // The box test runs in SINGLE precision on conservatively rounded numbers (boxes rounded outward, the distance bounded
+  // from below by more than the conversion error, the running best rounded up): a double-precision instruction takes two
+  // issue slots on this part, and the 32 box tests per control point were as many of them as the scans they save.
+  // (Screening the POINTS of a group the same way was measured and lost: the lanes of a warp hold different control
+  // points, some lane nearly always needs the exact distance, and the warp then pays for both.)
   const int nGroups = (rp.n_valid + 31) >> 5;
-  double* s_box = s_mphi + rp.n_valid;  // 4 per group: x0 x1 y0 y1
+  float4* s_boxf = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(s_mphi + rp.n_valid) + 15) & ~(uintptr_t)15);  // per group: x0 x1 y0 y1, rounded outward
+  float* s_mabs = reinterpret_cast<float*>(s_boxf + nGroups);       // [0]: largest |coordinate| of the model
   __syncthreads();
   for(int g = threadIdx.x; g < nGroups; g += blockDim.x)
   {
@@ -161,9 +168,18 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
       x0 = fmin(x0, s_mx[k]); x1 = fmax(x1, s_mx[k]);
       y0 = fmin(y0, s_my[k]); y1 = fmax(y1, s_my[k]);
     }
-    s_box[4 * g] = x0; s_box[4 * g + 1] = x1; s_box[4 * g + 2] = y0; s_box[4 * g + 3] = y1;
+    s_boxf[g] = make_float4(__double2float_rd(x0), __double2float_ru(x1), __double2float_rd(y0), __double2float_ru(y1));
   }
   __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    float a = 0.f;
+    for(int g = 0; g < nGroups; g++)
+      a = fmaxf(a, fmaxf(fmaxf(fabsf(s_boxf[g].x), fabsf(s_boxf[g].y)), fmaxf(fabsf(s_boxf[g].z), fabsf(s_boxf[g].w))));
+    s_mabs[0] = a;
+  }
+  __syncthreads();
+  const float mabs = s_mabs[0];
   const int lane = threadIdx.x & 31;
   const int warpsTotal = gridDim.x * MATCH_WARPS;
   for(int h = blockIdx.x * MATCH_WARPS + (threadIdx.x >> 5); h < hc.n_hyp; h += warpsTotal)
@@ -186,6 +202,11 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
       // exact 1-NN among the valid model points ((0 + dx*dx) + dy*dy, lowest index on ties)
       int bi = -1;
       double bd = __longlong_as_double(0x7ff0000000000000LL);
+      float bdf = __int_as_float(0x7f800000);  // bd rounded up
+      // single-precision images of the query and a bound e on |image difference - true difference| per axis:
+      // two conversions (half an ulp each of a magnitude below |x| + |m|) and one subtraction (half an ulp of the result)
+      const float xf = (float)x, yf = (float)y;
+      const float e = 1.3e-7f * (fmaxf(fabsf(xf), fabsf(yf)) + mabs) + 1e-30f;
       auto scan_group = [&](int g)
       {
         const int k1 = min(32 * g + 32, rp.n_valid);
@@ -196,7 +217,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
           double d = 0.0;
           d += d0 * d0;
           d += d1 * d1;
-          if(d < bd || (d == bd && k < bi)) { bd = d; bi = k; }
+          if(d < bd || (d == bd && k < bi)) { bd = d; bi = k; bdf = __double2float_ru(d); }
         }
       };
       // seed with the group the previous control point of this lane ended in (usually the right one already)
@@ -205,11 +226,11 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
       for(int g = 0; g < nGroups; g++)
       {
         if(g == seed) continue;
-        const double ex = fmax(fmax(s_box[4 * g] - x, x - s_box[4 * g + 1]), 0.0);
-        const double ey = fmax(fmax(s_box[4 * g + 2] - y, y - s_box[4 * g + 3]), 0.0);
-        // lower bound of the squared distance to anything in the box, shaved by more than its rounding error
-        const double lb = (ex * ex + ey * ey) * (1.0 - 1e-12);
-        if(lb <= bd) scan_group(g);
+        const float4 b = s_boxf[g];
+        const float ex = fmaxf(fmaxf(b.x - xf, xf - b.y) * (1.f - 2e-7f) - e, 0.f);
+        const float ey = fmaxf(fmaxf(b.z - yf, yf - b.w) * (1.f - 2e-7f) - e, 0.f);
+        // lower bound of the squared distance to anything in the box
+        if((ex * ex + ey * ey) * (1.f - 1e-6f) <= bdf) scan_group(g);
       }
       prevBest = bi;
       if(bi < 0) continue;
@@ -589,7 +610,7 @@ int match_score_rnm(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
   rp.max_cnt_match = a.put<int>(nullptr, n_hyp, &h_max);
   rp.err_sum = a.put<double>(nullptr, n_hyp, &h_err);
   TSD_CUDA(cudaMemcpyAsync(m->d_buf, m->h_buf, inEnd, cudaMemcpyHostToDevice, m->stream));
-  const size_t smem = sizeof(double) * (4 * (size_t)n_control + 3 * (size_t)n_valid + 4 * (((size_t)n_valid + 31) / 32) + 2);
+  const size_t smem = sizeof(double) * (4 * (size_t)n_control + 3 * (size_t)n_valid) + 16 * (((size_t)n_valid + 31) / 32) + 8 * (size_t)n_valid + 32;
   if(smem > 200 * 1024) { set_error("control set / model too large for shared memory"); return TSD_E_INVALID; }
   if(smem > 48 * 1024) TSD_CUDA(cudaFuncSetAttribute(k_score_rnm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sm = 148;
