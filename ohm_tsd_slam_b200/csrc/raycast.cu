@@ -5,10 +5,12 @@
 //
 // The reference marches a beam serially: `position += ray` once per step and `i += 1.0` for the loop bound
 // (`i += 32.0` in the coarse partition-skipping loop).  Those running sums are NOT tr + k*ray in floating
-// point, so every lane of the warp replays the same serial additions (uniform work, 3 DADD per step) and
-// keeps the value of its own step; what is distributed over the lanes is the expensive part, the bilinear
-// sample (4 dependent-latency loads out of L2 + ~40 FP64 ops).  The first +/- sign change (hit) or -/+
-// sign change (abort) of a 32-step chunk is found with two ballots.
+// point.  The positions of a 32-step pass are obtained in closed form where that is exact (same binade, no
+// rounding tie: see `advance` below) and by replaying the serial additions on every lane where it is not; what
+// is distributed over the lanes is the expensive part, the bilinear sample (5 loads + ~40 FP64 ops), with the
+// samples of RC_DEPTH passes in flight.  The first +/- sign change (hit) or -/+ sign change (abort) of a pass is
+// found with two ballots.  On a sharded grid the kernel's epilogue is the all-gather of the per-beam first
+// events (stores into every band's exchange block over peer memory, k_raycast_merge picks the earliest).
 #include <string.h>
 
 #include "common.cuh"
