@@ -29,18 +29,23 @@ struct CLocale
   ~CLocale() { if(c) { uselocale(old); freelocale(c); } }
 };
 
-// tools.cpp:190-215
+// tools.cpp:190-215.  The reference reads a file that ends early as zeros / NaN without a word; here the end of the
+// file is remembered so that tsdg_load can refuse a truncated checkpoint.
+thread_local bool t_hit_eof = false;
+
 double get_double_line(FILE* f)
 {
   char line[1024];
-  if(!fgets(line, sizeof(line), f) || line[0] == '\n' || line[0] == 0) return NAN;
+  if(!fgets(line, sizeof(line), f)) { t_hit_eof = true; return NAN; }
+  if(line[0] == '\n' || line[0] == 0) return NAN;
   return strtod(line, NULL);
 }
 
 int get_int_line(FILE* f)
 {
   char line[1024];
-  if(!fgets(line, sizeof(line), f) || line[0] == '\n' || line[0] == 0) return 0;
+  if(!fgets(line, sizeof(line), f)) { t_hit_eof = true; return 0; }
+  if(line[0] == '\n' || line[0] == 0) return 0;
   return atoi(line);
 }
 
@@ -111,6 +116,7 @@ int tsdg_load(const char* path, int device, tsd_grid_t** out)
   CLocale pinned;
   FILE* f = fopen(path, "r");
   if(!f) { set_error("tsdg_load: cannot open %s", path); return TSD_E_INVALID; }
+  t_hit_eof = false;
   const double cellSize = get_double_line(f);
   const int layoutPartition = get_int_line(f);
   const int layoutGrid = get_int_line(f);
@@ -167,11 +173,25 @@ int tsdg_load(const char* path, int device, tsd_grid_t** out)
         return TSD_E_INVALID;
       }
     }
+    if(t_hit_eof)
+    {
+      fclose(f);
+      set_error("tsdg_load: %s ends in partition row %d of %d: truncated checkpoint", path, y, g->parts_y);
+      tsdg_destroy(g);
+      return TSD_E_INVALID;
+    }
     if(any)
     {
       anyContent = true;
-      cudaMemcpy(g->d_tsd + (size_t)y * rowDoubles, t.data(), sizeof(double) * rowDoubles, cudaMemcpyHostToDevice);
-      cudaMemcpy(g->d_weight + (size_t)y * rowDoubles, w.data(), sizeof(double) * rowDoubles, cudaMemcpyHostToDevice);
+      cudaError_t ce = cudaMemcpy(g->d_tsd + (size_t)y * rowDoubles, t.data(), sizeof(double) * rowDoubles, cudaMemcpyHostToDevice);
+      if(ce == cudaSuccess) ce = cudaMemcpy(g->d_weight + (size_t)y * rowDoubles, w.data(), sizeof(double) * rowDoubles, cudaMemcpyHostToDevice);
+      if(ce != cudaSuccess)
+      {
+        fclose(f);
+        set_error("tsdg_load: %s", cudaGetErrorString(ce));
+        tsdg_destroy(g);
+        return TSD_E_CUDA;
+      }
     }
   }
   fclose(f);

@@ -21,3 +21,6 @@ $NCU --set full --import-source on -k regex:'^k_raycast|^k_icp' --launch-skip 6 
 $NCU --set full --import-source on -k regex:'^k_score' --launch-skip 3 -c 6 -o $O/${R}_full_match \
     python tests/gpu_perf_match.py 20000 > $O/${R}_full_match.log 2>&1
 ls -la $O/${R}_*
+# (the two captures above stop before k_icp and k_score_pdf get their turn: those separately)
+$NCU --set full --import-source on -k regex:'^k_icp' --launch-skip 3 -c 3 -o $O/${R}_full_icp python tests/gpu_perf_icp.py C3 > $O/${R}_full_icp.log 2>&1
+$NCU --set full --import-source on -k regex:'^k_score_pdf' --launch-skip 1 -c 2 -o $O/${R}_full_pdf python tests/gpu_perf_match.py 20000 > $O/${R}_full_pdf.log 2>&1
