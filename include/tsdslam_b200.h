@@ -374,6 +374,38 @@ int match_score_pdf(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
                     int32_t* best, double t_best[9]);
 
 /* ------------------------------------------------------------------------------------------------
+ * Matcher pre-processing on the device: what TSD_PDFMatching.cpp:59-205 == RandomNormalMatching.cpp:94-247
+ * == PDFMatching.cpp:67-233 do on the host before they score -- PCA normals and orientations of model and scene
+ * (RandomMatching::calcNormals / calcPhi, RandomMatching.cpp:77-169), scene subsampling (:171-183), extractSamples (:41-50),
+ * pickControlSet (:52-75), the trial order and the hypothesis list -- for 10^5-hypothesis relocalisation without host work
+ * between the scan and the scores.  DELIBERATE departures from the reference, documented in DESIGN.md: random numbers come
+ * from a counter-based generator, match_rng(seed, stream, index) (SplitMix64 finaliser), not from the sequential libc rand()
+ * -- "keep scene point i" is match_rng(seed, 0, i) % 1000 >= threshold; "K of the valid indices without replacement, in
+ * random order" is "the K smallest keys match_rng(seed, stream, index), in key order" (stream 1: control set, 2: trials) --
+ * and pcaAnalysis' centroid is a double-precision running mean (the reference's is long double).
+ * Every pointer of the result points into pinned host memory owned by the matcher, valid until the next match_prepare /
+ * match_destroy on it; the device keeps a copy: handing these very pointers to match_score_tsd / _rnm / _pdf uploads
+ * nothing.  n_hyp == 0: nothing to score (too few valid points, as RandomNormalMatching.cpp:160-170). */
+typedef struct tsd_match_prep
+{
+  int32_t n, n_hyp, n_control, n_trials, n_valid_m, n_valid_s, span;
+  double phi_max, theta_min, theta_max;
+  const tsd_hypothesis_t* hyps;              /* n_hyp, in trial order, scene index ascending inside a trial */
+  const double *model, *scene;               /* n x 2 (copies of the inputs) */
+  const double *phi_m, *phi_s;               /* n; -1e6 where the mask is off */
+  const uint8_t *mask_m_pca, *mask_s_pca;    /* n */
+  const int32_t *idx_m_valid, *idx_s_valid;  /* n_valid_m, n_valid_s */
+  const int32_t *idx_control, *idx_trials;   /* n_control, n_trials */
+  const double *control, *phi_control;       /* 3 x n_control, n_control */
+  const double *model_valid, *phi_valid;     /* n_valid_m x 2, n_valid_m (match_score_rnm) */
+  const double *model_angles, *model_dists;  /* n_valid_m (match_score_pdf) */
+} tsd_match_prep_t;
+int match_prepare(tsd_matcher_t* m, int32_t n, const double* model, const uint8_t* mask_m, const double* scene,
+                  const uint8_t* mask_s, int32_t pca_search_range, uint32_t size_control_set, uint32_t trials, double phi_max,
+                  double resolution, uint64_t seed, tsd_match_prep_t* out);
+uint64_t match_rng(uint64_t seed, uint32_t stream, uint32_t index);
+
+/* ------------------------------------------------------------------------------------------------
  * One TsdGrid sharded over several devices INSIDE the library (one handle, one process; n_bands bands of whole
  * partition rows, band i on devices[i], or on device i mod #devices when devices is NULL; several bands may share a
  * device).  This is the handle behind obvious::TsdGrid(cellSize, layoutPartition, layoutGrid, nBands) in the adapter

@@ -5,6 +5,7 @@ CUDA device: there is no CPU path behind it."""
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -38,7 +39,7 @@ EXPORTS = [
     "tsdg_sharded_free_footprint", "tsdg_sharded_push", "tsdg_sharded_push_batch", "tsdg_sharded_sync", "tsdg_sharded_last_push_stats",
     "tsdg_sharded_raycast_mask", "tsdg_sharded_interpolate_bilinear", "tsdg_sharded_partition_states", "tsdg_sharded_download_partition",
     "tsdg_localize", "icp_create", "icp_destroy", "icp_set_termination", "icp_set_max_iterations", "icp_run", "icp_pairs", "icp_set_trace", "icp_get_trace",
-    "match_create", "match_destroy", "match_score_tsd", "match_score_rnm", "match_score_pdf",
+    "match_create", "match_destroy", "match_prepare", "match_rng", "match_score_tsd", "match_score_rnm", "match_score_pdf",
 ]
 
 
@@ -139,6 +140,10 @@ def lib():
     L.icp_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _up, _up, _ip, _dp, _dp, _ip]
     L.match_create.argtypes = [C.c_int, _vpp]
     L.match_destroy.argtypes = [C.c_void_p]
+    L.match_prepare.argtypes = [C.c_void_p, C.c_int32, _dp, _bp, _dp, _bp, C.c_int32, C.c_uint32, C.c_uint32, C.c_double, C.c_double,
+                                C.c_uint64, C.POINTER(MatchPrepStruct)]
+    L.match_rng.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
+    L.match_rng.restype = C.c_uint64
     L.match_score_tsd.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, _hp, C.c_int32, _dp, _dp, _dp, _dp, C.c_double,
                                   C.c_int32, _dp, _dp, C.c_double, _dp, _ip, _dp]
     L.match_score_rnm.argtypes = [C.c_void_p, C.c_int32, _hp, C.c_int32, _dp, _dp, _dp, _dp, C.c_double, C.c_int32, _dp,
@@ -660,6 +665,47 @@ def _hyps(h):
     return h, h.ctypes.data_as(_hp)
 
 
+class MatchPrepStruct(C.Structure):
+    """tsd_match_prep_t (include/tsdslam_b200.h)"""
+    _fields_ = [("n", C.c_int32), ("n_hyp", C.c_int32), ("n_control", C.c_int32), ("n_trials", C.c_int32),
+                ("n_valid_m", C.c_int32), ("n_valid_s", C.c_int32), ("span", C.c_int32),
+                ("phi_max", C.c_double), ("theta_min", C.c_double), ("theta_max", C.c_double),
+                ("hyps", C.c_void_p), ("model", C.c_void_p), ("scene", C.c_void_p), ("phi_m", C.c_void_p), ("phi_s", C.c_void_p),
+                ("mask_m_pca", C.c_void_p), ("mask_s_pca", C.c_void_p), ("idx_m_valid", C.c_void_p), ("idx_s_valid", C.c_void_p),
+                ("idx_control", C.c_void_p), ("idx_trials", C.c_void_p), ("control", C.c_void_p), ("phi_control", C.c_void_p),
+                ("model_valid", C.c_void_p), ("phi_valid", C.c_void_p), ("model_angles", C.c_void_p), ("model_dists", C.c_void_p)]
+
+
+class MatchPrep:
+    """Result of match_prepare: numpy copies for inspection + the raw struct, whose pointers name the device-resident set."""
+
+    def __init__(self, raw: MatchPrepStruct):
+        self.raw = raw
+        for f in ("n", "n_hyp", "n_control", "n_trials", "n_valid_m", "n_valid_s", "span", "phi_max", "theta_min", "theta_max"):
+            setattr(self, f, getattr(raw, f))
+
+        def arr(ptr, count, dtype):
+            if count <= 0 or not ptr:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=count).copy()
+        n, c, vm = raw.n, raw.n_control, raw.n_valid_m
+        self.hyps = arr(raw.hyps, 2 * raw.n_hyp, np.int32).reshape(-1, 2)
+        self.phi_m, self.phi_s = arr(raw.phi_m, n, np.float64), arr(raw.phi_s, n, np.float64)
+        self.mask_m_pca, self.mask_s_pca = arr(raw.mask_m_pca, n, np.uint8), arr(raw.mask_s_pca, n, np.uint8)
+        self.idx_m_valid, self.idx_s_valid = arr(raw.idx_m_valid, vm, np.int32), arr(raw.idx_s_valid, raw.n_valid_s, np.int32)
+        self.idx_control, self.idx_trials = arr(raw.idx_control, c, np.int32), arr(raw.idx_trials, raw.n_trials, np.int32)
+        self.control = arr(raw.control, 3 * c, np.float64).reshape(3, c)
+        self.phi_control = arr(raw.phi_control, c, np.float64)
+        self.model_valid = arr(raw.model_valid, 2 * vm, np.float64).reshape(-1, 2)
+        self.phi_valid = arr(raw.phi_valid, vm, np.float64)
+        self.model_angles, self.model_dists = arr(raw.model_angles, vm, np.float64), arr(raw.model_dists, vm, np.float64)
+
+
+def match_rng(seed: int, stream: int, index: int) -> int:
+    return int(lib().match_rng(seed, stream, index))
+
+
 class Matcher:
     """Hypothesis scorers of TSD_PDFMatching / RandomNormalMatching / PDFMatching on the device."""
 
@@ -678,6 +724,49 @@ class Matcher:
             self.close()
         except Exception:
             pass
+
+    def prepare(self, M, mask_m, S, mask_s, pca_search_range=10, size_control_set=360, trials=30, phi_max=math.pi / 4,
+                resolution=0.0, seed=1) -> MatchPrep:
+        """match_prepare: the matchers' pre-processing on the device (counter-based random numbers)."""
+        M, S = _f64(M), _f64(S)
+        mm, ms = np.ascontiguousarray(mask_m, dtype=np.uint8), np.ascontiguousarray(mask_s, dtype=np.uint8)
+        raw = MatchPrepStruct()
+        check(lib().match_prepare(self.h, len(M), _d(M), mm.ctypes.data_as(_bp), _d(S), ms.ctypes.data_as(_bp), pca_search_range,
+                                  size_control_set, trials, phi_max, resolution, seed, C.byref(raw)))
+        return MatchPrep(raw)
+
+    def score_prepared(self, which: str, prep: MatchPrep, grid: "Grid" = None, t_sensor=None, zrand=0.05, scale_distance=1.0,
+                       scale_orientation=1.0, params=None):
+        """Scores the device-resident prepared set (no upload of it): which = "tsd" | "rnm" | "pdf".  Returns (per-hypothesis
+        array(s)..., best, T)."""
+        r = prep.raw
+        nh = r.n_hyp
+        best = C.c_int32()
+        T = np.empty((3, 3))
+        cast = lambda p, t: C.cast(C.c_void_p(p), t)
+        common = (nh, cast(r.hyps, _hp), r.n, cast(r.model, _dp), cast(r.scene, _dp), cast(r.phi_m, _dp), cast(r.phi_s, _dp), r.phi_max,
+                  r.n_control, cast(r.control, _dp))
+        if which == "tsd":
+            score = np.empty(max(nh, 1))
+            ts = _f64(t_sensor)
+            check(lib().match_score_tsd(self.h, grid.h, *common, _d(ts), zrand, _d(score), C.byref(best), _d(T)))
+            return score[:nh], best.value, T
+        if which == "rnm":
+            cnt = np.empty(max(nh, 1), dtype=np.int32)
+            mx = np.empty(max(nh, 1), dtype=np.int32)
+            err = np.empty(max(nh, 1))
+            check(lib().match_score_rnm(self.h, *common, cast(r.phi_control, _dp), r.n_valid_m, cast(r.model_valid, _dp),
+                                        cast(r.phi_valid, _dp), r.theta_min, r.theta_max, scale_distance, scale_orientation,
+                                        r.n_control // 3, cnt.ctypes.data_as(_ip), mx.ctypes.data_as(_ip), _d(err), C.byref(best), _d(T)))
+            return cnt[:nh], mx[:nh], err[:nh], best.value, T
+        if which == "pdf":
+            prob = np.empty(max(nh, 1))
+            fov = np.empty(max(nh, 1), dtype=np.int32)
+            pr = _f64(params)
+            check(lib().match_score_pdf(self.h, *common, r.n_valid_m, cast(r.model_angles, _dp), cast(r.model_dists, _dp), _d(pr),
+                                        _d(prob), fov.ctypes.data_as(_ip), C.byref(best), _d(T)))
+            return prob[:nh], fov[:nh], best.value, T
+        raise ValueError(which)
 
     def score_tsd(self, grid: Grid, hyps, M, S, phi_m, phi_s, phi_max, control, t_sensor, zrand):
         h, hp = _hyps(hyps)

@@ -24,6 +24,11 @@ struct tsd_matcher
   size_t cap;
   void* d_buf;
   void* h_buf;  // pinned
+  // match_prepare's result: one block on the device and its mirror in pinned host memory, same layout, so that a host
+  // pointer into the mirror names its device twin (resident())
+  size_t prep_cap, prep_bytes;
+  unsigned char* d_prep;
+  unsigned char* h_prep;
 };
 
 struct HypCommon
@@ -398,6 +403,352 @@ __global__ void __launch_bounds__(1024) k_first_max(int n, const double* score, 
   }
 }
 
+// ---------------------------------------------------------------- matcher pre-processing on the device
+// RandomMatching.cpp:41-183 (extractSamples, pickControlSet, calcNormals, calcPhi, subsampleMask) and the trial /
+// hypothesis enumeration of the three matchers (TSD_PDFMatching.cpp:59-205 == RandomNormalMatching.cpp:94-247 ==
+// PDFMatching.cpp:67-233), so that a relocalisation with 10^5 hypotheses needs no host work between the scan and the
+// scores.  Two DELIBERATE departures from the reference, both confined to this entry point (the adapter's match() keeps
+// the reference's host code and libc rand() so that its goldens can be replayed):
+//   * random numbers come from a counter-based generator (SplitMix64 finaliser over (seed, stream, index)) instead of the
+//     sequential rand(): "keep point i" is rng(seed, 0, i) % 1000 >= threshold as in subsampleMask; "draw K of the valid
+//     indices without replacement, in random order" is "the K smallest of the keys rng(seed, stream, index), in key order"
+//     -- the same distribution as erasing random elements of a shrinking vector, but a function of (seed, index) that
+//     every thread can evaluate on its own;
+//   * the centroid inside pcaAnalysis is a running mean in double precision (gsl_stats_mean uses long double, which the
+//     device does not have): normals agree with the reference's to ~1e-15.
+__host__ __device__ __forceinline__ uint64_t tsd_rng(uint64_t seed, uint32_t stream, uint32_t idx)
+{
+  uint64_t z = seed + 0x9E3779B97F4A7C15ULL * ((((uint64_t)stream << 32) | idx) + 1ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+#define PREP_MAX_WINDOW 32
+
+__device__ double prep_nrm2(const double* x, int n, int stride)  // gslcblas source_nrm2_r.h
+{
+  double scale = 0.0, ssq = 1.0;
+  if(n == 1) return fabs(x[0]);
+  for(int i = 0; i < n; i++)
+  {
+    const double v = x[i * stride];
+    if(v != 0.0)
+    {
+      const double ax = fabs(v);
+      if(scale < ax) { ssq = 1.0 + ssq * (scale / ax) * (scale / ax); scale = ax; }
+      else { ssq += (ax / scale) * (ax / scale); }
+    }
+  }
+  return scale * sqrt(ssq);
+}
+
+// obvious::Matrix::pcaAnalysis for a rows x 2 matrix (gsl/Matrix.cpp:227-327: centroid, M'M, one-sided Jacobi SVD,
+// projections, extents); only the short axis' direction and the two squared lengths are handed back
+__device__ void prep_pca(const double* Ain, int rows, double* xShort, double* yShort, double* lenLongSqr, double* lenShortSqr)
+{
+  const double eps = 2.2204460492503131e-16;
+  double M[2 * PREP_MAX_WINDOW];
+  double cent[2];
+  for(int c = 0; c < 2; c++)
+  {
+    double mean = 0.0;
+    for(int i = 0; i < rows; i++) mean += (Ain[2 * i + c] - mean) / (double)(i + 1);
+    cent[c] = mean;
+  }
+  for(int c = 0; c < 2; c++)
+    for(int i = 0; i < rows; i++) M[2 * i + c] = Ain[2 * i + c] + -cent[c];
+  double A[4] = {0.0, 0.0, 0.0, 0.0};
+  for(int k = 0; k < rows; k++)
+    for(int i = 0; i < 2; i++)
+    {
+      const double temp = 1.0 * M[2 * k + i];
+      if(temp != 0.0)
+        for(int j = 0; j < 2; j++) A[2 * i + j] += temp * M[2 * k + j];
+    }
+  double V[4] = {1.0, 0.0, 0.0, 1.0}, S[2];
+  const double tolerance = 10 * 2 * eps;
+  for(int j = 0; j < 2; j++) S[j] = eps * prep_nrm2(A + j, 2, 2);
+  int count = 1, sweep = 0;
+  while(count > 0 && sweep <= 12)
+  {
+    count = 1;
+    double pp = 0.0;
+    for(int i = 0; i < 2; i++) pp += A[2 * i] * A[2 * i + 1];
+    pp *= 2.0;
+    const double a = prep_nrm2(A, 2, 2), b = prep_nrm2(A + 1, 2, 2);
+    const double q = a * a - b * b;
+    const double v = hypot(pp, q);
+    const double abserr_a = S[0], abserr_b = S[1];
+    const bool sorted = (a >= b), orthog = (fabs(pp) <= tolerance * (a * b)), noisya = (a < abserr_a), noisyb = (b < abserr_b);
+    if(sorted && (orthog || noisya || noisyb)) count--;
+    else
+    {
+      double cosine, sine;
+      if(v == 0 || !sorted) { cosine = 0.0; sine = 1.0; }
+      else
+      {
+        cosine = sqrt((v + q) / (2.0 * v));
+        sine = pp / (2.0 * v * cosine);
+      }
+      for(int i = 0; i < 2; i++)
+      {
+        const double Aik = A[2 * i + 1], Aij = A[2 * i];
+        A[2 * i] = Aij * cosine + Aik * sine;
+        A[2 * i + 1] = -Aij * sine + Aik * cosine;
+      }
+      S[0] = fabs(cosine) * abserr_a + fabs(sine) * abserr_b;
+      S[1] = fabs(sine) * abserr_a + fabs(cosine) * abserr_b;
+      for(int i = 0; i < 2; i++)
+      {
+        const double Qij = V[2 * i], Qik = V[2 * i + 1];
+        V[2 * i] = Qij * cosine + Qik * sine;
+        V[2 * i + 1] = -Qij * sine + Qik * cosine;
+      }
+    }
+    sweep++;
+  }
+  // extents of the projections on the two axes; the axes' end points are centre -+ V(:, i) * ext / 2, so their
+  // difference is V(:, i) * ext up to the rounding of (c + e) - (c - e), which is replayed
+  double ext[2], mid[2];
+  for(int i = 0; i < 2; i++)
+  {
+    double mx = 0.0, mn = 0.0;
+    for(int j = 0; j < rows; j++)
+    {
+      double temp = 0.0;
+      for(int k = 0; k < 2; k++) temp += V[2 * k + i] * M[2 * j + k];
+      const double pj = 0.0 + 1.0 * temp;
+      if(j == 0) { mx = pj; mn = pj; }
+      else { if(pj > mx) mx = pj; if(pj < mn) mn = pj; }
+    }
+    ext[i] = mx - mn;
+    mid[i] = (ext[i] > 1e-6) ? (mx + mn) / 2.0 : 0.0;
+  }
+  for(int i = 0; i < 2; i++)
+    for(int j = 0; j < 2; j++) cent[j] += V[2 * j + i] * mid[i];
+  double d[2][2];
+  for(int i = 0; i < 2; i++)
+    for(int j = 0; j < 2; j++)
+    {
+      const double e = V[2 * j + i] * ext[i] / 2.0;
+      d[i][j] = (cent[j] + e) - (cent[j] - e);
+    }
+  *lenLongSqr = d[0][0] * d[0][0] + d[0][1] * d[0][1];
+  *xShort = d[1][0];
+  *yShort = d[1][1];
+  *lenShortSqr = d[1][0] * d[1][0] + d[1][1] * d[1][1];
+}
+
+// RandomMatching::calcNormals (RandomMatching.cpp:77-146) + calcPhi (:148-169) for point i
+__device__ void prep_normal(const double* P, const uint8_t* maskIn, uint8_t* maskOut, double* N, double* phi, int points, int r, int i)
+{
+  if(i < r || i >= points - r) { maskOut[i] = 0; phi[i] = -1e6; N[2 * i] = 0.0; N[2 * i + 1] = 0.0; return; }
+  N[2 * i] = 0.0; N[2 * i + 1] = 0.0;
+  if(maskIn[i])
+  {
+    double A[2 * PREP_MAX_WINDOW];
+    int cnt = 0;
+    for(int j = -r; j < r; j++)
+      if(maskIn[i + j]) { A[2 * cnt] = P[2 * (i + j)]; A[2 * cnt + 1] = P[2 * (i + j) + 1]; cnt++; }
+    if(cnt > 3)
+    {
+      double xs, ys, ll, ls;
+      prep_pca(A, cnt, &xs, &ys, &ll, &ls);
+      if(ls > 1e-6 && (ll / ls) < 4.0) maskOut[i] = 0;
+      else
+      {
+        const double len = sqrt(ls);
+        if((P[2 * i] * xs + P[2 * i + 1] * ys) < 0.0) { N[2 * i] = xs / len; N[2 * i + 1] = ys / len; }
+        else { N[2 * i] = -xs / len; N[2 * i + 1] = -ys / len; }
+      }
+    }
+    else maskOut[i] = 0;
+  }
+  phi[i] = maskOut[i] ? atan2(N[2 * i + 1], N[2 * i]) : -1e6;
+}
+
+struct PrepParams
+{
+  int n, r;
+  unsigned size_control, trials;
+  int span;
+  uint64_t seed;
+  const double* M;
+  const double* S;
+  const uint8_t* maskM;
+  const uint8_t* maskS;
+  uint8_t* maskMpca;
+  uint8_t* maskSpca;
+  double* NM;   // scratch n x 2
+  double* NS;
+  double* phiM;
+  double* phiS;
+  int* idxM;    // n
+  int* idxS;
+  int* idxControl;
+  int* idxTrials;
+  int* prefS;   // n + 1: number of valid (post-PCA) scene points before index i
+  unsigned* hypOff;  // trials + 1
+  double* control;   // 3 x C
+  double* phiControl;
+  double* modelValid;  // nValidM x 2
+  double* phiValid;
+  double* modelAngles;
+  double* modelDists;
+  int* header;       // [0] nValidM [1] nValidS [2] nControl [3] nTrials [4] nHyp
+  double* headerD;   // [0] thetaMin [1] thetaMax
+};
+
+// ordered compaction of the indices i in [r, n - r) with mask[i] (extractSamples); one block
+__device__ int prep_compact(const uint8_t* mask, int n, int r, int* out, unsigned* s_scan)
+{
+  const int tid = threadIdx.x, lane = tid & 31, nw = blockDim.x >> 5;
+  int base = 0;
+  for(int i0 = 0; i0 < n; i0 += blockDim.x)
+  {
+    const int i = i0 + tid;
+    const bool v = i >= r && i < n - r && mask[i];
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    if(lane == 0) s_scan[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int off = base, total = 0;
+    for(int w = 0; w < nw; w++)
+    {
+      const int c = (int)s_scan[w];
+      if(w < (tid >> 5)) off += c;
+      total += c;
+    }
+    if(v) out[off + __popc(bal & ((1u << lane) - 1u))] = i;
+    base += total;
+    __syncthreads();
+  }
+  return base;
+}
+
+// the K entries of idx[0..nv) with the smallest (rng(seed, stream, idx), idx), in that order
+__device__ void prep_pick(const int* idx, int nv, int K, uint64_t seed, uint32_t stream, int* out)
+{
+  for(int a = threadIdx.x; a < nv; a += blockDim.x)
+  {
+    const uint64_t ka = tsd_rng(seed, stream, (uint32_t)idx[a]);
+    int rank = 0;
+    for(int b = 0; b < nv; b++)
+    {
+      const uint64_t kb = tsd_rng(seed, stream, (uint32_t)idx[b]);
+      rank += (kb < ka || (kb == ka && b < a)) ? 1 : 0;
+    }
+    if(rank < K) out[rank] = idx[a];
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_prepare(PrepParams pp)
+{
+  __shared__ unsigned s_scan[40];
+  const int tid = threadIdx.x, n = pp.n, r = pp.r;
+  // ----- model: normals, orientations, valid indices
+  for(int i = tid; i < n; i += blockDim.x) pp.maskMpca[i] = pp.maskM[i];
+  __syncthreads();
+  for(int i = tid; i < n; i += blockDim.x) prep_normal(pp.M, pp.maskM, pp.maskMpca, pp.NM, pp.phiM, n, r, i);
+  __syncthreads();
+  const int nvm = prep_compact(pp.maskMpca, n, r, pp.idxM, s_scan);
+  // ----- scene: subsampling (RandomNormalMatching.cpp:126-131, RandomMatching.cpp:171-183), then the same
+  int valid = 0;
+  for(int i = tid; i < n; i += blockDim.x) valid += pp.maskS[i] ? 1 : 0;
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  if((tid & 31) == 0) s_scan[tid >> 5] = (unsigned)valid;
+  __syncthreads();
+  valid = 0;
+  for(int w = 0; w < (int)(blockDim.x >> 5); w++) valid += (int)s_scan[w];
+  __syncthreads();
+  double probability = 180.0 / (double)valid;
+  int thresh = 0;
+  if(probability < 0.99)
+  {
+    if(probability < 0.0) probability = 0.0;
+    thresh = (int)(1000.0 - probability * 1000.0 + 0.5);
+  }
+  for(int i = tid; i < n; i += blockDim.x)
+  {
+    uint8_t keep = pp.maskS[i];
+    if(thresh > 0 && (int)(tsd_rng(pp.seed, 0u, (uint32_t)i) % 1000ULL) < thresh) keep = 0;
+    pp.maskSpca[i] = keep;
+  }
+  __syncthreads();
+  for(int i = tid; i < n; i += blockDim.x) prep_normal(pp.S, pp.maskS, pp.maskSpca, pp.NS, pp.phiS, n, r, i);
+  __syncthreads();
+  const int nvs = prep_compact(pp.maskSpca, n, r, pp.idxS, s_scan);
+  // ----- control set (pickControlSet) and trial order
+  const int C = min((int)pp.size_control, nvs);
+  const int T = min((int)pp.trials, nvm);
+  prep_pick(pp.idxS, nvs, C, pp.seed, 1u, pp.idxControl);
+  prep_pick(pp.idxM, nvm, T, pp.seed, 2u, pp.idxTrials);
+  // valid scene points before index i
+  if(tid == 0)
+  {
+    int acc = 0;
+    for(int i = 0; i < n; i++) { pp.prefS[i] = acc; acc += pp.maskSpca[i] ? 1 : 0; }
+    pp.prefS[n] = acc;
+  }
+  __syncthreads();
+  for(int c = tid; c < C; c += blockDim.x)
+  {
+    const int idx = pp.idxControl[c];
+    pp.control[c] = pp.S[2 * idx];
+    pp.control[C + c] = pp.S[2 * idx + 1];
+    pp.control[2 * C + c] = 1.0;
+    pp.phiControl[c] = atan2(pp.NS[2 * idx + 1], pp.NS[2 * idx]);
+  }
+  for(int k = tid; k < nvm; k += blockDim.x)
+  {
+    const int idx = pp.idxM[k];
+    const double x = pp.M[2 * idx], y = pp.M[2 * idx + 1];
+    pp.modelValid[2 * k] = x;
+    pp.modelValid[2 * k + 1] = y;
+    pp.phiValid[k] = pp.phiM[idx];
+    pp.modelAngles[k] = atan2(y, x);
+    pp.modelDists[k] = sqrt(x * x + y * y);
+  }
+  // ----- hypotheses per trial: the valid scene indices in [max(idx - span, r), min(idx + span, n - r))
+  if(tid == 0)
+  {
+    unsigned acc = 0;
+    for(int t = 0; t < T; t++)
+    {
+      const int idx = pp.idxTrials[t];
+      const int iMin = max(idx - pp.span, r), iMax = min(idx + pp.span, n - r);
+      pp.hypOff[t] = acc;
+      if(iMax > iMin) acc += (unsigned)(pp.prefS[iMax] - pp.prefS[iMin]);
+    }
+    pp.hypOff[T] = acc;
+    pp.header[0] = nvm; pp.header[1] = nvs; pp.header[2] = C; pp.header[3] = T; pp.header[4] = (int)acc;
+    if(nvm > 0)
+    {
+      pp.headerD[0] = atan2(pp.M[2 * pp.idxM[0] + 1], pp.M[2 * pp.idxM[0]]);
+      pp.headerD[1] = atan2(pp.M[2 * pp.idxM[nvm - 1] + 1], pp.M[2 * pp.idxM[nvm - 1]]);
+    }
+    else { pp.headerD[0] = 0.0; pp.headerD[1] = 0.0; }
+  }
+}
+
+// block t writes the hypotheses of trial t, in scene order, at their place in the list
+__global__ void __launch_bounds__(256) k_prepare_emit(PrepParams pp, tsd_hypothesis_t* hyps, unsigned cap)
+{
+  const int T = pp.header[3];
+  for(int t = blockIdx.x; t < T; t += gridDim.x)
+  {
+    const int idx = pp.idxTrials[t];
+    const int iMin = max(idx - pp.span, pp.r), iMax = min(idx + pp.span, pp.n - pp.r);
+    const unsigned off = pp.hypOff[t];
+    for(int i = iMin + (int)threadIdx.x; i < iMax; i += blockDim.x)
+      if(pp.maskSpca[i])
+      {
+        const unsigned at = off + (unsigned)(pp.prefS[i] - pp.prefS[iMin]);
+        if(at < cap) { hyps[at].idx_model = idx; hyps[at].idx_scene = i; }
+      }
+  }
+}
+
 // ---------------------------------------------------------------- host side
 static int ensure(tsd_matcher* m, size_t bytes)
 {
@@ -434,6 +785,17 @@ struct Arena
 };
 
 static size_t a16(size_t b) { return ((b + 15) / 16) * 16; }
+
+// An input array that lies inside the mirror of the prepared set (match_prepare) is already on the device: its twin sits
+// at the same offset of the device block.  Everything else is staged and uploaded as before.
+template <typename T>
+static const T* put_in(tsd_matcher* m, Arena& a, const T* src, size_t count)
+{
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(src);
+  if(src && m->h_prep && p >= m->h_prep && p + sizeof(T) * count <= m->h_prep + m->prep_bytes)
+    return reinterpret_cast<const T*>(m->d_prep + (p - m->h_prep));
+  return a.put(src, count);
+}
 
 static void set_identity3(double T[9])
 {
@@ -496,6 +858,8 @@ int match_destroy(tsd_matcher_t* m)
   if(m->stream) cudaStreamSynchronize(m->stream);
   cudaFree(m->d_buf);
   cudaFreeHost(m->h_buf);
+  cudaFree(m->d_prep);
+  cudaFreeHost(m->h_prep);
   if(m->stream) cudaStreamDestroy(m->stream);
   cudaGetLastError();
   delete m->mtx;
@@ -528,14 +892,14 @@ int match_score_tsd(tsd_matcher_t* m, tsd_grid_t* grid, int32_t n_hyp, const tsd
   Arena a{(unsigned char*)m->h_buf, (unsigned char*)m->d_buf, 0};
   HypCommon hc;
   hc.n_hyp = n_hyp;
-  hc.hyps = a.put(hyps, n_hyp);
-  hc.model = a.put(model, 2 * (size_t)n);
-  hc.scene = a.put(scene, 2 * (size_t)n);
-  hc.phi_m = a.put(phi_m, n);
-  hc.phi_s = a.put(phi_s, n);
+  hc.hyps = put_in(m, a, hyps, n_hyp);
+  hc.model = put_in(m, a, model, 2 * (size_t)n);
+  hc.scene = put_in(m, a, scene, 2 * (size_t)n);
+  hc.phi_m = put_in(m, a, phi_m, n);
+  hc.phi_s = put_in(m, a, phi_s, n);
   hc.phi_max = phi_max;
   hc.n_control = n_control;
-  hc.control = a.put(control, 3 * (size_t)n_control + (n_control == 0 ? 1 : 0));
+  hc.control = put_in(m, a, control, 3 * (size_t)n_control + (n_control == 0 ? 1 : 0));
   const double* d_ts = a.put(t_sensor, 9);
   const size_t inEnd = a.off;
   double* h_score;
@@ -586,19 +950,19 @@ int match_score_rnm(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
   Arena a{(unsigned char*)m->h_buf, (unsigned char*)m->d_buf, 0};
   HypCommon hc;
   hc.n_hyp = n_hyp;
-  hc.hyps = a.put(hyps, n_hyp);
-  hc.model = a.put(model, 2 * (size_t)n);
-  hc.scene = a.put(scene, 2 * (size_t)n);
-  hc.phi_m = a.put(phi_m, n);
-  hc.phi_s = a.put(phi_s, n);
+  hc.hyps = put_in(m, a, hyps, n_hyp);
+  hc.model = put_in(m, a, model, 2 * (size_t)n);
+  hc.scene = put_in(m, a, scene, 2 * (size_t)n);
+  hc.phi_m = put_in(m, a, phi_m, n);
+  hc.phi_s = put_in(m, a, phi_s, n);
   hc.phi_max = phi_max;
   hc.n_control = n_control;
-  hc.control = a.put(control, 3 * (size_t)n_control + (n_control == 0 ? 1 : 0));
+  hc.control = put_in(m, a, control, 3 * (size_t)n_control + (n_control == 0 ? 1 : 0));
   RnmParams rp;
-  rp.phi_control = a.put(phi_control, (size_t)n_control + (n_control == 0 ? 1 : 0));
+  rp.phi_control = put_in(m, a, phi_control, (size_t)n_control + (n_control == 0 ? 1 : 0));
   rp.n_valid = n_valid;
-  rp.model_valid = a.put(model_valid, 2 * (size_t)n_valid + (n_valid == 0 ? 1 : 0));
-  rp.phi_valid = a.put(phi_valid, (size_t)n_valid + (n_valid == 0 ? 1 : 0));
+  rp.model_valid = put_in(m, a, model_valid, 2 * (size_t)n_valid + (n_valid == 0 ? 1 : 0));
+  rp.phi_valid = put_in(m, a, phi_valid, (size_t)n_valid + (n_valid == 0 ? 1 : 0));
   rp.theta_min = theta_min;
   rp.theta_max = theta_max;
   rp.scale_distance = scale_distance;
@@ -671,21 +1035,21 @@ int match_score_pdf(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
   Arena a{(unsigned char*)m->h_buf, (unsigned char*)m->d_buf, 0};
   HypCommon hc;
   hc.n_hyp = n_hyp;
-  hc.hyps = a.put(hyps, n_hyp);
-  hc.model = a.put(model, 2 * (size_t)n);
-  hc.scene = a.put(scene, 2 * (size_t)n);
-  hc.phi_m = a.put(phi_m, n);
-  hc.phi_s = a.put(phi_s, n);
+  hc.hyps = put_in(m, a, hyps, n_hyp);
+  hc.model = put_in(m, a, model, 2 * (size_t)n);
+  hc.scene = put_in(m, a, scene, 2 * (size_t)n);
+  hc.phi_m = put_in(m, a, phi_m, n);
+  hc.phi_s = put_in(m, a, phi_s, n);
   hc.phi_max = phi_max;
   hc.n_control = n_control;
-  hc.control = a.put(control, 3 * (size_t)n_control + (n_control == 0 ? 1 : 0));
+  hc.control = put_in(m, a, control, 3 * (size_t)n_control + (n_control == 0 ? 1 : 0));
   PdfParams pp;
   pp.n_valid = n_valid;
   pp.sorted = 1;
   for(int k = 1; k < n_valid; k++)
     if(!(model_angles[k - 1] < model_angles[k])) { pp.sorted = 0; break; }
-  pp.model_angles = a.put(model_angles, n_valid);
-  pp.model_dists = a.put(model_dists, n_valid);
+  pp.model_angles = put_in(m, a, model_angles, n_valid);
+  pp.model_dists = put_in(m, a, model_dists, n_valid);
   for(int i = 0; i < 12; i++) pp.p[i] = params[i];
   const size_t inEnd = a.off;
   double* h_prob;
@@ -713,5 +1077,118 @@ int match_score_pdf(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
   best_transform(*best, hyps, model, scene, phi_m, phi_s, t_best);
   return TSD_OK;
 }
+
+int match_prepare(tsd_matcher_t* m, int32_t n, const double* model, const uint8_t* mask_m, const double* scene,
+                  const uint8_t* mask_s, int32_t pca_search_range, uint32_t size_control_set, uint32_t trials, double phi_max,
+                  double resolution, uint64_t seed, tsd_match_prep_t* out)
+{
+  TSD_LOCK(m);
+  if(!m || !out || n < 3 || !model || !mask_m || !scene || !mask_s) return TSD_E_INVALID;
+  memset(out, 0, sizeof(*out));
+  const int r = pca_search_range / 2;
+  if(r < 1 || 2 * r > PREP_MAX_WINDOW) { set_error("match_prepare: pca_search_range must be 2 .. %d", PREP_MAX_WINDOW); return TSD_E_INVALID; }
+  if(n > 4096) { set_error("match_prepare supports at most 4096 points"); return TSD_E_INVALID; }
+  // RandomNormalMatching.cpp:184-197
+  if(!(phi_max <= M_PI * 0.5)) phi_max = M_PI * 0.5;
+  if(!(resolution > 1e-6)) { set_error("match_prepare: resolution not properly set (%g)", resolution); return TSD_E_INVALID; }
+  int span = (int)floor(phi_max / resolution);
+  if(span > n) span = n;
+  if(span < 0) span = 0;
+  const size_t tmax = std::min<size_t>(trials, (size_t)n), cmax = std::min<size_t>(size_control_set, (size_t)n);
+  const size_t capHyp = tmax * std::min<size_t>(2 * (size_t)span, (size_t)n) + 1;
+  TSD_CUDA(cudaSetDevice(m->device));
+  TSD_CUDA(cudaStreamSynchronize(m->stream));
+  // layout of the block (identical on both sides)
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t at = off; off += a16(bytes); return at; };
+  const size_t oM = take(16 * (size_t)n), oS = take(16 * (size_t)n), oMaskM = take(n), oMaskS = take(n);
+  const size_t inEnd = off;
+  const size_t oMaskMp = take(n), oMaskSp = take(n), oNM = take(16 * (size_t)n), oNS = take(16 * (size_t)n);
+  const size_t oPhiM = take(8 * (size_t)n), oPhiS = take(8 * (size_t)n), oIdxM = take(4 * (size_t)n), oIdxS = take(4 * (size_t)n);
+  const size_t oIdxC = take(4 * (cmax + 1)), oIdxT = take(4 * (tmax + 1)), oPref = take(4 * ((size_t)n + 1)), oHypOff = take(4 * (tmax + 2));
+  const size_t oCtrl = take(8 * 3 * (cmax + 1)), oPhiC = take(8 * (cmax + 1));
+  const size_t oMV = take(16 * (size_t)n), oPV = take(8 * (size_t)n), oAng = take(8 * (size_t)n), oDst = take(8 * (size_t)n);
+  const size_t oHdr = take(32), oHdrD = take(16);
+  const size_t fixedEnd = off;
+  const size_t oHyps = take(sizeof(tsd_hypothesis_t) * capHyp);
+  if(off > m->prep_cap)
+  {
+    if(m->d_prep) cudaFree(m->d_prep);
+    if(m->h_prep) cudaFreeHost(m->h_prep);
+    m->d_prep = m->h_prep = nullptr;
+    m->prep_cap = m->prep_bytes = 0;
+    size_t cap = 1 << 20;
+    while(cap < off) cap <<= 1;
+    TSD_CUDA(cudaMalloc(&m->d_prep, cap));
+    TSD_CUDA(cudaMallocHost(&m->h_prep, cap));
+    m->prep_cap = cap;
+  }
+  m->prep_bytes = 0;  // (nothing is resident until this call has succeeded)
+  unsigned char *H = m->h_prep, *D = m->d_prep;
+  memcpy(H + oM, model, 16 * (size_t)n);
+  memcpy(H + oS, scene, 16 * (size_t)n);
+  memcpy(H + oMaskM, mask_m, n);
+  memcpy(H + oMaskS, mask_s, n);
+  TSD_CUDA(cudaMemcpyAsync(D, H, inEnd, cudaMemcpyHostToDevice, m->stream));
+  PrepParams pp;
+  pp.n = n; pp.r = r; pp.size_control = (unsigned)cmax; pp.trials = (unsigned)tmax; pp.span = span; pp.seed = seed;
+  pp.M = (const double*)(D + oM); pp.S = (const double*)(D + oS);
+  pp.maskM = D + oMaskM; pp.maskS = D + oMaskS; pp.maskMpca = D + oMaskMp; pp.maskSpca = D + oMaskSp;
+  pp.NM = (double*)(D + oNM); pp.NS = (double*)(D + oNS); pp.phiM = (double*)(D + oPhiM); pp.phiS = (double*)(D + oPhiS);
+  pp.idxM = (int*)(D + oIdxM); pp.idxS = (int*)(D + oIdxS); pp.idxControl = (int*)(D + oIdxC); pp.idxTrials = (int*)(D + oIdxT);
+  pp.prefS = (int*)(D + oPref); pp.hypOff = (unsigned*)(D + oHypOff);
+  pp.control = (double*)(D + oCtrl); pp.phiControl = (double*)(D + oPhiC);
+  pp.modelValid = (double*)(D + oMV); pp.phiValid = (double*)(D + oPV); pp.modelAngles = (double*)(D + oAng); pp.modelDists = (double*)(D + oDst);
+  pp.header = (int*)(D + oHdr); pp.headerD = (double*)(D + oHdrD);
+  k_prepare<<<1, 1024, 0, m->stream>>>(pp);
+  TSD_LAUNCHED();
+  k_prepare_emit<<<(unsigned)std::max<size_t>(tmax, 1), 256, 0, m->stream>>>(pp, (tsd_hypothesis_t*)(D + oHyps), (unsigned)capHyp);
+  TSD_LAUNCHED();
+  TSD_CUDA(cudaMemcpyAsync(H + inEnd, D + inEnd, fixedEnd - inEnd, cudaMemcpyDeviceToHost, m->stream));
+  TSD_CUDA(cudaStreamSynchronize(m->stream));
+  const int* hdr = (const int*)(H + oHdr);
+  const double* hdrD = (const double*)(H + oHdrD);
+  const int nvm = hdr[0], nvs = hdr[1];
+  int nHyp = hdr[4];
+  if((size_t)nHyp > capHyp) { set_error("match_prepare: hypothesis list overflow (%d > %zu)", nHyp, capHyp); return TSD_E_INVALID; }
+  // RandomNormalMatching.cpp:160-170: too few valid points -> no match
+  if(nvs < 3 || nvm < 3) nHyp = 0;
+  if(nHyp > 0)
+  {
+    TSD_CUDA(cudaMemcpyAsync(H + oHyps, D + oHyps, sizeof(tsd_hypothesis_t) * (size_t)nHyp, cudaMemcpyDeviceToHost, m->stream));
+    TSD_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  m->prep_bytes = oHyps + sizeof(tsd_hypothesis_t) * (size_t)nHyp;
+  out->n = n;
+  out->n_hyp = nHyp;
+  out->n_control = hdr[2];
+  out->n_trials = hdr[3];
+  out->n_valid_m = nvm;
+  out->n_valid_s = nvs;
+  out->span = span;
+  out->phi_max = phi_max;
+  out->theta_min = hdrD[0];
+  out->theta_max = hdrD[1];
+  out->hyps = (const tsd_hypothesis_t*)(H + oHyps);
+  out->model = (const double*)(H + oM);
+  out->scene = (const double*)(H + oS);
+  out->phi_m = (const double*)(H + oPhiM);
+  out->phi_s = (const double*)(H + oPhiS);
+  out->mask_m_pca = H + oMaskMp;
+  out->mask_s_pca = H + oMaskSp;
+  out->idx_m_valid = (const int32_t*)(H + oIdxM);
+  out->idx_s_valid = (const int32_t*)(H + oIdxS);
+  out->idx_control = (const int32_t*)(H + oIdxC);
+  out->idx_trials = (const int32_t*)(H + oIdxT);
+  out->control = (const double*)(H + oCtrl);
+  out->phi_control = (const double*)(H + oPhiC);
+  out->model_valid = (const double*)(H + oMV);
+  out->phi_valid = (const double*)(H + oPV);
+  out->model_angles = (const double*)(H + oAng);
+  out->model_dists = (const double*)(H + oDst);
+  return TSD_OK;
+}
+
+uint64_t match_rng(uint64_t seed, uint32_t stream, uint32_t index) { return tsd_rng(seed, stream, index); }
 
 }  // extern "C"
