@@ -679,10 +679,12 @@ class MatchPrepStruct(C.Structure):
 class MatchPrep:
     """Result of match_prepare: numpy copies for inspection + the raw struct, whose pointers name the device-resident set."""
 
-    def __init__(self, raw: MatchPrepStruct):
+    def __init__(self, raw: MatchPrepStruct, copy: bool = True):
         self.raw = raw
         for f in ("n", "n_hyp", "n_control", "n_trials", "n_valid_m", "n_valid_s", "span", "phi_max", "theta_min", "theta_max"):
             setattr(self, f, getattr(raw, f))
+        if not copy:
+            return
 
         def arr(ptr, count, dtype):
             if count <= 0 or not ptr:
@@ -726,14 +728,14 @@ class Matcher:
             pass
 
     def prepare(self, M, mask_m, S, mask_s, pca_search_range=10, size_control_set=360, trials=30, phi_max=math.pi / 4,
-                resolution=0.0, seed=1) -> MatchPrep:
+                resolution=0.0, seed=1, copy=True) -> MatchPrep:
         """match_prepare: the matchers' pre-processing on the device (counter-based random numbers)."""
         M, S = _f64(M), _f64(S)
         mm, ms = np.ascontiguousarray(mask_m, dtype=np.uint8), np.ascontiguousarray(mask_s, dtype=np.uint8)
         raw = MatchPrepStruct()
         check(lib().match_prepare(self.h, len(M), _d(M), mm.ctypes.data_as(_bp), _d(S), ms.ctypes.data_as(_bp), pca_search_range,
                                   size_control_set, trials, phi_max, resolution, seed, C.byref(raw)))
-        return MatchPrep(raw)
+        return MatchPrep(raw, copy)
 
     def score_prepared(self, which: str, prep: MatchPrep, grid: "Grid" = None, t_sensor=None, zrand=0.05, scale_distance=1.0,
                        scale_orientation=1.0, params=None):

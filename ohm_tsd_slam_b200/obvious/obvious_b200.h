@@ -878,13 +878,22 @@ private:
 class RandomMatching
 {
 public:
-  RandomMatching(unsigned int sizeControlSet, int device = 0) : _sizeControlSet(sizeControlSet), _m(NULL), _pcaSearchRange(10)
+  RandomMatching(unsigned int sizeControlSet, int device = 0)
+      : _sizeControlSet(sizeControlSet), _m(NULL), _pcaSearchRange(10), _devPrep(false), _devSeed(1)
   {
     OBVIOUS_B200_CHECK(match_create(device, &_m));
   }
   virtual ~RandomMatching() { match_destroy(_m); }
   void activateTrace() {}
   void deactivateTrace() {}
+  // Not in the reference: the pre-processing of match() (normals, subsampling, control set, trials, hypothesis list) on
+  // the device with a counter-based random generator (match_prepare) instead of the host code with libc rand().  Same
+  // distributions, different draws; every call of match() uses the next seed.
+  void setDevicePreprocessing(bool on, uint64_t seed = 1)
+  {
+    _devPrep = on;
+    _devSeed = seed;
+  }
 
 protected:
   struct Prep
@@ -1163,6 +1172,19 @@ protected:
     return p;
   }
 
+  // match_prepare on M / S; false: nothing to score
+  bool prepareOnDevice(Matrix* Mm, const bool* maskM, Matrix* Sm, const bool* maskS, unsigned int trials, double phiMax,
+                       double resolution, tsd_match_prep_t* P)
+  {
+    const int n = (int)Mm->getRows();
+    if((int)Sm->getRows() != n || n < 3 || !(resolution > 1e-6)) return false;
+    std::vector<uint8_t> mm(n), ms(n);
+    for(int i = 0; i < n; i++) { mm[i] = maskM[i] ? 1 : 0; ms[i] = maskS[i] ? 1 : 0; }
+    OBVIOUS_B200_CHECK(match_prepare(_m, n, Mm->data(), mm.data(), Sm->data(), ms.data(), _pcaSearchRange, _sizeControlSet, trials,
+                                     phiMax, resolution, _devSeed++, P));
+    return P->n_hyp > 0;
+  }
+
   static Matrix toMatrix(const double T[9])
   {
     Matrix M(3, 3);
@@ -1173,6 +1195,8 @@ protected:
   unsigned int _sizeControlSet;
   tsd_matcher_t* _m;
   int _pcaSearchRange;
+  bool _devPrep;
+  uint64_t _devSeed;
 };
 
 class TSD_PDFMatching : public RandomMatching  // ransacMatching/TSD_PDFMatching.h
@@ -1191,11 +1215,19 @@ public:
     (void)NM; (void)transMax;
     Matrix TBest(3, 3);
     TBest.setIdentity();
-    Prep p = prepare(M, maskM, S, maskS, _trials, phiMax, resolution);
-    if(!p.ok || p.hyps.empty()) return TBest;
     double ts[9], T[9];
     TSensor.getData(ts);
     int32_t best = -1;
+    if(_devPrep)
+    {
+      tsd_match_prep_t P;
+      if(!prepareOnDevice(M, maskM, S, maskS, _trials, phiMax, resolution, &P)) return TBest;
+      OBVIOUS_B200_CHECK(match_score_tsd(_m, _grid.handle(), P.n_hyp, P.hyps, P.n, P.model, P.scene, P.phi_m, P.phi_s, P.phi_max,
+                                         P.n_control, P.control, ts, _zrand, NULL, &best, T));
+      return toMatrix(T);
+    }
+    Prep p = prepare(M, maskM, S, maskS, _trials, phiMax, resolution);
+    if(!p.ok || p.hyps.empty()) return TBest;
     OBVIOUS_B200_CHECK(match_score_tsd(_m, _grid.handle(), (int32_t)p.hyps.size(), p.hyps.data(), p.n, p.M.data(), p.S.data(),
                                        p.phiM.data(), p.phiS.data(), p.phiMax, (int32_t)p.idxControl.size(), p.control.data(), ts,
                                        _zrand, NULL, &best, T));
@@ -1222,6 +1254,17 @@ public:
     (void)NM; (void)transMax;
     Matrix TBest(3, 3);
     TBest.setIdentity();
+    if(_devPrep)
+    {
+      tsd_match_prep_t P;
+      double Td[9];
+      int32_t bestd = -1;
+      if(!prepareOnDevice(M, maskM, S, maskS, _trials, phiMax, resolution, &P)) return TBest;
+      OBVIOUS_B200_CHECK(match_score_rnm(_m, P.n_hyp, P.hyps, P.n, P.model, P.scene, P.phi_m, P.phi_s, P.phi_max, P.n_control,
+                                         P.control, P.phi_control, P.n_valid_m, P.model_valid, P.phi_valid, P.theta_min, P.theta_max,
+                                         _scaleDistance, _scaleOrientation, (uint32_t)(P.n_control / 3), NULL, NULL, NULL, &bestd, Td));
+      return toMatrix(Td);
+    }
     Prep p = prepare(M, maskM, S, maskS, _trials, phiMax, resolution);
     if(!p.ok || p.hyps.empty()) return TBest;
     std::vector<double> mv(2 * p.idxMValid.size()), pv(p.idxMValid.size());
@@ -1267,6 +1310,16 @@ public:
     (void)NM; (void)transMax;
     Matrix TBest(3, 3);
     TBest.setIdentity();
+    if(_devPrep)
+    {
+      tsd_match_prep_t P;
+      double Td[9];
+      int32_t bestd = -1;
+      if(!prepareOnDevice(M, maskM, S, maskS, _trials, phiMax, resolution, &P)) return TBest;
+      OBVIOUS_B200_CHECK(match_score_pdf(_m, P.n_hyp, P.hyps, P.n, P.model, P.scene, P.phi_m, P.phi_s, P.phi_max, P.n_control,
+                                         P.control, P.n_valid_m, P.model_angles, P.model_dists, _p, NULL, NULL, &bestd, Td));
+      return toMatrix(Td);
+    }
     Prep p = prepare(M, maskM, S, maskS, _trials, phiMax, resolution);
     if(!p.ok || p.hyps.empty()) return TBest;
     std::vector<double> ang(p.idxMValid.size()), dst(p.idxMValid.size());

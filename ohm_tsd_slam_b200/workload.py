@@ -264,6 +264,31 @@ def hypothesis_benchmark(device: int = 0, n_hyp: int = 100000, reps: int = 3, di
             amax(t)
             dt = float(t[0])
         out[name] = {"ms": dt * 1e3, "hypotheses_per_s": n_hyp / dt}
+    if world == 1:
+        # the whole relocalisation from the raw model / scene points -- pre-processing on the device
+        # (match_prepare: normals, subsampling, control set, trials, hypothesis list) + scoring of the resident set
+        phi_max = math.radians(30.0)
+        leg = {}
+        for name in ("tsd", "rnm", "pdf"):
+            kw = ({"grid": g, "t_sensor": hs.pose, "zrand": 0.25} if name == "tsd" else
+                  {"scale_distance": 1.0 / 0.15 ** 2, "scale_orientation": 0.33} if name == "rnm" else {"params": wl.PDF_PARAMS})
+            for k in range(2):
+                prep = mt.prepare(M, mM, S, mS, 10, 360, 1000, phi_max, cfg.sensor.angular_res, seed=k, copy=False)
+                res = mt.score_prepared(name, prep, **kw)
+            t0 = time.perf_counter()
+            for k in range(reps):
+                prep = mt.prepare(M, mM, S, mS, 10, 360, 1000, phi_max, cfg.sensor.angular_res, seed=10 + k, copy=False)
+            tp = (time.perf_counter() - t0) / reps
+            t0 = time.perf_counter()
+            for k in range(reps):
+                prep = mt.prepare(M, mM, S, mS, 10, 360, 1000, phi_max, cfg.sensor.angular_res, seed=10 + k, copy=False)
+                res = mt.score_prepared(name, prep, **kw)
+            tt = (time.perf_counter() - t0) / reps
+            leg[name] = {"prepare_ms": tp * 1e3, "prepare_plus_score_ms": tt * 1e3, "n_hypotheses": int(prep.n_hyp),
+                         "best": int(res[-2])}
+        leg["what"] = ("match_prepare (1000 trials, 360 control points, counter-based random numbers) + scoring of the resident "
+                       "set, from the raw 1081-point model and scene in host memory to the winning transform")
+        out["device_prepared"] = leg
     if keep_inputs:
         out["_inputs"] = {"workload": wl, "pose": hs.pose.copy(), "map_scans": scans[:3], "cfg": cfg}
     return out

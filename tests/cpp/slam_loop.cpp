@@ -78,6 +78,10 @@ int main(int argc, char** argv)
   icp->setMaxIterations(icpIterations);
   icp->setConvergenceCounter(icpIterations);
   obvious::TSD_PDFMatching* tsdMatcher = (mode == 3) ? new obvious::TSD_PDFMatching(*grid, 100, 0.15, 140, 0.25) : NULL;
+#ifdef OBVIOUS_B200_H
+  // adapter build only: SLAM_LOOP_DEVICE_PREP=1 moves the matcher's pre-processing to the device (match_prepare)
+  if(tsdMatcher && getenv("SLAM_LOOP_DEVICE_PREP")) tsdMatcher->setDevicePreprocessing(true, 42);
+#endif
 
   std::vector<float> ranges(beams);
   obvious::SensorPolar2D* sensor = NULL;

@@ -31,10 +31,12 @@ def build_exe():
     return EXE
 
 
-def run(name, mode, bands=None):
+def run(name, mode, bands=None, device_prep=False):
     env = dict(os.environ)
     if bands:
         env["SLAM_LOOP_BANDS"] = str(bands)
+    if device_prep:
+        env["SLAM_LOOP_DEVICE_PREP"] = "1"
     out = subprocess.run([build_exe(), os.path.join(ROOT, "tests", "golden", f"scans_{name}.bin")] + ARGS[name] + [str(mode)],
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr
@@ -88,6 +90,9 @@ def test_slam_loop_with_tsd_matcher():
     a = run("tiny", 0)[:-1]
     b = run("tiny", 3)[:-1]
     assert a.shape == b.shape and np.max(np.abs(a[:, 1:3] - b[:, 1:3])) < 0.05 and np.max(np.abs(a[:, 3] - b[:, 3])) < 0.02
+    # the same with the matcher's pre-processing on the device (match_prepare, counter-based random numbers)
+    c = run("tiny", 3, device_prep=True)[:-1]
+    assert a.shape == c.shape and np.max(np.abs(a[:, 1:3] - c[:, 1:3])) < 0.05 and np.max(np.abs(a[:, 3] - c[:, 3])) < 0.02
 
 
 THREADS_EXE = os.path.join(ROOT, "tests", "cpp", "threads_b200")
