@@ -380,8 +380,9 @@ int match_score_pdf(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
  * pickControlSet (:52-75), the trial order and the hypothesis list -- for 10^5-hypothesis relocalisation without host work
  * between the scan and the scores.  DELIBERATE departures from the reference, documented in DESIGN.md: random numbers come
  * from a counter-based generator, match_rng(seed, stream, index) (SplitMix64 finaliser), not from the sequential libc rand()
- * -- "keep scene point i" is match_rng(seed, 0, i) % 1000 >= threshold; "K of the valid indices without replacement, in
- * random order" is "the K smallest keys match_rng(seed, stream, index), in key order" (stream 1: control set, 2: trials) --
+ * -- "keep scene point i" is match_rng(seed, 0, i) % 1000 >= threshold; "K of the valid indices without replacement" is
+ * "the K smallest keys match_rng(seed, stream, index)": the trials (stream 2) in key order, i.e. in random order as in the
+ * reference; the control set (stream 1) in scene order -- it is a set to every consumer, and neighbours help the scorers --
  * and pcaAnalysis' centroid is a double-precision running mean (the reference's is long double).
  * Every pointer of the result points into pinned host memory owned by the matcher, valid until the next match_prepare /
  * match_destroy on it; the device keeps a copy: handing these very pointers to match_score_tsd / _rnm / _pdf uploads
