@@ -81,3 +81,38 @@ def test_argument_validation_of_the_wider_surface(tmp_path):
     assert L.tsdg_band_connect(None, 0, None) == -1
     box = (C.c_int32 * 4)()
     assert L.tsdg_scan_box(None, None, box) == -1
+
+
+def test_argument_validation_of_the_round_two_surface():
+    """The entry points added in round 2 refuse NULL handles / buffers and bad sizes before anything touches CUDA."""
+    L = capi.lib()
+    h = C.c_void_p()
+    one = (C.c_int * 1)(0)
+    assert L.tsdg_create_sharded(0.025, 5, 8, 0, one, C.byref(h)) == -1 and not h.value      # no bands
+    assert L.tsdg_create_sharded(0.025, 5, 8, 99, one, C.byref(h)) == -1 and not h.value     # more bands than partition rows
+    assert L.tsdg_create_sharded(0.025, 5, 3, 1, one, C.byref(h)) == -1                      # invalid layout
+    assert L.tsdg_create_sharded(0.025, 5, 8, 1, one, None) == -1
+    assert L.tsdg_sharded_destroy(None) == 0
+    assert L.tsdg_sharded_num_bands(None) == 0
+    assert not L.tsdg_sharded_band(None, 0)
+    assert L.tsdg_sharded_push(None, None) == -1
+    assert L.tsdg_sharded_push_batch(None, None, 2) == -1
+    assert L.tsdg_sharded_sync(None) == -1
+    assert L.tsdg_sharded_set_max_truncation(None, 0.1) == -1
+    assert L.tsdg_sharded_free_footprint(None, 0.0, 0.0, 1.0, 1.0) == -1
+    assert L.tsdg_sharded_raycast_mask(None, None, None, None, None, None, None) == -1
+    assert L.tsdg_sharded_interpolate_bilinear(None, 1, None, None, None) == -1
+    assert L.tsdg_sharded_partition_states(None, None, None) == -1
+    assert L.tsdg_sharded_download_partition(None, 0, None, None) == -1
+    assert L.tsdg_localize(None, None, None, None, None, 0, None, None, None, None, None, None, None) == -1
+    assert L.icp_pairs(None, None, 0, None, 0, None, None, None, None, None) == -1
+    assert L.match_prepare(None, 10, None, None, None, None, 10, 360, 30, 0.5, 0.004, 1, None) == -1
+    assert L.tsds_prepare_scan(None, 0, None, 1.0, 30.0, 0.004, None, None, None, None, None, None, None) == -1
+    assert L.tsdg_raycast_mask_sharded(None, None, None, None, None, None, None) == -1
+    assert L.tsdg_raycast_sharded_launch(None, None, None) == -1
+    assert L.tsdg_raycast_sharded_collect(None, 0, None, None, None, None) == -1
+    assert L.tsdg_band_rcx_export(None, None) == -1
+    # the counter-based generator of match_prepare is a pure host/device function: fixed values, uniform-looking residues
+    assert capi.match_rng(1, 2, 3) == 0x12e80ffcfbbbd251
+    r = [capi.match_rng(7, 0, i) % 1000 for i in range(4000)]
+    assert 450 < sum(r) / len(r) < 550 and len(set(r)) > 900
