@@ -121,6 +121,9 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_tsd(HypCommon hc, Gr
 }
 
 // ---------------------------------------------------------------- K10: RandomNormalMatching.cpp:265-342
+#define RNM_GROUP 16   // valid model points per bounding box
+#define RNM_SUPER 8    // boxes per super-box
+
 struct RnmParams
 {
   const double* phi_control;
@@ -161,14 +164,20 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
   // issue slots on this part, and the 32 box tests per control point were as many of them as the scans they save.
   // (Screening the POINTS of a group the same way was measured and lost: the lanes of a warp hold different control
   // points, some lane nearly always needs the exact distance, and the warp then pays for both.)
-  const int nGroups = (rp.n_valid + 31) >> 5;
+  // Two levels: groups of RNM_GROUP points, and super-groups of RNM_SUPER groups whose box is tested first (per control
+  // point: ~9 + 2 x 8 box tests and 2-3 scans of 16 points instead of 34 box tests and 2-3 scans of 32: 6.2 -> 5.8 ms).
+  // (Measured and dropped, profiles/r02_notes.md: opening a box for the whole warp if any lane wants it, with a vote that
+  //  skips the exact distance of a point no lane can use: 8.9 ms -- the union of 32 lanes' boxes is most of the model.)
+  const int nGroups = (rp.n_valid + RNM_GROUP - 1) / RNM_GROUP;
+  const int nSuper = (nGroups + RNM_SUPER - 1) / RNM_SUPER;
   float4* s_boxf = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(s_mphi + rp.n_valid) + 15) & ~(uintptr_t)15);  // per group: x0 x1 y0 y1, rounded outward
-  float* s_mabs = reinterpret_cast<float*>(s_boxf + nGroups);       // [0]: largest |coordinate| of the model
+  float4* s_sboxf = s_boxf + nGroups;                               // per super-group
+  float* s_mabs = reinterpret_cast<float*>(s_sboxf + nSuper);       // [0]: largest |coordinate| of the model
   __syncthreads();
   for(int g = threadIdx.x; g < nGroups; g += blockDim.x)
   {
-    double x0 = s_mx[32 * g], x1 = x0, y0 = s_my[32 * g], y1 = y0;
-    for(int k = 32 * g + 1; k < min(32 * g + 32, rp.n_valid); k++)
+    double x0 = s_mx[RNM_GROUP * g], x1 = x0, y0 = s_my[RNM_GROUP * g], y1 = y0;
+    for(int k = RNM_GROUP * g + 1; k < min(RNM_GROUP * g + RNM_GROUP, rp.n_valid); k++)
     {
       x0 = fmin(x0, s_mx[k]); x1 = fmax(x1, s_mx[k]);
       y0 = fmin(y0, s_my[k]); y1 = fmax(y1, s_my[k]);
@@ -176,11 +185,22 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
     s_boxf[g] = make_float4(__double2float_rd(x0), __double2float_ru(x1), __double2float_rd(y0), __double2float_ru(y1));
   }
   __syncthreads();
+  for(int sg = threadIdx.x; sg < nSuper; sg += blockDim.x)
+  {
+    float4 b = s_boxf[RNM_SUPER * sg];
+    for(int g = RNM_SUPER * sg + 1; g < min(RNM_SUPER * sg + RNM_SUPER, nGroups); g++)
+    {
+      const float4 c = s_boxf[g];
+      b.x = fminf(b.x, c.x); b.y = fmaxf(b.y, c.y); b.z = fminf(b.z, c.z); b.w = fmaxf(b.w, c.w);
+    }
+    s_sboxf[sg] = b;
+  }
+  __syncthreads();
   if(threadIdx.x == 0)
   {
     float a = 0.f;
-    for(int g = 0; g < nGroups; g++)
-      a = fmaxf(a, fmaxf(fmaxf(fabsf(s_boxf[g].x), fabsf(s_boxf[g].y)), fmaxf(fabsf(s_boxf[g].z), fabsf(s_boxf[g].w))));
+    for(int g = 0; g < nSuper; g++)
+      a = fmaxf(a, fmaxf(fmaxf(fabsf(s_sboxf[g].x), fabsf(s_sboxf[g].y)), fmaxf(fabsf(s_sboxf[g].z), fabsf(s_sboxf[g].w))));
     s_mabs[0] = a;
   }
   __syncthreads();
@@ -214,8 +234,8 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
       const float e = 1.3e-7f * (fmaxf(fabsf(xf), fabsf(yf)) + mabs) + 1e-30f;
       auto scan_group = [&](int g)
       {
-        const int k1 = min(32 * g + 32, rp.n_valid);
-        for(int k = 32 * g; k < k1; k++)
+        const int k1 = min(RNM_GROUP * g + RNM_GROUP, rp.n_valid);
+        for(int k = RNM_GROUP * g; k < k1; k++)
         {
           const double d0 = x - s_mx[k];
           const double d1 = y - s_my[k];
@@ -226,16 +246,21 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
         }
       };
       // seed with the group the previous control point of this lane ended in (usually the right one already)
-      const int seed = (prevBest >= 0) ? (prevBest >> 5) : -1;
+      const int seed = (prevBest >= 0) ? (prevBest / RNM_GROUP) : -1;
       if(seed >= 0) scan_group(seed);
-      for(int g = 0; g < nGroups; g++)
+      // lower bound of the squared distance to anything in a box
+      auto box_lb = [&](const float4 b)
       {
-        if(g == seed) continue;
-        const float4 b = s_boxf[g];
         const float ex = fmaxf(fmaxf(b.x - xf, xf - b.y) * (1.f - 2e-7f) - e, 0.f);
         const float ey = fmaxf(fmaxf(b.z - yf, yf - b.w) * (1.f - 2e-7f) - e, 0.f);
-        // lower bound of the squared distance to anything in the box
-        if((ex * ex + ey * ey) * (1.f - 1e-6f) <= bdf) scan_group(g);
+        return (ex * ex + ey * ey) * (1.f - 1e-6f);
+      };
+      for(int sg = 0; sg < nSuper; sg++)
+      {
+        if(!(box_lb(s_sboxf[sg]) <= bdf)) continue;
+        const int g1 = min(RNM_SUPER * sg + RNM_SUPER, nGroups);
+        for(int g = RNM_SUPER * sg; g < g1; g++)
+          if(g != seed && box_lb(s_boxf[g]) <= bdf) scan_group(g);
       }
       prevBest = bi;
       if(bi < 0) continue;
@@ -992,7 +1017,8 @@ int match_score_rnm(tsd_matcher_t* m, int32_t n_hyp, const tsd_hypothesis_t* hyp
   rp.max_cnt_match = a.put<int>(nullptr, n_hyp, &h_max);
   rp.err_sum = a.put<double>(nullptr, n_hyp, &h_err);
   TSD_CUDA(cudaMemcpyAsync(m->d_buf, m->h_buf, inEnd, cudaMemcpyHostToDevice, m->stream));
-  const size_t smem = sizeof(double) * (4 * (size_t)n_control + 3 * (size_t)n_valid) + 16 * (((size_t)n_valid + 31) / 32) + 8 * (size_t)n_valid + 32;
+  const size_t nGroupsH = ((size_t)n_valid + RNM_GROUP - 1) / RNM_GROUP;
+  const size_t smem = sizeof(double) * (4 * (size_t)n_control + 3 * (size_t)n_valid) + 16 * (nGroupsH + (nGroupsH + RNM_SUPER - 1) / RNM_SUPER) + 64;
   if(smem > 200 * 1024) { set_error("control set / model too large for shared memory"); return TSD_E_INVALID; }
   if(smem > 48 * 1024) TSD_CUDA(cudaFuncSetAttribute(k_score_rnm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sm = 148;
