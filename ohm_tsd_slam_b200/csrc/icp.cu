@@ -563,7 +563,7 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
           const double px = s_sx[q], py = s_sy[q];
           const int pqx = cell_of(px, bx0, invh), pqy = cell_of(py, by0, invh);
           double bestD = S.pbd[ql];
-          int best = S.prev[ql];
+          int best = lane == 0 ? S.prev[ql] : -1;  // (only lane 0 merges and writes the result)
           // a cell in ring k is farther than (k - 1) h: the bound found so far (last iteration's neighbour) limits the rings
           int Rq = R;
           if(bestD < INF) Rq = min(R, (int)(sqrt(bestD) * invh * (1.0 + 1e-9)) + 1);
@@ -826,6 +826,7 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
       P.tr_mse[iter] = rms;
       for(int i = 0; i < 16; i++) P.tr_T[16 * iter + i] = S.T[i];
     }
+    __syncthreads();  // the scene points and lower bounds just written are read by other threads in the next search
     ICP_STAMP(4)
     eRetval = retval;
     // Icp.cpp:496-507
