@@ -1532,9 +1532,12 @@ static int ensure_scan_capacity(tsd_grid* g, int n)
   TSD_CUDA(cudaMalloc(&g->d_rc, g->rc_bytes));
   TSD_CUDA(cudaMalloc(&g->d_dirs, sizeof(double2) * (cap + 1)));
   TSD_CUDA(cudaMalloc(&g->d_gate, sizeof(float2) * (size_t)cap * PUSH_MAX_SCANS));
+  // (the padding behind a scan's last beam is copied into shared memory with the scan, 16 bytes at a time: defined bytes)
+  TSD_CUDA(cudaMemsetAsync(g->d_in, 0, g->in_bytes, g->stream));
   for(int i = 0; i < 2; i++)
   {
     TSD_CUDA(cudaMallocHost(&g->h_in2[i], g->in_bytes));
+    memset(g->h_in2[i], 0, g->in_bytes);
     if(!g->ev_in[i]) TSD_CUDA(cudaEventCreateWithFlags(&g->ev_in[i], cudaEventDisableTiming));
   }
   g->h_in = g->h_in2[0];
