@@ -45,7 +45,8 @@ struct RayParams
 #define RC_PREFETCH_PASSES 6
 #endif
 #ifndef RC_DEPTH
-#define RC_DEPTH 3   // passes of a ray whose samples are in flight at once (C3, ms per call: 1 -> 0.41, 2 -> 0.30, 3 and 4 -> 0.29)
+#define RC_DEPTH 2   // PAIRS of passes of a ray whose samples are in flight at once (single passes, C3, ms per call: 1 -> 0.41,
+                     // 2 -> 0.30, 3 and 4 -> 0.29)
 #endif
 
 // L2 prefetch of the two cell rows a bilinear sample at (cx, cy) reads (clamped like sample_issue: always a valid address)
@@ -187,38 +188,26 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
         *oy = ay;
       }
     };
-    // One pass: evaluate the samples in `cur` (taken at this lane's position (cmx, cmy)), then refill `cur` with the
-    // samples of the pass after next.  Returns true when the ray is finished.  The loop below alternates between two
-    // sets of registers, so that no loaded value has to be moved (a move waits for its load) before it is needed.
-    auto pass = [&](SampleLoads& cur, double& cmx, double& cmy) -> bool
+    // validity of this lane's iteration in the pass that starts at step b: i_k <= idxMax
+    auto valid_of = [&](unsigned long long b) -> bool
     {
-      // validity of this lane's iteration: i_k <= idxMax
-      bool valid;
-      const bool nearEnd = !(idxMin + (double)(base + 31u) + 2.0 < idxMax);
-      if(!nearEnd) valid = true;
-      else
-      {
-        double mi = 0.0;
-        // replay the reference's counter up to this pass (uniform), keep this lane's value
-        while(kExact < base) { iExact += 1.0; kExact++; }
-        double ii = iExact;
+      const bool nearEnd = !(idxMin + (double)(b + 31u) + 2.0 < idxMax);
+      if(!nearEnd) return true;
+      double mi = 0.0;
+      // replay the reference's counter up to this pass (uniform), keep this lane's value
+      while(kExact < b) { iExact += 1.0; kExact++; }
+      double ii = iExact;
 #pragma unroll 8
-        for(int k = 0; k < 32; k++)
-        {
-          if(k == lane) mi = ii;
-          ii += 1.0;
-        }
-        valid = mi <= idxMax;
+      for(int k = 0; k < 32; k++)
+      {
+        if(k == lane) mi = ii;
+        ii += 1.0;
       }
-      // positions of the pass after next while the loads of this pass and the next are in flight
-      double mx2, my2;
-      advance(&mx2, &my2);
-      double v = __longlong_as_double(0x7ff8000000000000LL);
-      double t = 0.0;
-      const int rv = sample_finish(cur, &t);
-      if(valid && rv == TSD_INTERPOLATE_SUCCESS) v = t;
-      double prev = __shfl_up_sync(0xffffffffu, v, 1);
-      if(lane == 0) prev = carry;
+      return mi <= idxMax;
+    };
+    // the first event of a pass, if any; true when the ray is finished
+    auto events = [&](const SampleLoads& cur, double cmx, double cmy, bool valid, double v, double prev) -> bool
+    {
       // a step belongs to the band that owns its sample's partition (everything, for an unsharded grid)
       const bool mine = valid && (cur.py >= g.row_begin) && (cur.py < g.row_end);
       const bool hit = mine && (prev > 0) && (v < 0);
@@ -260,21 +249,49 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
       }
       nFine += 32;
       base += 32;
-      carry = __shfl_sync(0xffffffffu, v, 31);
-      cmx = mx2;
-      cmy = my2;
-      cur = sample_issue(g, mx2, my2);
+      return false;
+    };
+    // TWO consecutive passes at a time (64 steps): their samples are finished side by side -- two independent dependency
+    // chains per lane, where one pass alone leaves the warp waiting on its own previous instruction most of the time --,
+    // then their events are looked at in order, then both sets of registers are refilled with the samples of the pair
+    // RC_DEPTH pairs ahead.  Returns true when the ray is finished.  The sets are only ever refilled in place, never moved
+    // (a move of a loaded value waits for its load).
+    auto pass2 = [&](SampleLoads& A, double& ax, double& ay, SampleLoads& B, double& bx, double& by) -> bool
+    {
+      const bool validA = valid_of(base), validB = valid_of(base + 32u);
+      // positions of the pair RC_DEPTH pairs ahead while the loads of the pairs in between are in flight
+      double nax, nay, nbx, nby;
+      advance(&nax, &nay);
+      advance(&nbx, &nby);
+      const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+      double tA = 0.0, tB = 0.0;
+      const int rvA = sample_finish(A, &tA);
+      const int rvB = sample_finish(B, &tB);
+      const double vA = (validA && rvA == TSD_INTERPOLATE_SUCCESS) ? tA : nanv;
+      const double vB = (validB && rvB == TSD_INTERPOLATE_SUCCESS) ? tB : nanv;
+      double prevA = __shfl_up_sync(0xffffffffu, vA, 1);
+      double prevB = __shfl_up_sync(0xffffffffu, vB, 1);
+      const double lastA = __shfl_sync(0xffffffffu, vA, 31);
+      if(lane == 0) { prevA = carry; prevB = lastA; }
+      if(events(A, ax, ay, validA, vA, prevA)) return true;
+      if(events(B, bx, by, validB, vB, prevB)) return true;
+      carry = __shfl_sync(0xffffffffu, vB, 31);
+      ax = nax; ay = nay;
+      A = sample_issue(g, nax, nay);
+      bx = nbx; by = nby;
+      B = sample_issue(g, nbx, nby);
       // ... and the cells the ray reaches RC_PREFETCH_PASSES passes later are called into L2 (approximate positions are
       // good enough for that): a ray walks through memory it has never touched -- a new partition every 32 steps, a new
       // 2 MB page every partition row.
-      sample_prefetch(g, mx2 + (32.0 * RC_PREFETCH_PASSES) * ray0, my2 + (32.0 * RC_PREFETCH_PASSES) * ray1);
+      sample_prefetch(g, nax + (32.0 * RC_PREFETCH_PASSES) * ray0, nay + (32.0 * RC_PREFETCH_PASSES) * ray1);
+      sample_prefetch(g, nbx + (32.0 * RC_PREFETCH_PASSES) * ray0, nby + (32.0 * RC_PREFETCH_PASSES) * ray1);
       return false;
     };
-    // RC_DEPTH passes in flight, each with its own registers
-    double pmx[RC_DEPTH], pmy[RC_DEPTH];
-    SampleLoads psl[RC_DEPTH];
+    // RC_DEPTH pairs of passes in flight, each with its own registers
+    double pmx[2 * RC_DEPTH], pmy[2 * RC_DEPTH];
+    SampleLoads psl[2 * RC_DEPTH];
 #pragma unroll
-    for(int d = 0; d < RC_DEPTH; d++)
+    for(int d = 0; d < 2 * RC_DEPTH; d++)
     {
       advance(&pmx[d], &pmy[d]);
       psl[d] = sample_issue(g, pmx[d], pmy[d]);
@@ -284,7 +301,7 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
     {
 #pragma unroll
       for(int d = 0; d < RC_DEPTH; d++)
-        if(!done) done = pass(psl[d], pmx[d], pmy[d]);
+        if(!done) done = pass2(psl[2 * d], pmx[2 * d], pmy[2 * d], psl[2 * d + 1], pmx[2 * d + 1], pmy[2 * d + 1]);
     }
   }
 
