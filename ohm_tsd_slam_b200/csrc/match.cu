@@ -621,6 +621,7 @@ struct PrepParams
   double* phiValid;
   double* modelAngles;
   double* modelDists;
+  unsigned long long* keys;  // scratch, n
   int* header;       // [0] nValidM [1] nValidS [2] nControl [3] nTrials [4] nHyp
   double* headerD;   // [0] thetaMin [1] thetaMax
 };
@@ -652,16 +653,19 @@ __device__ int prep_compact(const uint8_t* mask, int n, int r, int* out, unsigne
 }
 
 // the K entries of idx[0..nv) with the smallest (rng(seed, stream, idx), idx): in that order, or (ascending) in index order
-__device__ void prep_pick(const int* idx, int nv, int K, uint64_t seed, uint32_t stream, int* out, bool ascending, int* s_tmp)
+__device__ void prep_pick(const int* idx, int nv, int K, uint64_t seed, uint32_t stream, int* out, bool ascending, int* s_tmp,
+                          unsigned long long* keys)
 {
+  for(int a = threadIdx.x; a < nv; a += blockDim.x) keys[a] = tsd_rng(seed, stream, (uint32_t)idx[a]);
+  __syncthreads();
   // rank of every entry among the keys; picked <=> rank < K
   for(int a = threadIdx.x; a < nv; a += blockDim.x)
   {
-    const uint64_t ka = tsd_rng(seed, stream, (uint32_t)idx[a]);
+    const uint64_t ka = keys[a];
     int rank = 0;
     for(int b = 0; b < nv; b++)
     {
-      const uint64_t kb = tsd_rng(seed, stream, (uint32_t)idx[b]);
+      const uint64_t kb = keys[b];
       rank += (kb < ka || (kb == ka && b < a)) ? 1 : 0;
     }
     if(!ascending) { if(rank < K) out[rank] = idx[a]; }
@@ -723,8 +727,9 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp)
   // lanes that hold neighbouring control points want the same parts of the model (k_score_rnm: 4.9 -> 2.2 ms on 38 k
   // hypotheses against the random order pickControlSet leaves behind).  The trials keep their random order: it is the
   // order of the hypothesis list, and the first best hypothesis wins.
-  prep_pick(pp.idxS, nvs, C, pp.seed, 1u, pp.idxControl, true, pp.prefS);
-  prep_pick(pp.idxM, nvm, T, pp.seed, 2u, pp.idxTrials, false, nullptr);
+  prep_pick(pp.idxS, nvs, C, pp.seed, 1u, pp.idxControl, true, pp.prefS, pp.keys);
+  __syncthreads();
+  prep_pick(pp.idxM, nvm, T, pp.seed, 2u, pp.idxTrials, false, nullptr, pp.keys);
   __syncthreads();
   // valid scene points before index i
   if(tid == 0)
@@ -1152,7 +1157,7 @@ int match_prepare(tsd_matcher_t* m, int32_t n, const double* model, const uint8_
   const size_t oIdxC = take(4 * (cmax + 1)), oIdxT = take(4 * (tmax + 1)), oPref = take(4 * ((size_t)n + 1)), oHypOff = take(4 * (tmax + 2));
   const size_t oCtrl = take(8 * 3 * (cmax + 1)), oPhiC = take(8 * (cmax + 1));
   const size_t oMV = take(16 * (size_t)n), oPV = take(8 * (size_t)n), oAng = take(8 * (size_t)n), oDst = take(8 * (size_t)n);
-  const size_t oHdr = take(32), oHdrD = take(16);
+  const size_t oHdr = take(32), oHdrD = take(16), oKeys = take(8 * (size_t)n);
   const size_t fixedEnd = off;
   const size_t oHyps = take(sizeof(tsd_hypothesis_t) * capHyp);
   if(off > m->prep_cap)
@@ -1183,7 +1188,7 @@ int match_prepare(tsd_matcher_t* m, int32_t n, const double* model, const uint8_
   pp.prefS = (int*)(D + oPref); pp.hypOff = (unsigned*)(D + oHypOff);
   pp.control = (double*)(D + oCtrl); pp.phiControl = (double*)(D + oPhiC);
   pp.modelValid = (double*)(D + oMV); pp.phiValid = (double*)(D + oPV); pp.modelAngles = (double*)(D + oAng); pp.modelDists = (double*)(D + oDst);
-  pp.header = (int*)(D + oHdr); pp.headerD = (double*)(D + oHdrD);
+  pp.header = (int*)(D + oHdr); pp.headerD = (double*)(D + oHdrD); pp.keys = (unsigned long long*)(D + oKeys);
   k_prepare<<<1, 1024, 0, m->stream>>>(pp);
   TSD_LAUNCHED();
   k_prepare_emit<<<(unsigned)std::max<size_t>(tmax, 1), 256, 0, m->stream>>>(pp, (tsd_hypothesis_t*)(D + oHyps), (unsigned)capHyp);
