@@ -654,7 +654,7 @@ __device__ int prep_compact(const uint8_t* mask, int n, int r, int* out, unsigne
 
 // the K entries of idx[0..nv) with the smallest (rng(seed, stream, idx), idx): in that order, or (ascending) in index order
 __device__ void prep_pick(const int* idx, int nv, int K, uint64_t seed, uint32_t stream, int* out, bool ascending, int* s_tmp,
-                          unsigned long long* keys)
+                          unsigned long long* keys, unsigned* s_scan)
 {
   for(int a = threadIdx.x; a < nv; a += blockDim.x) keys[a] = tsd_rng(seed, stream, (uint32_t)idx[a]);
   __syncthreads();
@@ -672,16 +672,28 @@ __device__ void prep_pick(const int* idx, int nv, int K, uint64_t seed, uint32_t
     else s_tmp[a] = rank < K ? 1 : 0;
   }
   if(!ascending) return;
-  // idx is ascending: the place of a picked entry is the number of picked entries before it
+  // idx is ascending: the place of a picked entry is the number of picked entries before it (ordered compaction)
   __syncthreads();
-  for(int a = threadIdx.x; a < nv; a += blockDim.x)
-    if(s_tmp[a])
+  const int tid = threadIdx.x, lane = tid & 31, nw = blockDim.x >> 5;
+  int base = 0;
+  for(int a0 = 0; a0 < nv; a0 += blockDim.x)
+  {
+    const int a = a0 + tid;
+    const bool v = a < nv && s_tmp[a] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    if(lane == 0) s_scan[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int off = base, total = 0;
+    for(int w = 0; w < nw; w++)
     {
-      int before = 0;
-      for(int b = 0; b < a; b++) before += s_tmp[b];
-      out[before] = idx[a];
+      const int c = (int)s_scan[w];
+      if(w < (tid >> 5)) off += c;
+      total += c;
     }
-  __syncthreads();
+    if(v) out[off + __popc(bal & ((1u << lane) - 1u))] = idx[a];
+    base += total;
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp)
@@ -727,9 +739,9 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp)
   // lanes that hold neighbouring control points want the same parts of the model (k_score_rnm: 4.9 -> 2.2 ms on 38 k
   // hypotheses against the random order pickControlSet leaves behind).  The trials keep their random order: it is the
   // order of the hypothesis list, and the first best hypothesis wins.
-  prep_pick(pp.idxS, nvs, C, pp.seed, 1u, pp.idxControl, true, pp.prefS, pp.keys);
+  prep_pick(pp.idxS, nvs, C, pp.seed, 1u, pp.idxControl, true, pp.prefS, pp.keys, s_scan);
   __syncthreads();
-  prep_pick(pp.idxM, nvm, T, pp.seed, 2u, pp.idxTrials, false, nullptr, pp.keys);
+  prep_pick(pp.idxM, nvm, T, pp.seed, 2u, pp.idxTrials, false, nullptr, pp.keys, s_scan);
   __syncthreads();
   // valid scene points before index i
   if(tid == 0)
@@ -757,18 +769,48 @@ __global__ void __launch_bounds__(1024) k_prepare(PrepParams pp)
     pp.modelAngles[k] = atan2(y, x);
     pp.modelDists[k] = sqrt(x * x + y * y);
   }
-  // ----- hypotheses per trial: the valid scene indices in [max(idx - span, r), min(idx + span, n - r))
+  // ----- hypotheses per trial: the valid scene indices in [max(idx - span, r), min(idx + span, n - r)); their offsets in
+  // the list are an exclusive prefix sum over the trials (block scan, 1024 trials at a time)
+  {
+    const int lane = tid & 31, nw = blockDim.x >> 5;
+    unsigned base = 0;
+    for(int t0 = 0; t0 < T; t0 += blockDim.x)
+    {
+      const int t = t0 + tid;
+      unsigned c = 0;
+      if(t < T)
+      {
+        const int idx = pp.idxTrials[t];
+        const int iMin = max(idx - pp.span, r), iMax = min(idx + pp.span, n - r);
+        if(iMax > iMin) c = (unsigned)(pp.prefS[iMax] - pp.prefS[iMin]);
+      }
+      unsigned incl = c;
+#pragma unroll
+      for(int o = 1; o < 32; o <<= 1)
+      {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if(lane >= o) incl += v;
+      }
+      if(lane == 31) s_scan[tid >> 5] = incl;
+      __syncthreads();
+      unsigned off = base, total = 0;
+      for(int w = 0; w < nw; w++)
+      {
+        const unsigned v = s_scan[w];
+        if(w < (tid >> 5)) off += v;
+        total += v;
+      }
+      if(t < T) pp.hypOff[t] = off + incl - c;
+      base += total;
+      __syncthreads();
+    }
+    if(tid == 0) pp.hypOff[T] = base;
+    if(tid == 0) s_scan[39] = base;
+    __syncthreads();
+  }
   if(tid == 0)
   {
-    unsigned acc = 0;
-    for(int t = 0; t < T; t++)
-    {
-      const int idx = pp.idxTrials[t];
-      const int iMin = max(idx - pp.span, r), iMax = min(idx + pp.span, n - r);
-      pp.hypOff[t] = acc;
-      if(iMax > iMin) acc += (unsigned)(pp.prefS[iMax] - pp.prefS[iMin]);
-    }
-    pp.hypOff[T] = acc;
+    const unsigned acc = s_scan[39];
     pp.header[0] = nvm; pp.header[1] = nvs; pp.header[2] = C; pp.header[3] = T; pp.header[4] = (int)acc;
     if(nvm > 0)
     {
