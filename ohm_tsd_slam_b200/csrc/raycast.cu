@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "closed_form.cuh"
 
 using namespace tsd;
 
@@ -157,15 +158,8 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
     // passes per ray) the pass falls back to the serial chain.
     auto advance = [&](double* ox, double* oy)
     {
-      const double d0 = (pos0 + ray0) - pos0, d1 = (pos1 + ray1) - pos1;
-      const double e0 = pos0 + 32.0 * d0, e1 = pos1 + 32.0 * d1;
-      const unsigned h0 = (unsigned)__double2hiint(pos0) >> 20, h1 = (unsigned)__double2hiint(pos1) >> 20;
-      const unsigned x0 = h0 & 0x7ffu, x1 = h1 & 0x7ffu;
-      // half an ulp of the binade (exponent - 53); 0 if that would be subnormal: then the strict test below fails
-      const double hu0 = __hiloint2double(x0 > 53u ? (int)((x0 - 53u) << 20) : 0, 0);
-      const double hu1 = __hiloint2double(x1 > 53u ? (int)((x1 - 53u) << 20) : 0, 0);
-      const bool closed = (h0 == ((unsigned)__double2hiint(e0) >> 20)) && (h1 == ((unsigned)__double2hiint(e1) >> 20)) &&
-                          (fabs(ray0 - d0) < hu0) && (fabs(ray1 - d1) < hu1);
+      double d0, d1, e0, e1;
+      const bool closed = tsd_closed_form_pass(pos0, ray0, &d0, &e0) & tsd_closed_form_pass(pos1, ray1, &d1, &e1);
       if(closed)
       {
         const double k = (double)(lane + 1);

@@ -81,3 +81,19 @@ def test_fast_path_front_end_is_exact_where_it_is_certain(tmp_path):
     # the front end must decide almost everything, or it is not a fast path
     certain = float(out.stdout.split("certain ")[1].split("%")[0])
     assert certain > 99.0, out.stdout
+
+
+def test_raycast_closed_form_positions_equal_the_serial_sums(tmp_path):
+    """k_raycast replaces the 32 serial additions `position += ray` of a pass by p + k d where that is exact
+    (ohm_tsd_slam_b200/csrc/closed_form.cuh, host/device code).  tests/cpp/closedform_check.cpp runs that very function on
+    the CPU against the serial sums over 12 M cases (all binades of the map, binade boundaries, exact multiples and exact
+    ties of the position's ulp, tiny and zero steps): whenever it says "closed", all 32 partial sums agree bit for bit."""
+    import subprocess
+    exe = str(tmp_path / "closedform_check")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Werror",
+                    os.path.join(ROOT, "tests", "cpp", "closedform_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 mismatches" in out.stdout and "400000 exact ties refused" in out.stdout
+    closed = float(out.stdout.split("(")[1].split("%")[0])
+    assert closed > 50.0, out.stdout  # (an adversarial mix: a third of the cases sit on binade boundaries, ties or zero)
