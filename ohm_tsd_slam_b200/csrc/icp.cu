@@ -418,8 +418,10 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
     // (What an iteration costs is the instructions its 32 warps issue, so warps without queries skip the search altogether.)
     for(int l0 = 0; l0 < nQ; l0 += ICP_THREADS)
     {
-      if(l0 + (tid & ~31) >= nQ) continue;          // (warp-uniform)
-      const int ql = l0 + tid;                      // index among this CTA's queries
+      // (queries are dealt to the warps like cards: a warp's time is its busiest lane's, and eight warps with eleven
+      //  queries each finish sooner than three warps with thirty-two)
+      if(l0 + (tid >> 5) >= nQ) continue;           // (warp-uniform: the warp's first query)
+      const int ql = l0 + (tid & 31) * (ICP_THREADS / 32) + (tid >> 5);  // index among this CTA's queries
       const int q = ql * ICP_CLUSTER + (int)rank;   // scene point
       const bool exists = ql < nQ && q < nS;
       const double x = exists ? s_sx[q] : 0.0, y = exists ? s_sy[q] : 0.0;
