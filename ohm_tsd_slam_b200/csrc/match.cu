@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "nn_bounds.cuh"
 
 using namespace tsd;
 
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
       // single-precision images of the query and a bound e on |image difference - true difference| per axis:
       // two conversions (half an ulp each of a magnitude below |x| + |m|) and one subtraction (half an ulp of the result)
       const float xf = (float)x, yf = (float)y;
-      const float e = 1.3e-7f * (fmaxf(fabsf(xf), fabsf(yf)) + mabs) + 1e-30f;
+      const float e = tsd_nb_err(xf, yf, mabs);
       auto scan_group = [&](int g)
       {
         const int k1 = min(RNM_GROUP * g + RNM_GROUP, rp.n_valid);
@@ -249,12 +250,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_score_rnm(HypCommon hc, Rn
       const int seed = (prevBest >= 0) ? (prevBest / RNM_GROUP) : -1;
       if(seed >= 0) scan_group(seed);
       // lower bound of the squared distance to anything in a box
-      auto box_lb = [&](const float4 b)
-      {
-        const float ex = fmaxf(fmaxf(b.x - xf, xf - b.y) * (1.f - 2e-7f) - e, 0.f);
-        const float ey = fmaxf(fmaxf(b.z - yf, yf - b.w) * (1.f - 2e-7f) - e, 0.f);
-        return (ex * ex + ey * ey) * (1.f - 1e-6f);
-      };
+      auto box_lb = [&](const float4 b) { return tsd_nb_box_lb(b, xf, yf, e); };
       for(int sg = 0; sg < nSuper; sg++)
       {
         if(!(box_lb(s_sboxf[sg]) <= bdf)) continue;

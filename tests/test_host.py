@@ -97,3 +97,19 @@ def test_raycast_closed_form_positions_equal_the_serial_sums(tmp_path):
     assert " 0 mismatches" in out.stdout and "400000 exact ties refused" in out.stdout
     closed = float(out.stdout.split("(")[1].split("%")[0])
     assert closed > 50.0, out.stdout  # (an adversarial mix: a third of the cases sit on binade boundaries, ties or zero)
+
+
+def test_rnm_box_bound_never_exceeds_a_true_distance(tmp_path):
+    """k_score_rnm skips a group of model points when a single-precision lower bound of the squared distance to the
+    group's bounding box exceeds the best distance so far (ohm_tsd_slam_b200/csrc/nn_bounds.cuh, host/device code).
+    tests/cpp/nnbound_check.cpp runs those very functions on the CPU: over 2.4 M queries (anywhere, just outside an edge,
+    inside, off a corner; coordinates up to the largest map) the bound never exceeds the double-precision squared
+    distance to any point of the box, rounded up to single precision -- the quantity the kernel compares it with."""
+    import subprocess
+    exe = str(tmp_path / "nnbound_check")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Werror",
+                    os.path.join(ROOT, "tests", "cpp", "nnbound_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 violations" in out.stdout
+    assert float(out.stdout.split("positive for ")[1].split("%")[0]) > 40.0  # (the bound is not trivially zero)
