@@ -29,6 +29,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "icp_cells.cuh"
 
 using namespace tsd;
 
@@ -96,12 +97,8 @@ struct tsd_icp
   int trace_cap_it;
 };
 
-// cell coordinate of a point; clamped so that the hash input stays small and rings never overflow
-__device__ __forceinline__ int cell_of(double v, double v0, double invh)
-{
-  const double t = floor((v - v0) * invh);
-  return (int)fmin(fmax(t, -1.0e6), 1.0e6);
-}
+// cell coordinate of a point (icp_cells.cuh: host/device, checked on the CPU by tests/cpp/icpcell_check.cpp)
+__device__ __forceinline__ int cell_of(double v, double v0, double invh) { return tsd_icp_cell_of(v, v0, invh); }
 
 __device__ __forceinline__ unsigned slot_of(int cx, int cy)
 {
@@ -473,11 +470,7 @@ __global__ void __cluster_dims__(ICP_CLUSTER, 1, 1) __launch_bounds__(ICP_THREAD
           best = pm;
         }
         // shaved so that rounding never skips a cell wrongly
-        const double fx = (x - bx0) * invh - (double)qx, fy = (y - by0) * invh - (double)qy;
-        const double shave = 1e-9 * h;
-        const double gl = fmax(fx * h - shave, 0.0), gr = fmax((1.0 - fx) * h - shave, 0.0);
-        const double gd = fmax(fy * h - shave, 0.0), gu = fmax((1.0 - fy) * h - shave, 0.0);
-        l2 = gl * gl; r2 = gr * gr; d2 = gd * gd; u2 = gu * gu;
+        tsd_icp_edge_gaps2(x, y, bx0, by0, h, invh, qx, qy, &l2, &r2, &d2, &u2);
         open = 1u << 4;
       }
       bool first = true;

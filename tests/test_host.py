@@ -113,3 +113,17 @@ def test_rnm_box_bound_never_exceeds_a_true_distance(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     assert " 0 violations" in out.stdout
     assert float(out.stdout.split("positive for ")[1].split("%")[0]) > 40.0  # (the bound is not trivially zero)
+
+
+def test_icp_cell_gaps_never_exceed_a_true_distance(tmp_path):
+    """k_icp opens a neighbouring hash cell only if the query's gap to it does not exceed the best squared distance so far
+    (ohm_tsd_slam_b200/csrc/icp_cells.cuh, host/device code).  tests/cpp/icpcell_check.cpp runs those very functions on
+    the CPU: over 15 M query / model point pairs (cell boundaries included, origins kilometres away, five cell sizes) a
+    point lying in a neighbouring cell is never nearer than the gap says."""
+    import subprocess
+    exe = str(tmp_path / "icpcell_check")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Werror",
+                    os.path.join(ROOT, "tests", "cpp", "icpcell_check.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 violations" in out.stdout
