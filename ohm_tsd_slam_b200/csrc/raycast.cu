@@ -188,7 +188,17 @@ __device__ __forceinline__ void raycast_beam(const RayParams& rp, const int beam
       const bool nearEnd = !(idxMin + (double)(b + 31u) + 2.0 < idxMax);
       if(!nearEnd) return true;
       double mi = 0.0;
-      // replay the reference's counter up to this pass (uniform), keep this lane's value
+      // replay the reference's counter `i += 1.0` up to this pass (uniform), keep this lane's value.  Whole passes in
+      // closed form where that is exact (closed_form.cuh with r = 1: a ray that reaches the end of its range replayed
+      // 10 000 serial additions here, 40 us of the longest rays' 220), the rest one by one.
+      while(kExact + 32u <= b)
+      {
+        double dI, eI;
+        if(tsd_closed_form_pass(iExact, 1.0, &dI, &eI)) iExact = eI;
+        else
+          for(int k = 0; k < 32; k++) iExact += 1.0;
+        kExact += 32u;
+      }
       while(kExact < b) { iExact += 1.0; kExact++; }
       double ii = iExact;
 #pragma unroll 8
